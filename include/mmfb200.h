@@ -1,0 +1,78 @@
+/* mmfb200.h - C ABI of the B200-native multimodal-fusion block (libmmfb200.so).
+ *
+ * The reference (facebookresearch/mmf) has no FFI for this path: the boundary is the Python-level
+ * module contract of
+ *   BertSelfAttention/BertAttention/BertLayer/BertEncoder.forward   mmf/modules/hf_layers.py:161-355
+ *   BertBiAttention/BertBiOutput/BertConnectionLayer.forward         mmf/models/vilbert.py:388-556
+ *   BertVisioLinguisticEmbeddings.forward                            mmf/modules/embeddings.py:423-459
+ *   BertImageFeatureEmbeddings.forward                               mmf/models/vilbert.py:904-913
+ *   ModalEmbeddings.forward                                          mmf/models/mmbt.py:84-129
+ *   HuggingfaceEmbeddings.forward                                    mmf/models/transformers/backends/huggingface.py:131-159
+ * and their autograd backward (mmf/trainers/core/training_loop.py:211-213).  This header is what a
+ * binding for that path calls (mmf_b200/lib.py is the ctypes binding; INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated; bf16 = 16-bit bfloat, row-major, explicit
+ *     leading dimensions in ELEMENTS; the caller owns every buffer (outputs, saved-for-backward,
+ *     workspace); functions never allocate, never synchronise, enqueue on `stream` only
+ *   - return value: 0 = ok, otherwise an mmfb_status; mmfb_last_error() gives the message of the
+ *     last failure on the calling thread; no C++ exception crosses the ABI
+ *   - there is no CPU fallback: without an sm_100 device every compute entry point fails
+ */
+#ifndef MMFB200_H_
+#define MMFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mmfb_stream; /* cudaStream_t */
+
+typedef enum {
+  MMFB_OK = 0,
+  MMFB_ERR_ARG = 1,     /* bad shape / alignment / null pointer  -> ValueError in the binding */
+  MMFB_ERR_CUDA = 2,    /* CUDA runtime / driver failure         -> RuntimeError */
+  MMFB_ERR_DEVICE = 3   /* no sm_100 device                      -> RuntimeError */
+} mmfb_status;
+
+/* epilogues of mmfb_gemm */
+enum {
+  MMFB_EPI_BIAS = 0,            /* C = acc + bias                      (bias may be NULL)            */
+  MMFB_EPI_BIAS_GELU = 1,       /* C = acc + bias ; C2 = gelu_erf(C)   BertIntermediate              */
+  MMFB_EPI_BIAS_DROP_RESID = 2, /* C = dropout(acc + bias) + aux       BertSelfOutput/BertOutput pre-LN */
+  MMFB_EPI_GELU_BWD = 3,        /* C = acc * gelu_erf'(aux)            dgrad through BertIntermediate */
+  MMFB_EPI_ADD_AUX = 4,         /* C = acc + aux                       dgrad + residual gradient     */
+  MMFB_EPI_ATOMIC_F32 = 5       /* C(fp32) += acc                      split-K weight gradient       */
+};
+
+/* C[M,N] = epi( A[M,K] * B[N,K]^T ).  a_mn/b_mn = 0: operand stored [rows,K] (K contiguous);
+ * = 1: operand stored [K,rows] (rows contiguous), i.e. the transposed view of a row-major tensor. */
+typedef struct {
+  const void* A; int64_t lda; int a_mn;
+  const void* B; int64_t ldb; int b_mn;
+  void* C; int64_t ldc;          /* bf16 [M,N]; fp32 [M,N] for MMFB_EPI_ATOMIC_F32 */
+  void* C2;                      /* second bf16 output (MMFB_EPI_BIAS_GELU), same ldc */
+  const void* bias;              /* bf16 [N] or NULL */
+  const void* aux; int64_t ldaux;/* bf16 [M,N] residual / pre-activation or NULL */
+  const uint32_t* drop_mask; int64_t ldmask; float drop_scale; /* keep-bits [M, ldmask] words or NULL */
+  int M, N, K;
+  int epi;
+  int splits;                    /* split-K factor, MMFB_EPI_ATOMIC_F32 only (0/1 = none) */
+  int block_n;                   /* 0 = auto, else 128 or 256 */
+} mmfb_gemm_args;
+
+int mmfb_gemm(const mmfb_gemm_args* args, mmfb_stream stream);
+
+/* library / diagnostics */
+const char* mmfb_last_error(void);
+int mmfb_version(void);
+int mmfb_device_ok(void);          /* 1 if the current device is sm_100 */
+int64_t mmfb_launch_count(void);   /* number of kernels this library has launched in this process */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMFB200_H_ */

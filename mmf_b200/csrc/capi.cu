@@ -1,0 +1,127 @@
+// extern "C" surface of libmmfb200.so + host utilities (error state, device query, tensor maps).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "mmfb_internal.h"
+
+namespace mmfb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at first use through the runtime, so the library loads on a CPU-only host
+static encode_tiled_fn get_encode() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                 int box_outer) {
+  encode_tiled_fn enc = get_encode();
+  if (!enc) return set_error(MMFB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8))
+    return set_error(MMFB_ERR_ARG, "tensor map: base must be 16-byte aligned and ld a multiple of 8 (ptr=%p ld=%lld)",
+                     ptr, (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(MMFB_ERR_CUDA, "cuTensorMapEncodeTiled(2d inner=%lld outer=%lld ld=%lld box=%dx%d) failed: %d",
+                     (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer, (int)r);
+  return MMFB_OK;
+}
+
+int make_tmap_3d(CUtensorMap* map, const void* ptr, int64_t inner, int64_t d1, int64_t d2, int64_t ld1, int64_t ld2,
+                 int box_inner, int box_d1) {
+  encode_tiled_fn enc = get_encode();
+  if (!enc) return set_error(MMFB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld1 % 8) || (ld2 % 8))
+    return set_error(MMFB_ERR_ARG, "tensor map: base must be 16-byte aligned and strides multiples of 8");
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld1 * 2, (cuuint64_t)ld2 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_d1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MMFB_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return MMFB_OK;
+}
+
+static int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;  // not cached: a device may appear later (e.g. after CUDA_VISIBLE_DEVICES changes)
+    }
+    ok = (major == 10) ? 1 : 0;
+  }
+  return ok;
+}
+
+}  // namespace mmfb
+
+using namespace mmfb;
+
+#define MMFB_REQUIRE_DEVICE()                                                                              \
+  do {                                                                                                     \
+    if (!check_device())                                                                                   \
+      return set_error(MMFB_ERR_DEVICE, "libmmfb200 needs an sm_100 (B200) device; there is no CPU fallback"); \
+  } while (0)
+
+extern "C" {
+
+const char* mmfb_last_error(void) { return g_err; }
+int mmfb_version(void) { return 100; }
+int mmfb_device_ok(void) { return check_device(); }
+int64_t mmfb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mmfb_gemm(const mmfb_gemm_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_gemm: null args");
+  MMFB_REQUIRE_DEVICE();
+  return gemm(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

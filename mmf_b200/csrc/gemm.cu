@@ -1,0 +1,436 @@
+// tcgen05 GEMM family for the fusion block (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )       bf16 operands, fp32 accumulation in TMEM
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0     : TMA producer (one elected thread) - fills a STAGES-deep smem ring of 128x64 A tiles
+//                and BNx64 B tiles (SWIZZLE_128B), signalling `full[s]` with complete_tx bytes
+//   warp 1     : TMEM allocator + MMA issuer (one thread) - tcgen05.mma cta_group::1 kind::f16,
+//                128 x BN x 16 per instruction, accumulating into one of two TMEM stages;
+//                tcgen05.commit releases smem slots (`empty[s]`) and publishes the accumulator
+//                (`tmem_full[a]`)
+//   warps 2..5 : epilogue - tcgen05.ld (thread == accumulator row), fused elementwise epilogue,
+//                bf16 results staged in swizzled smem and written with TMA stores (or fp32
+//                vector reductions for the split-K weight-gradient GEMM)
+// Double-buffered accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Operand layouts: each of A and B may be K-major (row-major [rows, K]) or MN-major (row-major
+// [K, rows]); the latter is what the backward pass needs (dgrad reads W[out,in] as B[N=in,K=out],
+// wgrad reads dY[tokens,out] as A[M=out,K=tokens] and X[tokens,in] as B[N=in,K=tokens]) without
+// ever materialising a transpose in HBM.
+//
+// Reference ops this replaces (mmf = /root/reference): the nn.Linear calls in
+// mmf/modules/hf_layers.py:169-180 (Q,K,V), HF BertSelfOutput/BertIntermediate/BertOutput invoked at
+// hf_layers.py:248,289-290, mmf/models/vilbert.py:77-79,127,144-145,396-412,504-509 and their
+// autograd backward (mmf/trainers/core/training_loop.py:211-213).
+#include "common.cuh"
+#include "mmfb_internal.h"
+
+namespace mmfb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NUM_THREADS = 192;
+constexpr int STG_BYTES = 128 * 64 * 2;  // one 128-row x 64-col bf16 staging slice (SW128)
+
+struct GemmDev {
+  int M, N, K;
+  int splits;
+  float* c32;            // EPI_ATOMIC_F32 destination
+  int64_t ldc32;
+  const bf16* bias;      // [N] or null
+  const bf16* aux;       // residual / pre-activation, [M, ldaux]
+  int64_t ldaux;
+  const uint32_t* dmask; // dropout keep-bits, [M, ldmask] words (bit n%32 of word n/32), or null
+  int64_t ldmask;
+  float dscale;          // 1/(1-p)
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STG_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, GemmDev p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * STG_BYTES);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  const int units = tiles_m * tiles_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI != EPI_ATOMIC_F32) tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u % p.splits;
+        const int t = u / p.splits;
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full[s], C::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int pnl = 0; pnl < BM / 64; ++pnl) tma_load_2d(sa + pnl * 8192, &tmA, &full[s], m0 + pnl * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int pnl = 0; pnl < BN / 64; ++pnl) tma_load_2d(sb + pnl * 8192, &tmB, &full[s], n0 + pnl * 64, kb * BK);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u % p.splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = A_MN ? umma_desc_sw128(sa + kk * 2048, 8192, 1024) : umma_desc_sw128(sa + kk * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024) : umma_desc_sw128(sb + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;    // accumulator row inside the tile
+    const bool store_thread = (threadIdx.x == 64);
+    int as = 0;
+    uint32_t aph = 0;
+    int sbuf = 0;  // staging buffer toggle
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int t = u / p.splits;
+      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+
+      if (EPI == EPI_ATOMIC_F32) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int n = n0 + c * 32;
+          if (row_ok) {
+            float* dst = p.c32 + static_cast<int64_t>(m) * p.ldc32 + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n + j < p.N) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                             "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                             "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      } else {
+#pragma unroll 1
+        for (int sl = 0; sl < BN / 64; ++sl) {  // 64-column slices
+          // the staging buffer we are about to overwrite must have been drained by its TMA store
+          if (store_thread) {
+            if (EPI == EPI_BIAS_GELU) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          named_bar_sync(1, 128);
+          uint8_t* buf = stg + (EPI == EPI_BIAS_GELU ? 0 : sbuf) * STG_BYTES;
+          uint8_t* buf2 = stg + STG_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(t_row + sl * 64 + h * 32, r);
+            tmem_ld_wait();
+            if (sl == BN / 64 - 1 && h == 1) {
+              // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(&tempty[as]);
+            }
+            const int n = n0 + sl * 64 + h * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RESID) {
+              if (p.bias != nullptr && n < p.N) {
+                const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (n + q * 8 < p.N) {
+                    uint4 b = __ldg(bp + q);
+                    float2 f;
+                    f = unpack_bf16x2(b.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+                    f = unpack_bf16x2(b.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+                    f = unpack_bf16x2(b.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+                    f = unpack_bf16x2(b.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+                  }
+                }
+              }
+            }
+            if (EPI == EPI_BIAS_DROP_RESID) {
+              if (p.dmask != nullptr && row_ok && n < p.N) {
+                const uint32_t bits = __ldg(p.dmask + static_cast<int64_t>(m) * p.ldmask + (n >> 5));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * p.dscale : 0.0f;
+              }
+            }
+            if (EPI == EPI_BIAS_DROP_RESID || EPI == EPI_GELU_BWD || EPI == EPI_ADD_AUX) {
+              if (p.aux != nullptr && row_ok && n < p.N) {
+                const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(m) * p.ldaux + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (n + q * 8 < p.N) {
+                    uint4 a = __ldg(ap + q);
+                    float x[8];
+                    float2 f;
+                    f = unpack_bf16x2(a.x); x[0] = f.x; x[1] = f.y;
+                    f = unpack_bf16x2(a.y); x[2] = f.x; x[3] = f.y;
+                    f = unpack_bf16x2(a.z); x[4] = f.x; x[5] = f.y;
+                    f = unpack_bf16x2(a.w); x[6] = f.x; x[7] = f.y;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      if (EPI == EPI_GELU_BWD) v[q * 8 + e] *= gelu_erf_grad(x[e]);
+                      else v[q * 8 + e] += x[e];
+                    }
+                  }
+                }
+              }
+            }
+            // write this thread's 32 columns (64 bytes = four 16-byte chunks) into the swizzled slice
+            uint8_t* rowp = buf + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = (h * 4 + q) ^ (row & 7);
+              uint4 o;
+              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
+            }
+            if (EPI == EPI_BIAS_GELU) {
+              uint8_t* rowp2 = buf2 + row * 128;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int chunk = (h * 4 + q) ^ (row & 7);
+                uint4 o;
+                o.x = pack_bf16x2(gelu_erf(v[q * 8 + 0]), gelu_erf(v[q * 8 + 1]));
+                o.y = pack_bf16x2(gelu_erf(v[q * 8 + 2]), gelu_erf(v[q * 8 + 3]));
+                o.z = pack_bf16x2(gelu_erf(v[q * 8 + 4]), gelu_erf(v[q * 8 + 5]));
+                o.w = pack_bf16x2(gelu_erf(v[q * 8 + 6]), gelu_erf(v[q * 8 + 7]));
+                *reinterpret_cast<uint4*>(rowp2 + chunk * 16) = o;
+              }
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (store_thread) {
+            const int nn = n0 + sl * 64;
+            if (nn < p.N) {
+              tma_store_2d(&tmC, buf, nn, m0);
+              if (EPI == EPI_BIAS_GELU) tma_store_2d(&tmC2, buf2, nn, m0);
+            }
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+    if (store_thread) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA, tmB, tmC, tmC2;
+  // operand maps: K-major -> tensor [rows, K] (inner = K), box {64, rows_per_tile}
+  //               MN-major -> tensor [K, rows] (inner = rows), box {64, 64}
+  int rc;
+  if (!A_MN) rc = make_tmap_2d(&tmA, a.A, a.K, a.M, a.lda, 64, BM);
+  else rc = make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, 64, 64);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_2d(&tmB, a.B, a.K, a.N, a.ldb, 64, BN);
+  else rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, 64, 64);
+  if (rc) return rc;
+  if (EPI != EPI_ATOMIC_F32) {
+    rc = make_tmap_2d(&tmC, a.C, a.N, a.M, a.ldc, 64, BM);
+    if (rc) return rc;
+    if (EPI == EPI_BIAS_GELU) {
+      rc = make_tmap_2d(&tmC2, a.C2, a.N, a.M, a.ldc, 64, BM);
+      if (rc) return rc;
+    } else {
+      tmC2 = tmC;
+    }
+  } else {
+    tmC = tmA;
+    tmC2 = tmA;
+  }
+  GemmDev p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.splits = (EPI == EPI_ATOMIC_F32 && a.splits > 0) ? a.splits : 1;
+  const int kb_total = (a.K + BK - 1) / BK;
+  if (p.splits > kb_total) p.splits = kb_total;
+  // every split must own at least one k-block
+  while (p.splits > 1 && ((kb_total + p.splits - 1) / p.splits) * (p.splits - 1) >= kb_total) --p.splits;
+  p.c32 = reinterpret_cast<float*>(a.C);
+  p.ldc32 = a.ldc;
+  p.bias = reinterpret_cast<const bf16*>(a.bias);
+  p.aux = reinterpret_cast<const bf16*>(a.aux);
+  p.ldaux = a.ldaux;
+  p.dmask = a.drop_mask;
+  p.ldmask = a.ldmask;
+  p.dscale = a.drop_scale;
+
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * p.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return MMFB_OK;
+}
+
+template <int BN>
+static int dispatch(const mmfb_gemm_args& a, cudaStream_t s) {
+  const int key = (a.a_mn ? 100 : 0) + (a.b_mn ? 10 : 0) + a.epi;
+  switch (key) {
+    case 0 + EPI_BIAS: return launch<BN, false, false, EPI_BIAS>(a, s);
+    case 0 + EPI_BIAS_GELU: return launch<BN, false, false, EPI_BIAS_GELU>(a, s);
+    case 0 + EPI_BIAS_DROP_RESID: return launch<BN, false, false, EPI_BIAS_DROP_RESID>(a, s);
+    case 10 + EPI_BIAS: return launch<BN, false, true, EPI_BIAS>(a, s);
+    case 10 + EPI_GELU_BWD: return launch<BN, false, true, EPI_GELU_BWD>(a, s);
+    case 10 + EPI_ADD_AUX: return launch<BN, false, true, EPI_ADD_AUX>(a, s);
+    case 110 + EPI_ATOMIC_F32: return launch<BN, true, true, EPI_ATOMIC_F32>(a, s);
+    // test-only layout combinations (kept small: plain store epilogue)
+    case 100 + EPI_BIAS: return launch<BN, true, false, EPI_BIAS>(a, s);
+    case 110 + EPI_BIAS: return launch<BN, true, true, EPI_BIAS>(a, s);
+    default:
+      return set_error(MMFB_ERR_ARG, "gemm: unsupported (a_mn=%d, b_mn=%d, epi=%d)", a.a_mn, a.b_mn, a.epi);
+  }
+}
+
+int gemm(const mmfb_gemm_args& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(MMFB_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
+  if ((a.N % 8) || (a.K % 8) || (a.M % 8 && (a.a_mn)))
+    return set_error(MMFB_ERR_ARG, "gemm: N, K (and M for MN-major A) must be multiples of 8 (got %d,%d,%d)", a.M, a.N, a.K);
+  if ((a.lda % 8) || (a.ldb % 8) || (a.epi != EPI_ATOMIC_F32 && (a.ldc % 8)))
+    return set_error(MMFB_ERR_ARG, "gemm: leading dimensions must be multiples of 8 elements");
+  const int bn = a.block_n > 0 ? a.block_n : (a.N >= 256 ? 256 : 128);
+  if (bn == 256) return dispatch<256>(a, stream);
+  if (bn == 128) return dispatch<128>(a, stream);
+  return set_error(MMFB_ERR_ARG, "gemm: block_n must be 128 or 256");
+}
+
+}  // namespace mmfb

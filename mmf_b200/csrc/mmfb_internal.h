@@ -1,0 +1,35 @@
+// Internal host-side declarations shared by the translation units of libmmfb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mmfb200.h"
+
+namespace mmfb {
+
+enum {
+  EPI_BIAS = MMFB_EPI_BIAS,
+  EPI_BIAS_GELU = MMFB_EPI_BIAS_GELU,
+  EPI_BIAS_DROP_RESID = MMFB_EPI_BIAS_DROP_RESID,
+  EPI_GELU_BWD = MMFB_EPI_GELU_BWD,
+  EPI_ADD_AUX = MMFB_EPI_ADD_AUX,
+  EPI_ATOMIC_F32 = MMFB_EPI_ATOMIC_F32
+};
+
+// records a thread-local error message and returns `code`
+int set_error(int code, const char* fmt, ...);
+int num_sms();
+void count_launch(int n = 1);
+
+// bf16 2-D tensor map: tensor [outer, inner] with row stride `ld` elements, box {box_inner, box_outer},
+// SWIZZLE_128B (box_inner must be 64), out-of-bounds elements read as zero / are not written.
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                 int box_outer);
+// bf16 3-D tensor map: tensor [d2, d1, inner] with strides ld1 (rows) and ld2 (batches) in elements
+int make_tmap_3d(CUtensorMap* map, const void* ptr, int64_t inner, int64_t d1, int64_t d2, int64_t ld1,
+                 int64_t ld2, int box_inner, int box_d1);
+
+int gemm(const mmfb_gemm_args& a, cudaStream_t stream);
+
+}  // namespace mmfb

@@ -1,0 +1,95 @@
+"""ctypes binding of libmmfb200.so (the C ABI declared in include/mmfb200.h).
+
+The library is loaded eagerly and loudly: if it is missing it is built in-tree with nvcc; if that is
+impossible an ImportError is raised.  There is no Python/CPU fallback for any compute entry point.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "csrc", "libmmfb200.so")
+
+MMFB_OK, MMFB_ERR_ARG, MMFB_ERR_CUDA, MMFB_ERR_DEVICE = 0, 1, 2, 3
+
+EPI_BIAS = 0
+EPI_BIAS_GELU = 1
+EPI_BIAS_DROP_RESID = 2
+EPI_GELU_BWD = 3
+EPI_ADD_AUX = 4
+EPI_ATOMIC_F32 = 5
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("A", ctypes.c_void_p), ("lda", ctypes.c_int64), ("a_mn", ctypes.c_int),
+        ("B", ctypes.c_void_p), ("ldb", ctypes.c_int64), ("b_mn", ctypes.c_int),
+        ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
+        ("C2", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+        ("aux", ctypes.c_void_p), ("ldaux", ctypes.c_int64),
+        ("drop_mask", ctypes.c_void_p), ("ldmask", ctypes.c_int64), ("drop_scale", ctypes.c_float),
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("epi", ctypes.c_int),
+        ("splits", ctypes.c_int),
+        ("block_n", ctypes.c_int),
+    ]
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        try:
+            from .csrc.build import build
+            build()
+        except Exception as e:  # pragma: no cover - build environment problem
+            raise ImportError(
+                "libmmfb200.so is missing and could not be built (%s); run `python -m mmf_b200.csrc.build`" % (e,)
+            )
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.mmfb_last_error.restype = ctypes.c_char_p
+    lib.mmfb_launch_count.restype = ctypes.c_int64
+    return lib
+
+
+LIB = _load()
+LIB_PATH = _LIB_PATH
+
+
+def last_error():
+    return LIB.mmfb_last_error().decode("utf-8", "replace")
+
+
+def check(status):
+    """Turns an mmfb_status into the exception the reference path would raise."""
+    if status == MMFB_OK:
+        return
+    msg = last_error()
+    if status == MMFB_ERR_ARG:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def launch_count():
+    return int(LIB.mmfb_launch_count())
+
+
+def device_ok():
+    return bool(LIB.mmfb_device_ok())
+
+
+def header_symbols():
+    """Function names declared in include/mmfb200.h (used by the export test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "mmfb200.h")
+    with open(hdr) as fh:
+        txt = fh.read()
+    return sorted(set(re.findall(r"\b(mmfb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
