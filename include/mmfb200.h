@@ -66,6 +66,34 @@ typedef struct {
 
 int mmfb_gemm(const mmfb_gemm_args* args, mmfb_stream stream);
 
+/* Fused multi-head attention core (everything between the Q/K/V projections and the output projection):
+ *   ctx = dropout(softmax(Q K^T / sqrt(d) + mask)) V        BertSelfAttentionJit.forward hf_layers.py:182-210,
+ *   BertBiAttention.forward vilbert.py:421-461 (cross: q from one stream, k/v from the other).
+ * q [B*Sq, ldq], k/v [B*Skv, ld*]: bf16, head h in columns [h*head_dim, (h+1)*head_dim); usually three
+ * column slices of one fused projection buffer.  mask: additive fp32 [B, Skv] (the reference's
+ * [B,1,1,Skv] tensor) or NULL.  lse2 [B, heads, Sq] fp32 receives the log2-domain row log-sum-exp
+ * (saved for backward).  drop_mask: keep bits [B, heads, Sq, ceil(Skv/32)] (bit kv%32) or NULL.
+ * Limits: head_dim 64 or 128; Skv <= 384 (d=64) / 256 (d=128) - MMF's path has S <= 324. */
+typedef struct {
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  const float* mask;
+  void* ctx; int64_t ldo;            /* bf16 [B*Sq, ldo]: output of fwd, input of bwd */
+  float* lse2;
+  const uint32_t* drop_mask; float drop_scale;
+  /* backward only */
+  const void* dctx; int64_t ld_dctx; /* bf16 [B*Sq, ld_dctx] */
+  float* delta;                      /* fp32 scratch [B, heads, Sq] */
+  void* dq; int64_t ld_dq;           /* bf16 outputs, same head layout as q/k/v */
+  void* dk; int64_t ld_dk;
+  void* dv; int64_t ld_dv;
+  int B, heads, Sq, Skv, head_dim;
+} mmfb_attn_args;
+
+int mmfb_attention_fwd(const mmfb_attn_args* args, mmfb_stream stream);
+int mmfb_attention_bwd(const mmfb_attn_args* args, mmfb_stream stream);
+
 /* library / diagnostics */
 const char* mmfb_last_error(void);
 int mmfb_version(void);

@@ -1,0 +1,642 @@
+// Fused multi-head (self / cross) attention for the fusion block, forward and backward (sm_100a).
+//
+// Reference semantics (mmf/modules/hf_layers.py:182-210; mmf/models/vilbert.py:81-103, 421-461):
+//     scores = Q K^T / sqrt(d) + M        M = additive mask [B, Skv] (0 / -10000), NOT -inf
+//     probs  = dropout(softmax(scores))   a fully masked row becomes uniform, never NaN
+//     ctx    = probs V, heads merged back to [B, Sq, h*d]
+//
+// Forward: one CTA per (128-query tile, head, batch).  TMA stages Q, K, V head slices straight out of
+// the fused [tokens, 3*H] projection buffer (3-D tensor maps: sequence tails are zero-filled, never read
+// from the next sample).  The whole score row block S = Q K^T [128 x Skv] lives in TMEM (Skv <= 384),
+// so softmax is a single exact pass: thread r owns TMEM lane r == query row r (no shuffles), exp2 with
+// the 1/sqrt(d) scale folded into log2(e).  P is written to shared memory as the K-major A operand of
+// the second tcgen05 contraction O = P V (V is consumed MN-major from the same TMA tile), P reusing the
+// bytes of Q and K.  Row log-sum-exp (log2 domain) is saved for the backward.
+//
+// Backward: the probabilities are recomputed from Q, K and the saved row statistics (nothing of size
+// S x S ever touches HBM).  Two launches of ONE templated kernel:
+//   ROWS_ARE_Q = true : CTA owns 128 query rows, loops over key blocks,   dQ  = scale * dS K
+//   ROWS_ARE_Q = false: CTA owns 128 key rows,   loops over query blocks, dK^T-free formulation
+//                       S'^T = K Q^T, dP'^T = V dO^T,  dV = P^T dO,  dK = scale * dS^T Q
+// In both, thread r owns row r of the 128x128 S'/dP' tiles in TMEM, writes P'/dS' (bf16) to shared
+// memory as K-major A operands and the looped operand tile is re-read MN-major as the B operand of
+// the accumulation MMA - no transposes, no atomics, deterministic.
+#include "common.cuh"
+#include "mmfb_internal.h"
+
+namespace mmfb {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ----------------------------------------------------------------------------------------------
+// forward
+// ----------------------------------------------------------------------------------------------
+struct AttnFwdDev {
+  int B, H, Sq, Skv;
+  const float* mask;      // [B, Skv] additive, or null
+  bf16* ctx;              // [B*Sq, ldo]
+  int64_t ldo;
+  float* lse2;            // [B, H, Sq]  log2-domain log-sum-exp of the scaled+masked scores
+  const uint32_t* dmask;  // keep bits [B, H, Sq, W] (bit kv%32 of word kv/32) or null
+  int W;
+  float dscale;           // 1/(1-p)
+  float scale2;           // log2(e)/sqrt(d)
+};
+
+template <int D>
+__global__ void __launch_bounds__(160, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, AttnFwdDev p) {
+  constexpr int DC = D / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int SK = (p.Skv + 63) & ~63;
+  const int NB = SK / 64;
+  const int r0_bytes = max(NB * 16384, DC * 16384 + DC * SK * 128);
+  uint8_t* sQ = smem;                      // DC x [128 x 128B]
+  uint8_t* sK = smem + DC * 16384;         // DC x [SK x 128B]
+  uint8_t* sP = smem;                      // NB x [128 x 128B]   (aliases Q and K once S is complete)
+  uint8_t* sV = smem + r0_bytes;           // DC x [SK x 128B]
+  float* sMask = reinterpret_cast<float*>(sV + DC * SK * 128);  // [SK]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + SK);
+  uint64_t* qk_full = bars;
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_ready = bars + 2;
+  uint64_t* p_ready = bars + 3;
+  uint64_t* o_ready = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * 128;
+  const int need_cols = SK > D ? SK : D;  // S occupies SK columns, O later reuses columns [0, D)
+  const uint32_t tmem_cols = need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_init(qk_full, 1);
+      mbar_init(v_full, 1);
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, 128);
+      mbar_init(o_ready, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  } else {
+    for (int i = threadIdx.x; i < SK; i += 128)
+      sMask[i] = (i < p.Skv && p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads ----
+      mbar_expect_tx(qk_full, DC * 16384 + DC * SK * 128);
+      for (int c = 0; c < DC; ++c) tma_load_3d(sQ + c * 16384, &tmQ, qk_full, h * D + c * 64, q0, b);
+      for (int c = 0; c < DC; ++c)
+        for (int rb = 0; rb < NB; ++rb)
+          tma_load_3d(sK + c * SK * 128 + rb * 8192, &tmK, qk_full, h * D + c * 64, rb * 64, b);
+      mbar_expect_tx(v_full, DC * SK * 128);
+      for (int c = 0; c < DC; ++c)
+        for (int rb = 0; rb < NB; ++rb)
+          tma_load_3d(sV + c * SK * 128 + rb * 8192, &tmV, v_full, h * D + c * 64, rb * 64, b);
+      // ---- S = Q K^T ----
+      mbar_wait(qk_full, 0);
+      tc_fence_after();
+      for (int n0 = 0; n0 < SK; n0 += 256) {
+        const int nn = min(256, SK - n0);
+        const uint32_t idesc = umma_idesc_bf16(128, nn, false, false);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(smem_u32(sQ) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t db =
+              umma_desc_sw128(smem_u32(sK) + (kk >> 2) * SK * 128 + n0 * 128 + (kk & 3) * 32, 16, 1024);
+          umma_bf16(tmem_base + n0, da, db, idesc, kk > 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(s_ready);
+      // ---- O = P V ----
+      mbar_wait(p_ready, 0);
+      mbar_wait(v_full, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+      const int ksteps = (p.Skv + 15) / 16;
+      for (int kk = 0; kk < ksteps; ++kk) {
+        const uint64_t da = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+        const uint64_t db = umma_desc_sw128(smem_u32(sV) + kk * 2048, SK * 128, 1024);
+        umma_bf16(tmem_base, da, db, idesc_o, kk > 0 ? 1u : 0u);
+      }
+      umma_commit(o_ready);
+    }
+  } else {
+    // ------------------------------ softmax + epilogue (thread == query row) ------------------------------
+    const int row = threadIdx.x;
+    const int q = q0 + row;
+    const bool valid = q < p.Sq;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int nch = (p.Skv + 31) / 32;
+    mbar_wait(s_ready, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      uint32_t r[32];
+      tmem_ld32(trow + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        const float t = fmaf(__uint_as_float(r[j]), p.scale2, sMask[col < SK ? col : 0]);
+        if (col < p.Skv) mx = fmaxf(mx, t);
+      }
+    }
+    float sum = 0.0f;
+    const uint32_t* dm = (p.dmask != nullptr && valid)
+                             ? p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W
+                             : nullptr;
+    uint8_t* prow = sP + row * 128;
+#pragma unroll 1
+    for (int c = 0; c < SK / 32; ++c) {
+      float e[32];
+      if (c < nch) {
+        uint32_t r[32];
+        tmem_ld32(trow + c * 32, r);
+        tmem_ld_wait();
+        const uint32_t bits = dm ? __ldg(dm + c) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c * 32 + j;
+          const float t = fmaf(__uint_as_float(r[j]), p.scale2, sMask[col < SK ? col : 0]);
+          const float ev = (col < p.Skv) ? exp2f(t - mx) : 0.0f;
+          sum += ev;
+          e[j] = ((bits >> j) & 1u) ? ev : 0.0f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) e[j] = 0.0f;
+      }
+      uint8_t* chunk_base = prow + (c >> 1) * 16384;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
+        uint4 o;
+        o.x = pack_bf16x2(e[qd * 8 + 0], e[qd * 8 + 1]);
+        o.y = pack_bf16x2(e[qd * 8 + 2], e[qd * 8 + 3]);
+        o.z = pack_bf16x2(e[qd * 8 + 4], e[qd * 8 + 5]);
+        o.w = pack_bf16x2(e[qd * 8 + 6], e[qd * 8 + 7]);
+        *reinterpret_cast<uint4*>(chunk_base + chunk * 16) = o;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(p_ready);
+    if (valid) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = mx + log2f(sum);
+    const float inv = p.dscale / sum;
+    mbar_wait(o_ready, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(trow + c * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<int64_t>(b) * p.Sq + q) * p.ldo + h * D + c * 32);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[qd * 8 + 0]) * inv, __uint_as_float(r[qd * 8 + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(r[qd * 8 + 2]) * inv, __uint_as_float(r[qd * 8 + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(r[qd * 8 + 4]) * inv, __uint_as_float(r[qd * 8 + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * inv, __uint_as_float(r[qd * 8 + 7]) * inv);
+          dst[qd] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// backward
+// ----------------------------------------------------------------------------------------------
+struct AttnBwdDev {
+  int B, H, Sq, Skv;
+  const float* mask;      // [B, Skv] additive or null
+  const float* lse2;      // [B, H, Sq]
+  const float* delta;     // [B, H, Sq]  rowsum(dO * O)
+  const uint32_t* dmask;  // [B, H, Sq, W] or null
+  int W;
+  float dscale, scale2, scale;
+  bf16* out0;             // ROWS_ARE_Q: dQ ; else dK      [B*S_rows, ld0], head at col h*D
+  int64_t ld0;
+  bf16* out1;             // else-mode only: dV
+  int64_t ld1;
+};
+
+// rows: the operand pair that stays resident (R, Rg); cols: the looped pair (C, Cg)
+//   ROWS_ARE_Q :  R = Q_i, Rg = dO_i ; C = K_j, Cg = V_j ;  out0 = dQ_i = scale * sum_j dS' C
+//   !ROWS_ARE_Q:  R = K_j, Rg = V_j  ; C = Q_i, Cg = dO_i;  out0 = dK_j = scale * sum_i dS' C ; out1 = dV_j = sum_i P' Cg
+template <int D, bool ROWS_ARE_Q>
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRg,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCg, AttnBwdDev p) {
+  constexpr int DC = D / 64;
+  constexpr int TILE = DC * 16384;  // one [128 x D] bf16 operand tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR = smem;
+  uint8_t* sRg = sR + TILE;
+  uint8_t* sC = sRg + TILE;
+  uint8_t* sCg = sC + TILE;
+  uint8_t* sP = sCg + TILE;       // [128 x 128] bf16, 2 chunks of [128 x 128B]
+  uint8_t* sDS = sP + 32768;
+  float* sCol = reinterpret_cast<float*>(sDS + 32768);   // [2 buffers][2 stats][128] per-column statistics
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 512);
+  uint64_t* r_full = bars;
+  uint64_t* c_full = bars + 1;
+  uint64_t* s_ready = bars + 2;
+  uint64_t* p_ready = bars + 3;
+  uint64_t* acc_done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = rt * 128;
+  const int S_rows = ROWS_ARE_Q ? p.Sq : p.Skv;
+  const int S_cols = ROWS_ARE_Q ? p.Skv : p.Sq;
+  const int n_it = (S_cols + 127) / 128;
+  constexpr uint32_t TMEM_COLS = (256 + (ROWS_ARE_Q ? D : 2 * D)) <= 256 ? 256 : 512;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_O0 = 256, COL_O1 = 256 + D;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmRg);
+      tma_prefetch_desc(&tmC);
+      tma_prefetch_desc(&tmCg);
+      mbar_init(r_full, 1);
+      mbar_init(c_full, 1);
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, 128);
+      mbar_init(acc_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, 2 * TILE);
+      for (int c = 0; c < DC; ++c) {
+        tma_load_3d(sR + c * 16384, &tmR, r_full, h * D + c * 64, row0, b);
+        tma_load_3d(sRg + c * 16384, &tmRg, r_full, h * D + c * 64, row0, b);
+      }
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+      for (int it = 0; it < n_it; ++it) {
+        if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous accumulation MMAs have consumed C/Cg and P/dS
+        mbar_expect_tx(c_full, 2 * TILE);
+        for (int c = 0; c < DC; ++c) {
+          tma_load_3d(sC + c * 16384, &tmC, c_full, h * D + c * 64, it * 128, b);
+          tma_load_3d(sCg + c * 16384, &tmCg, c_full, h * D + c * 64, it * 128, b);
+        }
+        if (it == 0) mbar_wait(r_full, 0);
+        mbar_wait(c_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_bf16(tmem_base + COL_S, umma_desc_sw128(smem_u32(sR) + off, 16, 1024),
+                    umma_desc_sw128(smem_u32(sC) + off, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_bf16(tmem_base + COL_DP, umma_desc_sw128(smem_u32(sRg) + off, 16, 1024),
+                    umma_desc_sw128(smem_u32(sCg) + off, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(s_ready);
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        // accumulate over the 128 looped positions (K dimension of these MMAs), B operands MN-major
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_bf16(tmem_base + COL_O0, umma_desc_sw128(smem_u32(sDS) + aoff, 16, 1024),
+                    umma_desc_sw128(smem_u32(sC) + kk * 2048, 16384, 1024), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (!ROWS_ARE_Q) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16(tmem_base + COL_O1, umma_desc_sw128(smem_u32(sP) + aoff, 16, 1024),
+                      umma_desc_sw128(smem_u32(sCg) + kk * 2048, 16384, 1024), idesc_o,
+                      (it > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(acc_done);
+      }
+    }
+  } else {
+    const int row = threadIdx.x;
+    const int ridx = row0 + row;              // q (ROWS_ARE_Q) or kv index
+    const bool rvalid = ridx < S_rows;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+    // per-row scalars
+    float rowA = 0.0f, rowB = 0.0f;
+    if (ROWS_ARE_Q) {
+      if (rvalid) { rowA = p.lse2[bh * p.Sq + ridx]; rowB = p.delta[bh * p.Sq + ridx]; }
+    } else {
+      rowA = (rvalid && p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + ridx] * LOG2E : 0.0f;
+    }
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const int col0 = it * 128;
+      // per-column stats for this block; double-buffered: a thread can run at most one iteration ahead of the
+      // slowest (the bar.sync below), so buffer it&1 is never rewritten while still being read
+      float* sColA = sCol + (it & 1) * 256;
+      float* sColB = sColA + 128;
+      {
+        const int cidx = col0 + row;
+        float a = 0.0f, bb = 0.0f;
+        if (cidx < S_cols) {
+          if (ROWS_ARE_Q) {
+            a = (p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + cidx] * LOG2E : 0.0f;
+          } else {
+            a = p.lse2[bh * p.Sq + cidx];
+            bb = p.delta[bh * p.Sq + cidx];
+          }
+        }
+        sColA[row] = a;
+        sColB[row] = bb;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // P/dS smem free again
+      mbar_wait(s_ready, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(trow + COL_S + c * 32, rs);
+        tmem_ld32(trow + COL_DP + c * 32, rd);
+        tmem_ld_wait();
+        float pv[32], ds[32];
+        uint32_t bits = 0xFFFFFFFFu;
+        if (ROWS_ARE_Q && p.dmask != nullptr && rvalid) {
+          const int w = (col0 >> 5) + c;
+          if (w < p.W) bits = __ldg(p.dmask + (bh * p.Sq + ridx) * p.W + w);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int cl = c * 32 + j;
+          const int cidx = col0 + cl;
+          float t, l2, dl;
+          if (ROWS_ARE_Q) {
+            t = fmaf(__uint_as_float(rs[j]), p.scale2, sColA[cl]);
+            l2 = rowA; dl = rowB;
+          } else {
+            t = fmaf(__uint_as_float(rs[j]), p.scale2, rowA);
+            l2 = sColA[cl]; dl = sColB[cl];
+          }
+          float pr = (cidx < S_cols && rvalid) ? exp2f(t - l2) : 0.0f;
+          float keep = 1.0f;
+          if (p.dmask != nullptr) {
+            if (ROWS_ARE_Q) {
+              keep = ((bits >> j) & 1u) ? p.dscale : 0.0f;
+            } else if (cidx < S_cols && rvalid) {
+              const uint32_t wv = __ldg(p.dmask + (bh * p.Sq + cidx) * p.W + (ridx >> 5));
+              keep = ((wv >> (ridx & 31)) & 1u) ? p.dscale : 0.0f;
+            }
+          }
+          const float dp = __uint_as_float(rd[j]) * keep;
+          ds[j] = pr * (dp - dl);
+          pv[j] = pr * keep;
+        }
+        uint8_t* dsrow = sDS + (c >> 1) * 16384 + row * 128;
+        uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
+          uint4 o;
+          o.x = pack_bf16x2(ds[qd * 8 + 0], ds[qd * 8 + 1]);
+          o.y = pack_bf16x2(ds[qd * 8 + 2], ds[qd * 8 + 3]);
+          o.z = pack_bf16x2(ds[qd * 8 + 4], ds[qd * 8 + 5]);
+          o.w = pack_bf16x2(ds[qd * 8 + 6], ds[qd * 8 + 7]);
+          *reinterpret_cast<uint4*>(dsrow + chunk * 16) = o;
+          if (!ROWS_ARE_Q) {
+            o.x = pack_bf16x2(pv[qd * 8 + 0], pv[qd * 8 + 1]);
+            o.y = pack_bf16x2(pv[qd * 8 + 2], pv[qd * 8 + 3]);
+            o.z = pack_bf16x2(pv[qd * 8 + 4], pv[qd * 8 + 5]);
+            o.w = pack_bf16x2(pv[qd * 8 + 6], pv[qd * 8 + 7]);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue ----
+    mbar_wait(acc_done, (n_it - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int o = 0; o < (ROWS_ARE_Q ? 1 : 2); ++o) {
+      bf16* outp = (o == 0) ? p.out0 : p.out1;
+      const int64_t ld = (o == 0) ? p.ld0 : p.ld1;
+      const float mul = (o == 0) ? p.scale : 1.0f;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(trow + (o == 0 ? COL_O0 : COL_O1) + c * 32, r);
+        tmem_ld_wait();
+        if (rvalid) {
+          uint4* dst = reinterpret_cast<uint4*>(outp + (static_cast<int64_t>(b) * S_rows + ridx) * ld + h * D + c * 32);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[qd * 8 + 0]) * mul, __uint_as_float(r[qd * 8 + 1]) * mul);
+            v.y = pack_bf16x2(__uint_as_float(r[qd * 8 + 2]) * mul, __uint_as_float(r[qd * 8 + 3]) * mul);
+            v.z = pack_bf16x2(__uint_as_float(r[qd * 8 + 4]) * mul, __uint_as_float(r[qd * 8 + 5]) * mul);
+            v.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * mul, __uint_as_float(r[qd * 8 + 7]) * mul);
+            dst[qd] = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d] : one warp per (token, head)
+__global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
+                                  int64_t ld_o, float* __restrict__ delta, int B, int H, int Sq, int D) {
+  const int64_t gw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = static_cast<int64_t>(B) * Sq * H;
+  if (gw >= total) return;
+  const int h = gw % H;
+  const int64_t tok = gw / H;  // b*Sq + q
+  const bf16* a = dO + tok * ld_do + h * D;
+  const bf16* o = O + tok * ld_o + h * D;
+  float s = 0.0f;
+  for (int i = lane * 2; i < D; i += 64) {
+    const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
+    const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + i));
+    s += x.x * y.x + x.y * y.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int64_t bq = tok;  // b*Sq + q
+    const int b = bq / Sq, q = bq % Sq;
+    delta[(static_cast<int64_t>(b) * H + h) * Sq + q] = s;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------------
+static int check_attn_common(const mmfb_attn_args& a, const char* who) {
+  if (a.B <= 0 || a.heads <= 0 || a.Sq <= 0 || a.Skv <= 0) return set_error(MMFB_ERR_ARG, "%s: empty problem", who);
+  if (a.head_dim != 64 && a.head_dim != 128)
+    return set_error(MMFB_ERR_ARG, "%s: head_dim must be 64 or 128 (got %d)", who, a.head_dim);
+  const int max_kv = a.head_dim == 64 ? 384 : 256;
+  if (a.Skv > max_kv)
+    return set_error(MMFB_ERR_ARG, "%s: Skv=%d exceeds the single-pass limit %d for head_dim %d", who, a.Skv, max_kv,
+                     a.head_dim);
+  return MMFB_OK;
+}
+
+template <int D>
+static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
+  const int W = a.heads * D;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQ, a.q, W, a.Sq, a.B, a.ldq, a.ldq * a.Sq, 64, 128))) return rc;
+  if ((rc = make_tmap_3d(&tmK, a.k, W, a.Skv, a.B, a.ldk, a.ldk * a.Skv, 64, 64))) return rc;
+  if ((rc = make_tmap_3d(&tmV, a.v, W, a.Skv, a.B, a.ldv, a.ldv * a.Skv, 64, 64))) return rc;
+  constexpr int DC = D / 64;
+  const int SK = (a.Skv + 63) & ~63, NB = SK / 64;
+  const int r0 = NB * 16384 > DC * 16384 + DC * SK * 128 ? NB * 16384 : DC * 16384 + DC * SK * 128;
+  const int smem = r0 + DC * SK * 128 + SK * 4 + 128 + 1024;
+  AttnFwdDev p;
+  p.B = a.B; p.H = a.heads; p.Sq = a.Sq; p.Skv = a.Skv;
+  p.mask = a.mask;
+  p.ctx = reinterpret_cast<bf16*>(a.ctx); p.ldo = a.ldo;
+  p.lse2 = a.lse2;
+  p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
+  p.scale2 = LOG2E / sqrtf(static_cast<float>(D));
+  auto kern = attn_fwd_kernel<D>;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd smem attr (%d B): %s", smem, cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
+  kern<<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return MMFB_OK;
+}
+
+int attn_fwd(const mmfb_attn_args& a, cudaStream_t stream) {
+  int rc = check_attn_common(a, "attn_fwd");
+  if (rc) return rc;
+  if (!a.q || !a.k || !a.v || !a.ctx || !a.lse2) return set_error(MMFB_ERR_ARG, "attn_fwd: null pointer");
+  return a.head_dim == 64 ? attn_fwd_launch<64>(a, stream) : attn_fwd_launch<128>(a, stream);
+}
+
+template <int D>
+static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
+  const int W = a.heads * D;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQ, a.q, W, a.Sq, a.B, a.ldq, a.ldq * a.Sq, 64, 128))) return rc;
+  if ((rc = make_tmap_3d(&tmdO, a.dctx, W, a.Sq, a.B, a.ld_dctx, a.ld_dctx * a.Sq, 64, 128))) return rc;
+  if ((rc = make_tmap_3d(&tmK, a.k, W, a.Skv, a.B, a.ldk, a.ldk * a.Skv, 64, 128))) return rc;
+  if ((rc = make_tmap_3d(&tmV, a.v, W, a.Skv, a.B, a.ldv, a.ldv * a.Skv, 64, 128))) return rc;
+  // delta = rowsum(dO * O)
+  {
+    const int64_t warps = static_cast<int64_t>(a.B) * a.Sq * a.heads;
+    const int threads = 256;
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    attn_delta_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, a.delta, a.B,
+        a.heads, a.Sq, D);
+    count_launch();
+  }
+  constexpr int DC = D / 64;
+  const int smem = 4 * DC * 16384 + 2 * 32768 + 2048 + 128 + 1024;
+  AttnBwdDev p;
+  p.B = a.B; p.H = a.heads; p.Sq = a.Sq; p.Skv = a.Skv;
+  p.mask = a.mask; p.lse2 = a.lse2; p.delta = a.delta;
+  p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
+  p.scale = 1.0f / sqrtf(static_cast<float>(D));
+  p.scale2 = LOG2E * p.scale;
+  {
+    auto kern = attn_bwd_kernel<D, true>;
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(dq) smem attr: %s", cudaGetErrorString(e));
+      set = true;
+    }
+    p.out0 = reinterpret_cast<bf16*>(a.dq); p.ld0 = a.ld_dq; p.out1 = nullptr; p.ld1 = 0;
+    dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
+    kern<<<grid, 160, smem, stream>>>(tmQ, tmdO, tmK, tmV, p);
+    count_launch();
+  }
+  {
+    auto kern = attn_bwd_kernel<D, false>;
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(dkv) smem attr: %s", cudaGetErrorString(e));
+      set = true;
+    }
+    p.out0 = reinterpret_cast<bf16*>(a.dk); p.ld0 = a.ld_dk;
+    p.out1 = reinterpret_cast<bf16*>(a.dv); p.ld1 = a.ld_dv;
+    dim3 grid((a.Skv + 127) / 128, a.heads, a.B);
+    kern<<<grid, 160, smem, stream>>>(tmK, tmV, tmQ, tmdO, p);
+    count_launch();
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd launch: %s", cudaGetErrorString(e));
+  return MMFB_OK;
+}
+
+int attn_bwd(const mmfb_attn_args& a, cudaStream_t stream) {
+  int rc = check_attn_common(a, "attn_bwd");
+  if (rc) return rc;
+  if (!a.q || !a.k || !a.v || !a.ctx || !a.lse2 || !a.dctx || !a.delta || !a.dq || !a.dk || !a.dv)
+    return set_error(MMFB_ERR_ARG, "attn_bwd: null pointer");
+  return a.head_dim == 64 ? attn_bwd_launch<64>(a, stream) : attn_bwd_launch<128>(a, stream);
+}
+
+}  // namespace mmfb

@@ -124,4 +124,16 @@ int mmfb_gemm(const mmfb_gemm_args* args, mmfb_stream stream) {
   return gemm(*args, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mmfb_attention_fwd(const mmfb_attn_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_attention_fwd: null args");
+  MMFB_REQUIRE_DEVICE();
+  return attn_fwd(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mmfb_attention_bwd(const mmfb_attn_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_attention_bwd: null args");
+  MMFB_REQUIRE_DEVICE();
+  return attn_bwd(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -31,5 +31,7 @@ int make_tmap_3d(CUtensorMap* map, const void* ptr, int64_t inner, int64_t d1, i
                  int64_t ld2, int box_inner, int box_d1);
 
 int gemm(const mmfb_gemm_args& a, cudaStream_t stream);
+int attn_fwd(const mmfb_attn_args& a, cudaStream_t stream);
+int attn_bwd(const mmfb_attn_args& a, cudaStream_t stream);
 
 }  // namespace mmfb

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import lib
-from .lib import LIB, GemmArgs, _ptr, _stream_ptr, check
+from .lib import LIB, AttnArgs, GemmArgs, _ptr, _stream_ptr, check
 
 
 def _req(t, dtype, name):
@@ -67,3 +67,74 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=lib.EPI_BIAS, bias=None, aux=None,
     if epi == lib.EPI_BIAS_GELU:
         return out, out2
     return out
+
+
+def _attn_args(q, k, v, B, heads, Sq, Skv, mask, drop_mask, drop_scale):
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.bfloat16, n)
+    W = q.shape[-1]
+    if W % heads:
+        raise ValueError(
+            "The hidden size (%d) is not a multiple of the number of attention heads (%d)" % (W, heads))
+    if q.shape[0] != B * Sq or k.shape[0] != B * Skv or v.shape[0] != B * Skv:
+        raise ValueError("attention: q/k/v row counts do not match B*Sq / B*Skv")
+    a = AttnArgs()
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.k, a.ldk = k.data_ptr(), k.stride(0)
+    a.v, a.ldv = v.data_ptr(), v.stride(0)
+    if mask is not None:
+        _req(mask, torch.float32, "mask")
+        if tuple(mask.shape) != (B, Skv) or not mask.is_contiguous():
+            raise ValueError("attention: additive mask must be contiguous fp32 [B, Skv]")
+        a.mask = mask.data_ptr()
+    if drop_mask is not None:
+        _req(drop_mask, torch.int32, "drop_mask")
+        if tuple(drop_mask.shape) != (B, heads, Sq, (Skv + 31) // 32) or not drop_mask.is_contiguous():
+            raise ValueError("attention: drop_mask must be contiguous int32 [B, heads, Sq, ceil(Skv/32)]")
+        a.drop_mask, a.drop_scale = drop_mask.data_ptr(), float(drop_scale)
+    a.B, a.heads, a.Sq, a.Skv, a.head_dim = B, heads, Sq, Skv, W // heads
+    return a
+
+
+def attention_fwd(q, k, v, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0, out=None):
+    """ctx, lse2 = fused softmax(QK^T/sqrt(d) + mask) V.  q [B*Sq, h*d], k/v [B*Skv, h*d] (views allowed)."""
+    a = _attn_args(q, k, v, B, heads, Sq, Skv, mask, drop_mask, drop_scale)
+    W = q.shape[-1]
+    ctx = out if out is not None else torch.empty(B * Sq, W, dtype=torch.bfloat16, device=q.device)
+    lse2 = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
+    a.ctx, a.ldo, a.lse2 = ctx.data_ptr(), ctx.stride(0), lse2.data_ptr()
+    check(LIB.mmfb_attention_fwd(ctypes.byref(a), _stream_ptr()))
+    return ctx, lse2
+
+
+def attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0,
+                  dq=None, dk=None, dv=None):
+    """dq, dk, dv from the saved q, k, v, ctx and row statistics (probabilities are recomputed)."""
+    a = _attn_args(q, k, v, B, heads, Sq, Skv, mask, drop_mask, drop_scale)
+    _req(dctx, torch.bfloat16, "dctx")
+    _req(ctx, torch.bfloat16, "ctx")
+    W = q.shape[-1]
+    dq = dq if dq is not None else torch.empty(B * Sq, W, dtype=torch.bfloat16, device=q.device)
+    dk = dk if dk is not None else torch.empty(B * Skv, W, dtype=torch.bfloat16, device=q.device)
+    dv = dv if dv is not None else torch.empty(B * Skv, W, dtype=torch.bfloat16, device=q.device)
+    delta = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
+    a.ctx, a.ldo, a.lse2 = ctx.data_ptr(), ctx.stride(0), lse2.data_ptr()
+    a.dctx, a.ld_dctx, a.delta = dctx.data_ptr(), dctx.stride(0), delta.data_ptr()
+    a.dq, a.ld_dq = dq.data_ptr(), dq.stride(0)
+    a.dk, a.ld_dk = dk.data_ptr(), dk.stride(0)
+    a.dv, a.ld_dv = dv.data_ptr(), dv.stride(0)
+    check(LIB.mmfb_attention_bwd(ctypes.byref(a), _stream_ptr()))
+    return dq, dk, dv
+
+
+def pack_keep_bits(keep):
+    """bool [..., n] -> int32 [..., ceil(n/32)] keep-bit words (bit j of word w = element 32*w + j)."""
+    n = keep.shape[-1]
+    pad = (-n) % 32
+    if pad:
+        keep = torch.nn.functional.pad(keep, (0, pad))
+    k = keep.reshape(*keep.shape[:-1], -1, 32).to(torch.int64)
+    weights = (1 << torch.arange(32, device=keep.device, dtype=torch.int64))
+    words = (k * weights).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+    return words.to(torch.int32).contiguous()

@@ -35,6 +35,25 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("q", ctypes.c_void_p), ("ldq", ctypes.c_int64),
+        ("k", ctypes.c_void_p), ("ldk", ctypes.c_int64),
+        ("v", ctypes.c_void_p), ("ldv", ctypes.c_int64),
+        ("mask", ctypes.c_void_p),
+        ("ctx", ctypes.c_void_p), ("ldo", ctypes.c_int64),
+        ("lse2", ctypes.c_void_p),
+        ("drop_mask", ctypes.c_void_p), ("drop_scale", ctypes.c_float),
+        ("dctx", ctypes.c_void_p), ("ld_dctx", ctypes.c_int64),
+        ("delta", ctypes.c_void_p),
+        ("dq", ctypes.c_void_p), ("ld_dq", ctypes.c_int64),
+        ("dk", ctypes.c_void_p), ("ld_dk", ctypes.c_int64),
+        ("dv", ctypes.c_void_p), ("ld_dv", ctypes.c_int64),
+        ("B", ctypes.c_int), ("heads", ctypes.c_int), ("Sq", ctypes.c_int), ("Skv", ctypes.c_int),
+        ("head_dim", ctypes.c_int),
+    ]
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         try:

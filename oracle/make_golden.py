@@ -1,0 +1,239 @@
+"""TEST INFRASTRUCTURE - generates tests/golden/*.pt by running the REFERENCE's own source files.
+
+Runs only in the build container (needs /root/reference):   python -m oracle.make_golden
+Each fixture holds seeded weights (reference state_dict key names), inputs, the reference's outputs
+and the gradients of a fixed random-projection loss  (out * W_rand).sum()  (out.sum()
+is degenerate after a final LayerNorm).  Shapes are tiny so the fixtures are a few hundred KB.
+All modules run in eval mode (dropout off): the reference's RNG stream is not reproducible elsewhere.
+"""
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader as R  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _perturb(module, seed):
+    """reference init (normal 0.02, zero bias, LN 1/0) + small perturbation of biases / LN so they matter"""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in module.named_parameters():
+            if p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif "LayerNorm.weight" in n or n.endswith("layer_norms.0.weight") or n.endswith(".1.weight"):
+                p.copy_(1.0 + torch.randn(p.shape, generator=g) * 0.02)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+
+
+def _grads(module, names):
+    sd = dict(module.named_parameters())
+    return {n: sd[n].grad.detach().clone() for n in names if sd[n].grad is not None}
+
+
+def _save(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(obj, path)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+def golden_bert_encoder():
+    from transformers import BertConfig
+    hl = R.hf_layers()
+    cfg = BertConfig(hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=2,
+                     vocab_size=50, max_position_embeddings=32)
+    enc = hl.BertEncoderJit(cfg).eval()
+    _perturb(enc, 11)
+    g = torch.Generator().manual_seed(12)
+    B, S = 3, 12
+    x = torch.randn(B, S, 64, generator=g, requires_grad=True)
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[0, 9:] = 0
+    mask[1, 5:] = 0
+    mask[2, :] = 0  # fully masked row: softmax must become uniform, not NaN (tests/models/test_vilbert.py:66)
+    add = (1.0 - mask[:, None, None, :].float()) * -10000.0
+    out = enc(x, add)[0]
+    w = torch.randn(out.shape, generator=g)
+    (out * w).sum().backward()
+    names = [n for n, _ in enc.named_parameters()]
+    _save("bert_encoder", {
+        "cfg": {"hidden": 64, "heads": 4, "inter": 128, "layers": 2},
+        "state_dict": {k: v.detach().clone() for k, v in enc.state_dict().items()},
+        "x": x.detach(), "mask": mask, "w_rand": w, "out": out.detach(), "dx": x.grad.detach(),
+        "grads": _grads(enc, names),
+    })
+
+
+def golden_vilbert_encoder():
+    vb = R.vilbert()
+    cfg = types.SimpleNamespace(
+        hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=3,
+        v_hidden_size=96, v_num_attention_heads=4, v_intermediate_size=96, v_num_hidden_layers=2,
+        bi_hidden_size=128, bi_num_attention_heads=4, v_biattention_id=[0, 1], t_biattention_id=[1, 2],
+        hidden_act="gelu", v_hidden_act="gelu", hidden_dropout_prob=0.1, v_hidden_dropout_prob=0.1,
+        attention_probs_dropout_prob=0.1, v_attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12,
+        fast_mode=False, with_coattention=True, in_batch_pairs=False, fixed_t_layer=0, fixed_v_layer=0,
+        dynamic_attention=False, visualization=False, chunk_size_feed_forward=0, is_decoder=False,
+        add_cross_attention=False, position_embedding_type="absolute", _attn_implementation="eager",
+    )
+    enc = vb.BertEncoder(cfg).eval()
+    _perturb(enc, 21)
+    g = torch.Generator().manual_seed(22)
+    B, T, Rn = 2, 7, 5
+    txt = torch.randn(B, T, 64, generator=g, requires_grad=True)
+    img = torch.randn(B, Rn, 96, generator=g, requires_grad=True)
+    tmask = torch.ones(B, T, dtype=torch.long)
+    tmask[1, 4:] = 0
+    imask = torch.ones(B, Rn, dtype=torch.long)
+    imask[0, 3:] = 0
+    tadd = (1.0 - tmask[:, None, None, :].float()) * -10000.0
+    iadd = (1.0 - imask[:, None, None, :].float()) * -10000.0
+    co = torch.zeros(B, 1, Rn, T)
+    t_layers, v_layers, _ = enc(txt, img, tadd, tadd, iadd, co, output_all_encoded_layers=False)
+    t_out, v_out = t_layers[-1], v_layers[-1]
+    wt = torch.randn(t_out.shape, generator=g)
+    wv = torch.randn(v_out.shape, generator=g)
+    ((t_out * wt).sum() + (v_out * wv).sum()).backward()
+    names = [n for n, p in enc.named_parameters()]
+    grads = _grads(enc, names)
+    unused = [n for n, p in enc.named_parameters() if p.grad is None]
+    _save("vilbert_encoder", {
+        "cfg": {k: getattr(cfg, k) for k in ("hidden_size", "num_attention_heads", "intermediate_size",
+                                              "num_hidden_layers", "v_hidden_size", "v_num_attention_heads",
+                                              "v_intermediate_size", "v_num_hidden_layers", "bi_hidden_size",
+                                              "bi_num_attention_heads", "v_biattention_id", "t_biattention_id")},
+        "state_dict": {k: v.detach().clone() for k, v in enc.state_dict().items()},
+        "txt": txt.detach(), "img": img.detach(), "tmask": tmask, "imask": imask, "wt": wt, "wv": wv,
+        "t_out": t_out.detach(), "v_out": v_out.detach(), "dtxt": txt.grad.detach(), "dimg": img.grad.detach(),
+        "grads": grads, "unused": unused,
+    })
+
+
+def golden_embeddings():
+    from transformers import BertConfig
+    em = R.embeddings()
+    vb = R.vilbert()
+    cfg = BertConfig(hidden_size=64, vocab_size=50, max_position_embeddings=32, type_vocab_size=2)
+    cfg.visual_embedding_dim = 40
+    mod = em.BertVisioLinguisticEmbeddings(cfg).eval()
+    _perturb(mod, 31)
+    g = torch.Generator().manual_seed(32)
+    B, T, Rn = 2, 9, 6
+    ids = torch.randint(0, 50, (B, T), generator=g)
+    seg = torch.randint(0, 2, (B, T), generator=g)
+    feats = torch.randn(B, Rn, 40, generator=g).abs()
+    vtype = torch.zeros(B, Rn, dtype=torch.long)
+    out_plain = mod(ids, seg, feats, vtype)
+    ali = torch.randint(-1, T, (B, Rn, 3), generator=g)
+    ali[0, 0, :] = -1  # a region aligned to nothing: the divide-by-zero guard
+    out_ali = mod(ids, seg, feats, vtype, ali)
+    out_text = mod(ids, seg)
+    # ViLBERT image embeddings
+    vcfg = types.SimpleNamespace(v_feature_size=40, v_hidden_size=96, hidden_dropout_prob=0.1)
+    imod = vb.BertImageFeatureEmbeddings(vcfg).eval()
+    _perturb(imod, 33)
+    loc = torch.rand(B, Rn, 5, generator=g)
+    iout = imod(feats, loc)
+    _save("embeddings", {
+        "vl_state_dict": {k: v.detach().clone() for k, v in mod.state_dict().items() if v.dtype.is_floating_point},
+        "ids": ids, "seg": seg, "feats": feats, "vtype": vtype, "alignment": ali,
+        "out_plain": out_plain.detach(), "out_alignment": out_ali.detach(), "out_text": out_text.detach(),
+        "img_state_dict": {k: v.detach().clone() for k, v in imod.state_dict().items()},
+        "loc": loc, "img_out": iout.detach(),
+    })
+
+
+def golden_mmbt():
+    from transformers import BertConfig
+    hl = R.hf_layers()
+    mm = R.mmbt()
+    hl.replace_with_jit = lambda: None
+    cfg = BertConfig(hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=1,
+                     vocab_size=50, max_position_embeddings=64, type_vocab_size=2)
+    cfg.modal_hidden_size = 40
+    transformer = hl.BertModelJit(cfg)
+    model = mm.MMBTModel(cfg, transformer, torch.nn.Identity()).eval()
+    _perturb(model, 41)
+    g = torch.Generator().manual_seed(42)
+    B, T, Rn = 2, 8, 10
+    ids = torch.randint(3, 50, (B, T), generator=g)
+    ids[:, 0] = 1  # [CLS]
+    lens = [8, 5]
+    mask = torch.zeros(B, T, dtype=torch.long)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+        ids[b, n - 1] = 2  # [SEP]
+    seg = torch.zeros(B, T, dtype=torch.long)
+    feats = torch.randn(B, Rn, 40, generator=g).abs()
+    # integer token surgery of MMBTBase.forward / extract_modal_end_token (bit-exact path)
+    sl = {"input_ids": ids.clone(), "input_mask": mask.clone(), "segment_ids": seg.clone()}
+    start = sl["input_ids"][:, 0].clone()
+    end = mm.MMBTBase.extract_modal_end_token(None, sl)
+    modal_tt = torch.full((B, 1), 1, dtype=torch.long)  # single segment, max_id == 0 -> token_value 1
+    out = model(feats, input_ids=sl["input_ids"], modal_start_tokens=start, modal_end_tokens=end,
+                attention_mask=sl["input_mask"], token_type_ids=sl["segment_ids"], modal_token_type_ids=modal_tt)
+    _save("mmbt", {
+        "cfg": {"hidden": 64, "heads": 4, "inter": 128, "layers": 1, "modal_hidden": 40},
+        "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items() if v.dtype.is_floating_point},
+        "ids": ids, "mask": mask, "seg": seg, "feats": feats,
+        "end_token": end, "shifted_ids": sl["input_ids"], "shifted_mask": sl["input_mask"],
+        "seq_out": out[0].detach(), "pooled": out[1].detach(),
+    })
+
+
+class _Cfg(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def golden_mmft_embeddings():
+    from transformers import BertConfig
+    hl = R.hf_layers()
+    hb = R.hf_backend()
+    tcfg = BertConfig(hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=1,
+                      vocab_size=50, max_position_embeddings=32, type_vocab_size=2, pad_token_id=0)
+    transformer = hl.BertModelJit(tcfg)
+    mcfg = _Cfg(modalities=[_Cfg(type="text", key="text", position_dim=32, embedding_dim=64, segment_id=0),
+                            _Cfg(type="image", key="image", position_dim=16, embedding_dim=40, segment_id=1)],
+                token_noise_mean=0.0, token_noise_std=0.01)
+    torch.manual_seed(51)
+    emb = hb.HuggingfaceEmbeddings(mcfg, tcfg, transformer).eval()
+    _perturb(emb, 52)
+    g = torch.Generator().manual_seed(53)
+    B, T, P = 2, 7, 4
+    tokens = {"text": torch.randint(0, 50, (B, T), generator=g), "image": torch.randn(B, P, 40, generator=g)}
+    pos = {"text": torch.arange(T).unsqueeze(0).expand(B, T).contiguous(),
+           "image": torch.arange(P).unsqueeze(0).expand(B, P).contiguous()}
+    seg = {"text": torch.zeros(B, T, dtype=torch.long), "image": torch.ones(B, P, dtype=torch.long)}
+    out = emb(tokens, pos, seg)
+    masks = [torch.ones(B, T), torch.ones(B, P)]
+    masks[0][1, 5:] = 0
+    am = hb.HuggingfaceBackend.generate_attention_mask(None, masks)
+    _save("mmft_embeddings", {
+        "state_dict": {k: v.detach().clone() for k, v in emb.state_dict().items()},
+        "tokens": tokens, "pos": pos, "seg": seg, "out": out.detach(), "masks": masks, "attention_mask": am,
+    })
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    golden_bert_encoder()
+    golden_vilbert_encoder()
+    golden_embeddings()
+    golden_mmbt()
+    golden_mmft_embeddings()
+
+
+if __name__ == "__main__":
+    main()

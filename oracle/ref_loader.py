@@ -21,8 +21,9 @@ import types
 
 REF_ROOT = os.environ.get("MMF_REFERENCE_ROOT", "/root/reference")
 
-_STUB_PREFIXES = ("mmf", "omegaconf", "pytorch_lightning", "iopath", "termcolor", "torchtext", "lmdb",
-                  "transformers3")
+# NB: `transformers3` is deliberately NOT stubbed: the reference's `try: from transformers3 ...` must fail
+# so that it falls back to the real (aliased) transformers.modeling_bert.
+_STUB_PREFIXES = ("mmf", "omegaconf", "pytorch_lightning", "iopath", "termcolor", "torchtext", "lmdb")
 
 
 class _Anything:
