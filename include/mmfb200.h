@@ -94,6 +94,60 @@ typedef struct {
 int mmfb_attention_fwd(const mmfb_attn_args* args, mmfb_stream stream);
 int mmfb_attention_bwd(const mmfb_attn_args* args, mmfb_stream stream);
 
+/* LayerNorm over the last dimension (eps 1e-12 on this path), one warp per row.
+ * fwd: x = LN(y)*gamma + beta, optional dropout on x (embeddings), saves mean / rstd (fp32 [M]).
+ * bwd: dy = dLN(dx (+dx2)); dz = dropout-backward(dy) for the dense branch that fed y = dropout(dense)+resid;
+ *      dgamma/dbeta/dbias (fp32 [H]) are ACCUMULATED (+=).  dz may equal dy (no dropout) or be NULL. */
+typedef struct {
+  const void* y; int64_t ldy;        /* bf16 [M,H] pre-LN input */
+  const void* gamma; const void* beta; /* bf16 [H] */
+  void* x; int64_t ldx;              /* fwd output bf16 [M,H] */
+  float* mean; float* rstd;          /* fp32 [M]: written by fwd, read by bwd */
+  const uint32_t* drop_mask; int64_t ldmask; float drop_scale;
+  float eps;
+  /* backward */
+  const void* dx; int64_t lddx;      /* bf16 [M,H] gradient wrt LN output */
+  const void* dx2; int64_t lddx2;    /* optional second gradient term added to dx, or NULL */
+  void* dy; int64_t lddy;            /* bf16 [M,H] gradient wrt y (residual branch) */
+  void* dz; int64_t lddz;            /* bf16 [M,H] gradient wrt the dropped dense output */
+  float* dgamma; float* dbeta; float* dbias;
+  int M, H;
+} mmfb_ln_args;
+
+int mmfb_layernorm_fwd(const mmfb_ln_args* args, mmfb_stream stream);
+int mmfb_layernorm_bwd(const mmfb_ln_args* args, mmfb_stream stream);
+
+/* out[n] += sum_m X[m,n]   (bias gradients), X bf16 [M,N], out fp32 [N] */
+int mmfb_colsum(const void* X, int64_t ldx, float* out, int M, int N, mmfb_stream stream);
+
+/* Philox keep-bits for nn.Dropout(p): word w bit j <-> element 32*w+j, P(bit=1) = 1-p (16-bit resolution) */
+int mmfb_dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, mmfb_stream stream);
+
+/* Embedding row composer (K1): y[r] = src0[src_row0[r]] + src1[src_row1[r]] + tab0[idx0[r]] + tab1[idx1[r]] +
+ * tab2[idx2[r]]; a NULL pointer or a negative index drops the term.  src*: bf16 [*, ldsrc] dense rows (e.g. the
+ * region-feature projection), tab*: bf16 [*, H] embedding tables.  Index arrays are int32 [M] on the device.
+ * Covers BertVisioLinguisticEmbeddings (embeddings.py:329-370), ModalEmbeddings (mmbt.py:92-129),
+ * HuggingfaceEmbeddings (huggingface.py:131-159) and BertImageFeatureEmbeddings (vilbert.py:904-913). */
+typedef struct {
+  const void* src[2]; int64_t ldsrc[2]; const int32_t* src_row[2];
+  const void* tab[3]; const int32_t* tab_idx[3];
+  void* y; int64_t ldy;
+  int M, H;
+} mmfb_compose_args;
+int mmfb_embed_compose(const mmfb_compose_args* args, mmfb_stream stream);
+
+/* backward of the composer: dsrc_k[src_row_k[r]] = dy[r] (bf16 store), dtab_k[idx_k[r]] += dy[r] (fp32 atomics) */
+typedef struct {
+  void* dsrc[2]; int64_t ldsrc[2]; const int32_t* src_row[2];
+  float* dtab[3]; const int32_t* tab_idx[3];
+  const void* dy; int64_t lddy;
+  int M, H;
+} mmfb_scatter_args;
+int mmfb_embed_scatter(const mmfb_scatter_args* args, mmfb_stream stream);
+
+/* fp32 -> bf16 cast of a flat (parameter) buffer */
+int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream);
+
 /* library / diagnostics */
 const char* mmfb_last_error(void);
 int mmfb_version(void);

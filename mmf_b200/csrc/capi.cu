@@ -136,4 +136,40 @@ int mmfb_attention_bwd(const mmfb_attn_args* args, mmfb_stream stream) {
   return attn_bwd(*args, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mmfb_layernorm_fwd(const mmfb_ln_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_layernorm_fwd: null args");
+  MMFB_REQUIRE_DEVICE();
+  return ln_fwd(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_layernorm_bwd(const mmfb_ln_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_layernorm_bwd: null args");
+  MMFB_REQUIRE_DEVICE();
+  return ln_bwd(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_colsum(const void* X, int64_t ldx, float* out, int M, int N, mmfb_stream stream) {
+  if (!X || !out) return set_error(MMFB_ERR_ARG, "mmfb_colsum: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return colsum(X, ldx, out, M, N, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, mmfb_stream stream) {
+  if (!out) return set_error(MMFB_ERR_ARG, "mmfb_dropout_bits: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return dropout_bits(out, nwords, seed, offset, p, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_embed_compose(const mmfb_compose_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_embed_compose: null args");
+  MMFB_REQUIRE_DEVICE();
+  return compose(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_embed_scatter(const mmfb_scatter_args* args, mmfb_stream stream) {
+  if (!args) return set_error(MMFB_ERR_ARG, "mmfb_embed_scatter: null args");
+  MMFB_REQUIRE_DEVICE();
+  return scatter(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream) {
+  if (!in || !out) return set_error(MMFB_ERR_ARG, "mmfb_cast_f32_bf16: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return cast_params(in, out, n, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -423,8 +423,12 @@ static int dispatch(const mmfb_gemm_args& a, cudaStream_t s) {
 
 int gemm(const mmfb_gemm_args& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(MMFB_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
-  if ((a.N % 8) || (a.K % 8) || (a.M % 8 && (a.a_mn)))
-    return set_error(MMFB_ERR_ARG, "gemm: N, K (and M for MN-major A) must be multiples of 8 (got %d,%d,%d)", a.M, a.N, a.K);
+  // only CONTIGUOUS extents need 16-byte granularity (TMA row pitch / vector epilogue); K of an MN-major operand
+  // (= the token count in the weight-gradient GEMM) is a row count and may be anything
+  if (a.N % 8) return set_error(MMFB_ERR_ARG, "gemm: N must be a multiple of 8 (got %d)", a.N);
+  if ((!a.a_mn || !a.b_mn) && (a.K % 8))
+    return set_error(MMFB_ERR_ARG, "gemm: K must be a multiple of 8 for K-major operands (got %d)", a.K);
+  if (a.a_mn && (a.M % 8)) return set_error(MMFB_ERR_ARG, "gemm: M must be a multiple of 8 for MN-major A (got %d)", a.M);
   if ((a.lda % 8) || (a.ldb % 8) || (a.epi != EPI_ATOMIC_F32 && (a.ldc % 8)))
     return set_error(MMFB_ERR_ARG, "gemm: leading dimensions must be multiples of 8 elements");
   const int bn = a.block_n > 0 ? a.block_n : (a.N >= 256 ? 256 : 128);

@@ -1,0 +1,436 @@
+// Row-wise (HBM-bound) kernels of the fusion block: LayerNorm forward/backward (with the dropout
+// backward and bias-gradient column sums folded in), bias-gradient column sums, Philox dropout keep-bit
+// generation, the embedding "compose + LayerNorm" kernel (region-feature / token gather + type /
+// position add + LN) and its scatter backward, fp32 -> bf16 parameter cast.
+//
+// All of them are one-warp-per-row, 16-byte vectorised, fully coalesced; nothing here is GEMM-shaped.
+// Reference ops: nn.LayerNorm(eps=1e-12) in HF BertSelfOutput/BertOutput (called at
+// mmf/modules/hf_layers.py:248,290) and mmf/models/vilbert.py:254,303,483,490,911; nn.Dropout at the same
+// sites; embeddings mmf/modules/embeddings.py:329-370,423-459, mmf/models/mmbt.py:92-129,
+// mmf/models/transformers/backends/huggingface.py:131-159, mmf/models/vilbert.py:904-913.
+#include "common.cuh"
+#include "mmfb_internal.h"
+
+namespace mmfb {
+
+constexpr int MAXV = 8;         // per-lane 8-element vectors: rows up to 8*256 = 2048 columns
+constexpr int ROW_WARPS = 8;    // warps per block
+
+__device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm forward:  x = LN(y) * gamma + beta  (+ optional dropout on the OUTPUT, used by the embeddings)
+// ----------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_fwd_kernel(const bf16* __restrict__ y, int64_t ldy, const bf16* __restrict__ gamma,
+              const bf16* __restrict__ beta, bf16* __restrict__ x, int64_t ldx, float* __restrict__ mean,
+              float* __restrict__ rstd, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale, int M,
+              int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float v[NV][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+      ld8(y + row * ldy + col, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+  }
+  const float mu = warp_sum(s) / H;
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mu; ss += d * d; }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(ss) / H + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+      float g[8], b[8], o[8];
+      ld8(gamma + col, g);
+      ld8(beta + col, b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mu) * rs * g[e] + b[e];
+      if (dmask != nullptr) {
+        const uint32_t w = __ldg(dmask + row * ldmask + (col >> 5));
+        const uint32_t bits = (w >> (col & 31)) & 0xFFu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = ((bits >> e) & 1u) ? o[e] * dscale : 0.0f;
+      }
+      st8(x + row * ldx + col, o);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm backward (+ dropout backward of the pre-LN dense branch + bias gradient)
+//   dy    = gamma*rstd * (dx - mean_h(dx*gamma) ... ) standard LN backward wrt the pre-LN sum y = z + resid
+//   dz    = dy * keep * dscale        (gradient of the dense output that was dropped)   [== dy when no dropout]
+//   dgamma += sum_rows dx * xhat ; dbeta += sum_rows dx ; dbias += sum_rows dz
+// dx_in may carry an extra additive term dx2 (the residual gradient arriving from a later consumer).
+// A persistent grid (grid-stride over row groups) keeps the number of fp32 atomics at 3*H per block.
+// ----------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_bwd_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
+              const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
+              bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  __shared__ float red[ROW_WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[NV][8], ab[NV][8], az[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ag[i][e] = 0.0f; ab[i][e] = 0.0f; az[i][e] = 0.0f; }
+
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + warp; row < M;
+       row += static_cast<int64_t>(gridDim.x) * ROW_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[NV][8], d[NV][8], xh[NV][8];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        float yy[8];
+        ld8(dx + row * lddx + col, d[i]);
+        if (dx2 != nullptr) {
+          float t[8];
+          ld8(dx2 + row * lddx2 + col, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[i][e] += t[e];
+        }
+        ld8(y + row * ldy + col, yy);
+        ld8(gamma + col, g[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[i][e] = (yy[e] - mu) * rs;
+          const float dg = d[i][e] * g[i][e];
+          s1 += dg;
+          s2 += dg * xh[i][e];
+          ag[i][e] += d[i][e] * xh[i][e];
+          ab[i][e] += d[i][e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (d[i][e] * g[i][e] - s1 - xh[i][e] * s2);
+        if (dy != nullptr) st8(dy + row * lddy + col, o);
+        if (dmask != nullptr) {
+          const uint32_t w = __ldg(dmask + row * ldmask + (col >> 5));
+          const uint32_t bits = (w >> (col & 31)) & 0xFFu;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = ((bits >> e) & 1u) ? o[e] * dscale : 0.0f;
+          st8(dz + row * lddz + col, o);
+        } else if (dz != nullptr && dz != dy) {
+          st8(dz + row * lddz + col, o);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) az[i][e] += o[e];
+      }
+    }
+  }
+  // block reduction of the three column-sum sets, 256 columns at a time, then one atomic per column
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 256 >= H) break;
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = which == 0 ? ag[i][e] : (which == 1 ? ab[i][e] : az[i][e]);
+      __syncthreads();
+      const int c = threadIdx.x;  // 256 threads <-> 256 columns
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < ROW_WARPS; ++w) t += red[w][c];
+      if (i * 256 + c < H) atomicAdd(dst + i * 256 + c, t);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// column sums (bias gradients):  out[n] += sum_m X[m, n]
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ X, int64_t ldx, float* __restrict__ out, int M, int N) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+  if (col < N) {
+    for (int64_t row = static_cast<int64_t>(blockIdx.y) * 8 + warp; row < M; row += static_cast<int64_t>(gridDim.y) * 8) {
+      float t[8];
+      ld8(X + row * ldx + col, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += t[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) atomicAdd(out + c, t);
+}
+
+// ----------------------------------------------------------------------------------------------
+// dropout keep-bits: word w, bit j keeps element 32*w + j with probability 1-p (16-bit resolution)
+// ----------------------------------------------------------------------------------------------
+__global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t nwords, uint64_t seed, uint64_t offset,
+                                    uint32_t thresh16) {
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 r = philox4x32(seed, offset + static_cast<uint64_t>(w) * 4 + i);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bits |= ((rr[k] & 0xFFFFu) >= thresh16 ? 1u : 0u) << (i * 8 + k * 2);
+      bits |= ((rr[k] >> 16) >= thresh16 ? 1u : 0u) << (i * 8 + k * 2 + 1);
+    }
+  }
+  out[w] = bits;
+}
+
+// ----------------------------------------------------------------------------------------------
+// embedding compose:  y[r] = src0[s0[r]] + src1[s1[r]] + tab0[i0[r]] + tab1[i1[r]] + tab2[i2[r]]   (absent terms: index < 0)
+// followed by LayerNorm (+dropout) -> x[r]; y (pre-LN) is saved for the backward.
+// ----------------------------------------------------------------------------------------------
+struct ComposeDev {
+  const bf16* src[2]; int64_t ldsrc[2]; const int32_t* srow[2];
+  const bf16* tab[3]; const int32_t* tidx[3];
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+compose_kernel(ComposeDev c, bf16* __restrict__ y, int64_t ldy, int M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int sidx[2], tix[3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) sidx[k] = (c.src[k] != nullptr && c.srow[k] != nullptr) ? c.srow[k][row] : -1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) tix[k] = (c.tab[k] != nullptr && c.tidx[k] != nullptr) ? c.tidx[k][row] : -1;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (sidx[k] >= 0) {
+          float t[8];
+          ld8(c.src[k] + static_cast<int64_t>(sidx[k]) * c.ldsrc[k] + col, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[e] += t[e];
+        }
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (tix[k] >= 0) {
+          float t[8];
+          ld8(c.tab[k] + static_cast<int64_t>(tix[k]) * H + col, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[e] += t[e];
+        }
+      st8(y + row * ldy + col, a);
+    }
+  }
+}
+
+struct ScatterDev {
+  bf16* dsrc[2]; int64_t ldsrc[2]; const int32_t* srow[2];
+  float* dtab[3]; const int32_t* tidx[3];
+};
+
+// backward of compose: dsrc_k[s_k[r]] = dy[r]  (rows are unique) ; dtab_k[i_k[r]] += dy[r]  (fp32 atomics)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+scatter_kernel(ScatterDev c, const bf16* __restrict__ dy, int64_t lddy, int M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int sidx[2], tix[3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) sidx[k] = (c.dsrc[k] != nullptr && c.srow[k] != nullptr) ? c.srow[k][row] : -1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) tix[k] = (c.dtab[k] != nullptr && c.tidx[k] != nullptr) ? c.tidx[k][row] : -1;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+      float a[8];
+      ld8(dy + row * lddy + col, a);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (sidx[k] >= 0) st8(c.dsrc[k] + static_cast<int64_t>(sidx[k]) * c.ldsrc[k] + col, a);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (tix[k] >= 0) {
+          float* d = c.dtab[k] + static_cast<int64_t>(tix[k]) * H + col;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) atomicAdd(d + e, a[e]);
+        }
+    }
+  }
+}
+
+// fp32 -> bf16 cast of the flat parameter buffer (done every forward, like autocast does)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(in + i);
+    const float4 b = *reinterpret_cast<const float4*>(in + i + 4);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + i) = u;
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------------
+static int check_rows(int M, int H, const char* who) {
+  if (M <= 0 || H <= 0) return set_error(MMFB_ERR_ARG, "%s: empty problem", who);
+  if (H % 8 || H > MAXV * 256) return set_error(MMFB_ERR_ARG, "%s: hidden size %d must be a multiple of 8 and <= %d", who, H, MAXV * 256);
+  return MMFB_OK;
+}
+static int launch_ok(const char* who) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "%s launch: %s", who, cudaGetErrorString(e));
+  count_launch();
+  return MMFB_OK;
+}
+
+int ln_fwd(const mmfb_ln_args& a, cudaStream_t s) {
+  int rc = check_rows(a.M, a.H, "layernorm_fwd");
+  if (rc) return rc;
+  if (!a.y || !a.gamma || !a.beta || !a.x) return set_error(MMFB_ERR_ARG, "layernorm_fwd: null pointer");
+#define LN_FWD(NV)                                                                                         \
+  ln_fwd_kernel<NV><<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(                          \
+      (const bf16*)a.y, a.ldy, (const bf16*)a.gamma, (const bf16*)a.beta, (bf16*)a.x, a.ldx, a.mean, a.rstd, \
+      a.drop_mask, a.ldmask, a.drop_scale, a.M, a.H, a.eps)
+  const int nv = (a.H + 255) / 256;
+  if (nv <= 1) LN_FWD(1); else if (nv == 2) LN_FWD(2); else if (nv == 3) LN_FWD(3); else if (nv == 4) LN_FWD(4); else LN_FWD(8);
+#undef LN_FWD
+  return launch_ok("layernorm_fwd");
+}
+
+int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
+  int rc = check_rows(a.M, a.H, "layernorm_bwd");
+  if (rc) return rc;
+  if (!a.dx || !a.y || !a.mean || !a.rstd || !a.gamma) return set_error(MMFB_ERR_ARG, "layernorm_bwd: null pointer");
+  if (a.drop_mask && !a.dz) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dropout mask given without dz");
+  int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = num_sms() * 2;
+  if (grid > cap) grid = cap;
+#define LN_BWD(NV)                                                                                              \
+  ln_bwd_kernel<NV><<<grid, ROW_WARPS * 32, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
+                                                    (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
+                                                    (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask,         \
+                                                    a.ldmask, a.drop_scale, a.dgamma, a.dbeta, a.dbias, a.M, a.H)
+  const int nv = (a.H + 255) / 256;
+  if (nv <= 1) LN_BWD(1); else if (nv == 2) LN_BWD(2); else if (nv == 3) LN_BWD(3); else if (nv == 4) LN_BWD(4); else LN_BWD(8);
+#undef LN_BWD
+  return launch_ok("layernorm_bwd");
+}
+
+int colsum(const void* X, int64_t ldx, float* out, int M, int N, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || N % 8) return set_error(MMFB_ERR_ARG, "colsum: bad shape %dx%d", M, N);
+  dim3 grid((N + 255) / 256, 1);
+  int rows_blocks = (M + 63) / 64;
+  const int cap = (num_sms() * 4 + grid.x - 1) / grid.x;
+  grid.y = rows_blocks < cap ? rows_blocks : cap;
+  if (grid.y < 1) grid.y = 1;
+  colsum_kernel<<<grid, 256, 0, s>>>((const bf16*)X, ldx, out, M, N);
+  return launch_ok("colsum");
+}
+
+int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, cudaStream_t s) {
+  if (nwords <= 0) return set_error(MMFB_ERR_ARG, "dropout_bits: empty");
+  if (!(p >= 0.0f && p < 1.0f)) return set_error(MMFB_ERR_ARG, "dropout_bits: p must be in [0,1), got %f", p);
+  const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  dropout_bits_kernel<<<static_cast<unsigned>((nwords + 255) / 256), 256, 0, s>>>(out, nwords, seed, offset, thresh);
+  return launch_ok("dropout_bits");
+}
+
+int compose(const mmfb_compose_args& a, cudaStream_t s) {
+  int rc = check_rows(a.M, a.H, "embed_compose");
+  if (rc) return rc;
+  if (!a.y) return set_error(MMFB_ERR_ARG, "embed_compose: null output");
+  ComposeDev c;
+  for (int k = 0; k < 2; ++k) { c.src[k] = (const bf16*)a.src[k]; c.ldsrc[k] = a.ldsrc[k]; c.srow[k] = a.src_row[k]; }
+  for (int k = 0; k < 3; ++k) { c.tab[k] = (const bf16*)a.tab[k]; c.tidx[k] = a.tab_idx[k]; }
+  compose_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(c, (bf16*)a.y, a.ldy, a.M, a.H);
+  return launch_ok("embed_compose");
+}
+
+int scatter(const mmfb_scatter_args& a, cudaStream_t s) {
+  int rc = check_rows(a.M, a.H, "embed_scatter");
+  if (rc) return rc;
+  if (!a.dy) return set_error(MMFB_ERR_ARG, "embed_scatter: null input");
+  ScatterDev c;
+  for (int k = 0; k < 2; ++k) { c.dsrc[k] = (bf16*)a.dsrc[k]; c.ldsrc[k] = a.ldsrc[k]; c.srow[k] = a.src_row[k]; }
+  for (int k = 0; k < 3; ++k) { c.dtab[k] = a.dtab[k]; c.tidx[k] = a.tab_idx[k]; }
+  scatter_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(c, (const bf16*)a.dy, a.lddy, a.M, a.H);
+  return launch_ok("embed_scatter");
+}
+
+int cast_params(const float* in, void* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return set_error(MMFB_ERR_ARG, "cast: empty");
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(MMFB_ERR_ARG, "cast: buffers must be 16-byte aligned");
+  const int64_t thr = (n + 7) / 8;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>(in, (bf16*)out, n);
+  return launch_ok("cast_f32_bf16");
+}
+
+}  // namespace mmfb

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import lib
-from .lib import LIB, AttnArgs, GemmArgs, _ptr, _stream_ptr, check
+from .lib import LIB, AttnArgs, ComposeArgs, GemmArgs, LnArgs, ScatterArgs, _ptr, _stream_ptr, check
 
 
 def _req(t, dtype, name):
@@ -138,3 +138,123 @@ def pack_keep_bits(keep):
     words = (k * weights).sum(-1)
     words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
     return words.to(torch.int32).contiguous()
+
+
+LN_EPS = 1e-12
+
+
+def layernorm_fwd(y, gamma, beta, eps=LN_EPS, drop_mask=None, drop_scale=1.0, out=None):
+    """x, mean, rstd = LayerNorm(y) over the last dim; y bf16 [M,H] (row stride allowed)."""
+    _req(y, torch.bfloat16, "y"); _req(gamma, torch.bfloat16, "gamma"); _req(beta, torch.bfloat16, "beta")
+    M, H = y.shape
+    x = out if out is not None else torch.empty(M, H, dtype=torch.bfloat16, device=y.device)
+    mean = torch.empty(M, dtype=torch.float32, device=y.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=y.device)
+    a = LnArgs()
+    a.y, a.ldy, a.gamma, a.beta = y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr()
+    a.x, a.ldx, a.mean, a.rstd = x.data_ptr(), x.stride(0), mean.data_ptr(), rstd.data_ptr()
+    if drop_mask is not None:
+        _req(drop_mask, torch.int32, "drop_mask")
+        a.drop_mask, a.ldmask, a.drop_scale = drop_mask.data_ptr(), drop_mask.stride(0), float(drop_scale)
+    a.eps, a.M, a.H = float(eps), M, H
+    check(LIB.mmfb_layernorm_fwd(ctypes.byref(a), _stream_ptr()))
+    return x, mean, rstd
+
+
+def layernorm_bwd(dx, y, mean, rstd, gamma, dgamma, dbeta, dbias=None, dx2=None, drop_mask=None, drop_scale=1.0,
+                  need_dz=True):
+    """Returns (dy, dz): dy = grad wrt y (goes to the residual branch), dz = grad wrt the dense output that was
+    dropped before the residual add (dz is dy when there is no dropout).  dgamma/dbeta/dbias (fp32 [H]) are
+    accumulated in place."""
+    _req(dx, torch.bfloat16, "dx"); _req(y, torch.bfloat16, "y"); _req(gamma, torch.bfloat16, "gamma")
+    M, H = y.shape
+    dy = torch.empty(M, H, dtype=torch.bfloat16, device=y.device)
+    a = LnArgs()
+    a.dx, a.lddx = dx.data_ptr(), dx.stride(0)
+    if dx2 is not None:
+        _req(dx2, torch.bfloat16, "dx2")
+        a.dx2, a.lddx2 = dx2.data_ptr(), dx2.stride(0)
+    a.y, a.ldy, a.mean, a.rstd, a.gamma = y.data_ptr(), y.stride(0), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
+    a.dy, a.lddy = dy.data_ptr(), dy.stride(0)
+    dz = dy
+    if drop_mask is not None:
+        _req(drop_mask, torch.int32, "drop_mask")
+        dz = torch.empty(M, H, dtype=torch.bfloat16, device=y.device)
+        a.drop_mask, a.ldmask, a.drop_scale = drop_mask.data_ptr(), drop_mask.stride(0), float(drop_scale)
+    a.dz, a.lddz = dz.data_ptr(), dz.stride(0)
+    for name, t in (("dgamma", dgamma), ("dbeta", dbeta), ("dbias", dbias)):
+        if t is not None:
+            _req(t, torch.float32, name)
+            setattr(a, name, t.data_ptr())
+    a.M, a.H = M, H
+    check(LIB.mmfb_layernorm_bwd(ctypes.byref(a), _stream_ptr()))
+    return dy, dz
+
+
+def colsum(x, out):
+    """out[n] += sum_m x[m,n] (x bf16 [M,N], out fp32 [N])."""
+    _req(x, torch.bfloat16, "x"); _req(out, torch.float32, "out")
+    check(LIB.mmfb_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], _stream_ptr()))
+    return out
+
+
+def dropout_bits(shape_rows, ncols, p, seed, offset, device):
+    """int32 keep-bit words [*shape_rows, ceil(ncols/32)] for nn.Dropout(p)."""
+    words = (ncols + 31) // 32
+    out = torch.empty(*shape_rows, words, dtype=torch.int32, device=device)
+    check(LIB.mmfb_dropout_bits(out.data_ptr(), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), float(p),
+                                _stream_ptr()))
+    return out
+
+
+def cast_f32_bf16(src, dst):
+    _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
+    if src.numel() != dst.numel() or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("cast: buffers must be contiguous and equally sized")
+    check(LIB.mmfb_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream_ptr()))
+    return dst
+
+
+def embed_compose(M, H, srcs=(), tabs=(), device=None):
+    """y[r] = sum_k src_k[row_k[r]] + sum_k tab_k[idx_k[r]].
+    srcs: up to 2 of (bf16 [*,H] tensor, int32 [M] rows); tabs: up to 3 of (bf16 [V,H] table, int32 [M] idx).
+    Negative indices drop the term for that row."""
+    a = ComposeArgs()
+    keep = []
+    for k, (t, rows) in enumerate(srcs):
+        _req(t, torch.bfloat16, "src%d" % k); _req(rows, torch.int32, "src_row%d" % k)
+        a.src[k], a.ldsrc[k], a.src_row[k] = t.data_ptr(), t.stride(0), rows.data_ptr()
+        device = t.device
+    for k, (t, idx) in enumerate(tabs):
+        _req(t, torch.bfloat16, "tab%d" % k); _req(idx, torch.int32, "tab_idx%d" % k)
+        if t.shape[1] != H or not t.is_contiguous():
+            raise ValueError("embedding table %d must be contiguous [V, %d]" % (k, H))
+        a.tab[k], a.tab_idx[k] = t.data_ptr(), idx.data_ptr()
+        device = t.device
+    y = torch.empty(M, H, dtype=torch.bfloat16, device=device)
+    a.y, a.ldy, a.M, a.H = y.data_ptr(), y.stride(0), M, H
+    check(LIB.mmfb_embed_compose(ctypes.byref(a), _stream_ptr()))
+    return y
+
+
+def embed_scatter(dy, dsrcs=(), dtabs=()):
+    """Backward of embed_compose: dsrcs (bf16 tensor, rows) get plain row stores, dtabs (fp32 table grad, idx) get
+    atomic accumulation."""
+    _req(dy, torch.bfloat16, "dy")
+    M, H = dy.shape
+    a = ScatterArgs()
+    for k, (t, rows) in enumerate(dsrcs):
+        _req(t, torch.bfloat16, "dsrc%d" % k)
+        a.dsrc[k], a.ldsrc[k], a.src_row[k] = t.data_ptr(), t.stride(0), rows.data_ptr()
+    for k, (t, idx) in enumerate(dtabs):
+        _req(t, torch.float32, "dtab%d" % k)
+        a.dtab[k], a.tab_idx[k] = t.data_ptr(), idx.data_ptr()
+    a.dy, a.lddy, a.M, a.H = dy.data_ptr(), dy.stride(0), M, H
+    check(LIB.mmfb_embed_scatter(ctypes.byref(a), _stream_ptr()))
+
+
+def unpack_keep_bits(words, n):
+    """int32 [..., W] -> bool [..., n] (test helper / oracle interop; runs on the words' device)."""
+    w = words.to(torch.int64) & 0xFFFFFFFF
+    bits = (w.unsqueeze(-1) >> torch.arange(32, device=words.device, dtype=torch.int64)) & 1
+    return bits.reshape(*words.shape[:-1], -1)[..., :n].bool()

@@ -54,6 +54,41 @@ class AttnArgs(ctypes.Structure):
     ]
 
 
+class LnArgs(ctypes.Structure):
+    _fields_ = [
+        ("y", ctypes.c_void_p), ("ldy", ctypes.c_int64),
+        ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("x", ctypes.c_void_p), ("ldx", ctypes.c_int64),
+        ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+        ("drop_mask", ctypes.c_void_p), ("ldmask", ctypes.c_int64), ("drop_scale", ctypes.c_float),
+        ("eps", ctypes.c_float),
+        ("dx", ctypes.c_void_p), ("lddx", ctypes.c_int64),
+        ("dx2", ctypes.c_void_p), ("lddx2", ctypes.c_int64),
+        ("dy", ctypes.c_void_p), ("lddy", ctypes.c_int64),
+        ("dz", ctypes.c_void_p), ("lddz", ctypes.c_int64),
+        ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p), ("dbias", ctypes.c_void_p),
+        ("M", ctypes.c_int), ("H", ctypes.c_int),
+    ]
+
+
+class ComposeArgs(ctypes.Structure):
+    _fields_ = [
+        ("src", ctypes.c_void_p * 2), ("ldsrc", ctypes.c_int64 * 2), ("src_row", ctypes.c_void_p * 2),
+        ("tab", ctypes.c_void_p * 3), ("tab_idx", ctypes.c_void_p * 3),
+        ("y", ctypes.c_void_p), ("ldy", ctypes.c_int64),
+        ("M", ctypes.c_int), ("H", ctypes.c_int),
+    ]
+
+
+class ScatterArgs(ctypes.Structure):
+    _fields_ = [
+        ("dsrc", ctypes.c_void_p * 2), ("ldsrc", ctypes.c_int64 * 2), ("src_row", ctypes.c_void_p * 2),
+        ("dtab", ctypes.c_void_p * 3), ("tab_idx", ctypes.c_void_p * 3),
+        ("dy", ctypes.c_void_p), ("lddy", ctypes.c_int64),
+        ("M", ctypes.c_int), ("H", ctypes.c_int),
+    ]
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         try:
@@ -66,6 +101,11 @@ def _load():
     lib = ctypes.CDLL(_LIB_PATH)
     lib.mmfb_last_error.restype = ctypes.c_char_p
     lib.mmfb_launch_count.restype = ctypes.c_int64
+    lib.mmfb_colsum.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_void_p]
+    lib.mmfb_dropout_bits.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64,
+                                      ctypes.c_float, ctypes.c_void_p]
+    lib.mmfb_cast_f32_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     return lib
 
 

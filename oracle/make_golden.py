@@ -47,13 +47,14 @@ def _save(name, obj):
 def golden_bert_encoder():
     from transformers import BertConfig
     hl = R.hf_layers()
-    cfg = BertConfig(hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=2,
+    # head_dim 64 (the reference's 768/12): the fused attention kernel supports head_dim 64 and 128
+    cfg = BertConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2,
                      vocab_size=50, max_position_embeddings=32)
     enc = hl.BertEncoderJit(cfg).eval()
     _perturb(enc, 11)
     g = torch.Generator().manual_seed(12)
     B, S = 3, 12
-    x = torch.randn(B, S, 64, generator=g, requires_grad=True)
+    x = torch.randn(B, S, 128, generator=g, requires_grad=True)
     mask = torch.ones(B, S, dtype=torch.long)
     mask[0, 9:] = 0
     mask[1, 5:] = 0
@@ -64,7 +65,7 @@ def golden_bert_encoder():
     (out * w).sum().backward()
     names = [n for n, _ in enc.named_parameters()]
     _save("bert_encoder", {
-        "cfg": {"hidden": 64, "heads": 4, "inter": 128, "layers": 2},
+        "cfg": {"hidden": 128, "heads": 2, "inter": 256, "layers": 2},
         "state_dict": {k: v.detach().clone() for k, v in enc.state_dict().items()},
         "x": x.detach(), "mask": mask, "w_rand": w, "out": out.detach(), "dx": x.grad.detach(),
         "grads": _grads(enc, names),
@@ -74,9 +75,9 @@ def golden_bert_encoder():
 def golden_vilbert_encoder():
     vb = R.vilbert()
     cfg = types.SimpleNamespace(
-        hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=3,
-        v_hidden_size=96, v_num_attention_heads=4, v_intermediate_size=96, v_num_hidden_layers=2,
-        bi_hidden_size=128, bi_num_attention_heads=4, v_biattention_id=[0, 1], t_biattention_id=[1, 2],
+        hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=3,
+        v_hidden_size=128, v_num_attention_heads=1, v_intermediate_size=128, v_num_hidden_layers=2,
+        bi_hidden_size=128, bi_num_attention_heads=2, v_biattention_id=[0, 1], t_biattention_id=[1, 2],
         hidden_act="gelu", v_hidden_act="gelu", hidden_dropout_prob=0.1, v_hidden_dropout_prob=0.1,
         attention_probs_dropout_prob=0.1, v_attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12,
         fast_mode=False, with_coattention=True, in_batch_pairs=False, fixed_t_layer=0, fixed_v_layer=0,
@@ -88,7 +89,7 @@ def golden_vilbert_encoder():
     g = torch.Generator().manual_seed(22)
     B, T, Rn = 2, 7, 5
     txt = torch.randn(B, T, 64, generator=g, requires_grad=True)
-    img = torch.randn(B, Rn, 96, generator=g, requires_grad=True)
+    img = torch.randn(B, Rn, 128, generator=g, requires_grad=True)
     tmask = torch.ones(B, T, dtype=torch.long)
     tmask[1, 4:] = 0
     imask = torch.ones(B, Rn, dtype=torch.long)
@@ -155,7 +156,7 @@ def golden_mmbt():
     hl = R.hf_layers()
     mm = R.mmbt()
     hl.replace_with_jit = lambda: None
-    cfg = BertConfig(hidden_size=64, num_attention_heads=4, intermediate_size=128, num_hidden_layers=1,
+    cfg = BertConfig(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=1,
                      vocab_size=50, max_position_embeddings=64, type_vocab_size=2)
     cfg.modal_hidden_size = 40
     transformer = hl.BertModelJit(cfg)
@@ -180,7 +181,7 @@ def golden_mmbt():
     out = model(feats, input_ids=sl["input_ids"], modal_start_tokens=start, modal_end_tokens=end,
                 attention_mask=sl["input_mask"], token_type_ids=sl["segment_ids"], modal_token_type_ids=modal_tt)
     _save("mmbt", {
-        "cfg": {"hidden": 64, "heads": 4, "inter": 128, "layers": 1, "modal_hidden": 40},
+        "cfg": {"hidden": 64, "heads": 1, "inter": 128, "layers": 1, "modal_hidden": 40},
         "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items() if v.dtype.is_floating_point},
         "ids": ids, "mask": mask, "seg": seg, "feats": feats,
         "end_token": end, "shifted_ids": sl["input_ids"], "shifted_mask": sl["input_mask"],

@@ -1,0 +1,108 @@
+"""CPU tests of the host-side logic (no GPU compute): C-ABI export, parameter pack, schedules, key names."""
+import ctypes
+import os
+import types
+
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from mmf_b200 import lib
+    syms = lib.header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib.LIB, s), s
+    assert lib.LIB.mmfb_version() >= 100
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    from mmf_b200 import lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    a = lib.GemmArgs()
+    rc = lib.LIB.mmfb_gemm(ctypes.byref(a), None)
+    assert rc == lib.MMFB_ERR_DEVICE
+    assert "no CPU fallback" in lib.last_error()
+    with pytest.raises(RuntimeError):
+        lib.check(rc)
+
+
+def test_param_pack_views_and_grad_handover():
+    from mmf_b200.engine import ParamPack
+    lin = [torch.nn.Linear(8, 16), torch.nn.Linear(8, 16), torch.nn.Linear(8, 16)]
+    params = [l.weight for l in lin] + [l.bias for l in lin]
+    before = [p.detach().clone() for p in params]
+    pack = ParamPack(params, "cpu")
+    for p, b in zip(params, before):
+        assert torch.equal(p.detach(), b)
+    assert pack.intact()
+    h = pack.handle(*params[0:3])           # fused q/k/v weight
+    assert tuple(h.w.shape) == (48, 8) and tuple(h.g.shape) == (48, 8)
+    # optimizer-style in-place update lands in the master buffer
+    with torch.no_grad():
+        params[1].add_(1.0)
+    assert torch.equal(pack.master[pack.offsets[1]:pack.offsets[1] + 128].view(16, 8), params[1].detach())
+    aliased = pack.prepare_grads()
+    assert not any(aliased)
+    grads = pack.autograd_grads(aliased)
+    for p, g in zip(params, grads):
+        p.grad = g
+    assert all(pack.prepare_grads())        # now aliased -> accumulate in place, autograd gets None
+    assert all(g is None for g in pack.autograd_grads([True] * len(params)))
+    lin[0].weight.data = lin[0].weight.data.clone()
+    assert not pack.intact()
+    with pytest.raises(ValueError):
+        pack.handle(params[0], params[2])   # not adjacent
+
+
+def test_vilbert_schedule_matches_oracle():
+    from mmf_b200.modules import vilbert_schedule
+    from oracle.fusion_oracle import vilbert_schedule as oracle_schedule
+    args = ([0, 1, 2, 3, 4, 5], [6, 7, 8, 9, 10, 11], 12, 6)
+    assert vilbert_schedule(*args) == oracle_schedule(*args)
+    assert vilbert_schedule([0, 1], [1, 2], 3, 2) == oracle_schedule([0, 1], [1, 2], 3, 2)
+
+
+def test_state_dict_keys_match_reference_modules():
+    from mmf_b200.modules import B200BertEncoder, B200ViLBertEncoder
+    g = torch.load(os.path.join(GOLD, "bert_encoder.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], hidden_dropout_prob=0.1,
+                                attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12)
+    enc = B200BertEncoder(cfg)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v.shape) for k, v in
+                                                                        g["state_dict"].items()}
+    g = torch.load(os.path.join(GOLD, "vilbert_encoder.pt"), weights_only=False)
+    cfg = types.SimpleNamespace(hidden_dropout_prob=0.1, v_hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                                v_attention_probs_dropout_prob=0.1, **g["cfg"])
+    enc = B200ViLBertEncoder(cfg)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v.shape) for k, v in
+                                                                        g["state_dict"].items()}
+
+
+def test_bad_head_split_raises_like_reference():
+    from mmf_b200.modules import B200BertEncoder
+    cfg = types.SimpleNamespace(hidden_size=100, num_attention_heads=3, intermediate_size=64, num_hidden_layers=1,
+                                hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12)
+    with pytest.raises(ValueError):
+        B200BertEncoder(cfg)
+
+
+def test_best_splits_prefers_full_waves():
+    from mmf_b200.engine import best_splits
+    assert best_splits(768, 768, 14592) >= 4      # 18 tiles -> needs split-K to fill 148 SMs
+    assert best_splits(3072, 768, 14592) >= 2
+    assert best_splits(128, 256, 64) == 1         # a single k-block cannot be split
+
+
+def test_additive_mask_shapes():
+    from mmf_b200.engine import additive_mask_2d
+    m4 = torch.zeros(2, 1, 1, 5)
+    assert tuple(additive_mask_2d(m4, 2, 5).shape) == (2, 5)
+    assert additive_mask_2d(None, 2, 5) is None
+    with pytest.raises(ValueError):
+        additive_mask_2d(torch.zeros(2, 1, 5, 5), 2, 5)
