@@ -161,10 +161,9 @@ def cpu_step_fn(B, p_drop):
         image_mask, vtype, att = O.visual_bert_masks(sl["input_mask"], sl["image_info_0"]["max_features"], R_REG)
         keep = None
         masks = None
-        if p_drop > 0:
-            keep = torch.rand(B, S_LEN, HID) >= p_drop
-            masks = [{"attn": torch.rand(B, HEADS, S_LEN, S_LEN) >= p_drop, "self_out": torch.rand(B, S_LEN, HID) >= p_drop,
-                      "out": torch.rand(B, S_LEN, HID) >= p_drop} for _ in range(LAYERS)]
+        if p_drop > 0:   # nn.Dropout-style RNG dropout at the reference's four sites per layer
+            keep = "rng"
+            masks = [{"attn": "rng", "self_out": "rng", "out": "rng"} for _ in range(LAYERS)]
         emb = O.visio_linguistic_embeddings(sl["input_ids"], sl["segment_ids"], sl["image_feature_0"], vtype, sd, "emb",
                                             keep=keep, p=p_drop)
         out = O.bert_encoder(emb, O.extended_attention_mask(att), sd, "encoder", LAYERS, HEADS, masks, p_drop, p_drop)
@@ -174,9 +173,22 @@ def cpu_step_fn(B, p_drop):
     return step
 
 
+def usable_cores():
+    """host threads this process may actually use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def run_cpu_arm(steps, warmup, B, p_drop):
     import torch
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     step = cpu_step_fn(B, p_drop)
     for _ in range(warmup):
@@ -200,6 +212,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="device-resident steps only (for ncu launch lists)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -268,23 +281,31 @@ def main():
     launches0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profile:
+        torch.cuda.profiler.start()    # ncu --profile-from-start off: capture exactly the timed steps
     e0.record()
     for _ in range(args.steps):
         step(dev_sl)
     e1.record()
     barrier()
+    if args.profile:
+        torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "launches": launches}))
+        return 0
     # ---------------- end-to-end timing (host inputs, loss read back) ----------------
     for _ in range(2):
-        float(step(to_device(host_sl, dev)))
+        float(step(to_device(host_sl, dev)).detach())
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
         loss = step(to_device(host_sl, dev))
-        _ = float(loss)            # D2H read of the step's result
+        _ = float(loss.detach())   # D2H read of the step's result
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)

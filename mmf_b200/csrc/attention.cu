@@ -264,7 +264,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
   uint8_t* sP = sCg + TILE;       // [128 x 128] bf16, 2 chunks of [128 x 128B]
   uint8_t* sDS = sP + 32768;
   float* sCol = reinterpret_cast<float*>(sDS + 32768);   // [2 buffers][2 stats][128] per-column statistics
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 512);
+  uint32_t* sBits = reinterpret_cast<uint32_t*>(sCol + 512);  // [2 buffers][128 cols][4 words] dropout keep bits
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBits + 1024);
   uint64_t* r_full = bars;
   uint64_t* c_full = bars + 1;
   uint64_t* s_ready = bars + 2;
@@ -389,7 +390,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         }
         sColA[row] = a;
         sColB[row] = bb;
+        if (!ROWS_ARE_Q && p.dmask != nullptr) {
+          // keys-as-rows orientation: this CTA needs, for every query column of the block, the 4 words covering its
+          // 128 key rows; staged once per block (coalesced 16-byte reads) instead of one global load per element
+          uint32_t* dst = sBits + (it & 1) * 512 + row * 4;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int wi = (row0 >> 5) + w;
+            dst[w] = (cidx < S_cols && wi < p.W) ? __ldg(p.dmask + (bh * p.Sq + cidx) * p.W + wi) : 0u;
+          }
+        }
       }
+      const uint32_t* sBitsCur = sBits + (it & 1) * 512;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // P/dS smem free again
       mbar_wait(s_ready, it & 1);
@@ -423,9 +435,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
           if (p.dmask != nullptr) {
             if (ROWS_ARE_Q) {
               keep = ((bits >> j) & 1u) ? p.dscale : 0.0f;
-            } else if (cidx < S_cols && rvalid) {
-              const uint32_t wv = __ldg(p.dmask + (bh * p.Sq + cidx) * p.W + (ridx >> 5));
-              keep = ((wv >> (ridx & 31)) & 1u) ? p.dscale : 0.0f;
+            } else {
+              const uint32_t wv = sBitsCur[cl * 4 + (row >> 5)];   // warp-uniform address: broadcast
+              keep = ((wv >> (row & 31)) & 1u) ? p.dscale : 0.0f;
             }
           }
           const float dp = __uint_as_float(rd[j]) * keep;
@@ -592,7 +604,7 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     count_launch();
   }
   constexpr int DC = D / 64;
-  const int smem = 4 * DC * 16384 + 2 * 32768 + 2048 + 128 + 1024;
+  const int smem = 4 * DC * 16384 + 2 * 32768 + 2048 + 4096 + 128 + 1024;
   AttnBwdDev p;
   p.B = a.B; p.H = a.heads; p.Sq = a.Sq; p.Skv = a.Skv;
   p.mask = a.mask; p.lse2 = a.lse2; p.delta = a.delta;

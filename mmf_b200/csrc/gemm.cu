@@ -9,9 +9,11 @@
 //                128 x BN x 16 per instruction, accumulating into one of two TMEM stages;
 //                tcgen05.commit releases smem slots (`empty[s]`) and publishes the accumulator
 //                (`tmem_full[a]`)
-//   warps 2..5 : epilogue - tcgen05.ld (thread == accumulator row), fused elementwise epilogue,
-//                bf16 results staged in swizzled smem and written with TMA stores (or fp32
-//                vector reductions for the split-K weight-gradient GEMM)
+//   warps 2..9 : epilogue - two sets of four warps (one warp per TMEM lane quarter) that take alternate
+//                64-column slices of the accumulator: tcgen05.ld (thread == accumulator row), fused
+//                elementwise epilogue, bf16 results staged in swizzled smem and written with TMA stores
+//                (or fp32 vector reductions for the split-K weight-gradient GEMM).  Eight warps because the
+//                GELU / GELU' epilogues are ALU-bound: two warps per scheduler hide each other's latency.
 // Double-buffered accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Operand layouts: each of A and B may be K-major (row-major [rows, K]) or MN-major (row-major
@@ -30,7 +32,7 @@ namespace mmfb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
 constexpr int STG_BYTES = 128 * 64 * 2;  // one 128-row x 64-col bf16 staging slice (SW128)
 
 struct GemmDev {
@@ -103,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 256);
     }
     fence_barrier_init();
   }
@@ -183,12 +185,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
-    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int set = (warp - 2) >> 2;        // 0: warps 2..5, 1: warps 6..9
     const int row = quarter * 32 + lane;    // accumulator row inside the tile
-    const bool store_thread = (threadIdx.x == 64);
+    const bool store_thread = (threadIdx.x == 64 + set * 128);
+    const int bar_id = 1 + set;
+    uint8_t* stg_set = stg + set * STG_BYTES;   // one staging slice per warp set
+    constexpr int NSL = BN / 64;            // 64-column slices per tile; this set owns slices sl with (sl & 1) == set
     int as = 0;
     uint32_t aph = 0;
-    int sbuf = 0;  // staging buffer toggle
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int t = u / p.splits;
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
@@ -200,7 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       if (EPI == EPI_ATOMIC_F32) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = set; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -222,21 +227,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_arrive(&tempty[as]);
       } else {
 #pragma unroll 1
-        for (int sl = 0; sl < BN / 64; ++sl) {  // 64-column slices
-          // the staging buffer we are about to overwrite must have been drained by its TMA store
-          if (store_thread) {
-            if (EPI == EPI_BIAS_GELU) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-          }
-          named_bar_sync(1, 128);
-          uint8_t* buf = stg + (EPI == EPI_BIAS_GELU ? 0 : sbuf) * STG_BYTES;
-          uint8_t* buf2 = stg + STG_BYTES;
+        for (int sl = set; sl < NSL; sl += 2) {  // 64-column slices of this warp set
+          // 1) everything that does not need the staging buffer: TMEM -> registers, fused math, bf16 packing.
+          //    The previous slice's TMA store drains the (single) staging buffer meanwhile.
+          uint32_t pk[32];                       // this thread's 64 output columns, packed bf16 pairs
+          uint32_t hk[EPI == EPI_BIAS_GELU ? 32 : 1];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
             tmem_ld32(t_row + sl * 64 + h * 32, r);
             tmem_ld_wait();
-            if (sl == BN / 64 - 1 && h == 1) {
-              // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+            if (sl + 2 >= NSL && h == 1) {
+              // this thread has drained its share of the accumulator: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               mbar_arrive(&tempty[as]);
             }
@@ -270,62 +272,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (EPI == EPI_BIAS_DROP_RESID || EPI == EPI_GELU_BWD || EPI == EPI_ADD_AUX) {
               if (p.aux != nullptr && row_ok && n < p.N) {
                 const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(m) * p.ldaux + n);
+                uint4 a4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a4[q] = (n + q * 8 < p.N) ? __ldg(ap + q) : make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  if (n + q * 8 < p.N) {
-                    uint4 a = __ldg(ap + q);
-                    float x[8];
-                    float2 f;
-                    f = unpack_bf16x2(a.x); x[0] = f.x; x[1] = f.y;
-                    f = unpack_bf16x2(a.y); x[2] = f.x; x[3] = f.y;
-                    f = unpack_bf16x2(a.z); x[4] = f.x; x[5] = f.y;
-                    f = unpack_bf16x2(a.w); x[6] = f.x; x[7] = f.y;
+                  float x[8];
+                  float2 f;
+                  f = unpack_bf16x2(a4[q].x); x[0] = f.x; x[1] = f.y;
+                  f = unpack_bf16x2(a4[q].y); x[2] = f.x; x[3] = f.y;
+                  f = unpack_bf16x2(a4[q].z); x[4] = f.x; x[5] = f.y;
+                  f = unpack_bf16x2(a4[q].w); x[6] = f.x; x[7] = f.y;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      if (EPI == EPI_GELU_BWD) v[q * 8 + e] *= gelu_erf_grad(x[e]);
-                      else v[q * 8 + e] += x[e];
-                    }
+                  for (int e = 0; e < 8; ++e) {
+                    if (EPI == EPI_GELU_BWD) v[q * 8 + e] *= gelu_erf_grad(x[e]);
+                    else v[q * 8 + e] += x[e];
                   }
                 }
               }
             }
-            // write this thread's 32 columns (64 bytes = four 16-byte chunks) into the swizzled slice
-            uint8_t* rowp = buf + row * 128;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int chunk = (h * 4 + q) ^ (row & 7);
-              uint4 o;
-              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
-            }
+            for (int j = 0; j < 16; ++j) pk[h * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             if (EPI == EPI_BIAS_GELU) {
-              uint8_t* rowp2 = buf2 + row * 128;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int chunk = (h * 4 + q) ^ (row & 7);
-                uint4 o;
-                o.x = pack_bf16x2(gelu_erf(v[q * 8 + 0]), gelu_erf(v[q * 8 + 1]));
-                o.y = pack_bf16x2(gelu_erf(v[q * 8 + 2]), gelu_erf(v[q * 8 + 3]));
-                o.z = pack_bf16x2(gelu_erf(v[q * 8 + 4]), gelu_erf(v[q * 8 + 5]));
-                o.w = pack_bf16x2(gelu_erf(v[q * 8 + 6]), gelu_erf(v[q * 8 + 7]));
-                *reinterpret_cast<uint4*>(rowp2 + chunk * 16) = o;
-              }
+              for (int j = 0; j < 16; ++j) hk[h * 16 + j] = pack_bf16x2(gelu_erf(v[2 * j]), gelu_erf(v[2 * j + 1]));
             }
           }
-          fence_proxy_async();
-          named_bar_sync(1, 128);
-          if (store_thread) {
-            const int nn = n0 + sl * 64;
-            if (nn < p.N) {
-              tma_store_2d(&tmC, buf, nn, m0);
-              if (EPI == EPI_BIAS_GELU) tma_store_2d(&tmC2, buf2, nn, m0);
+          // 2) stage + TMA store (C, then C2 for the GELU epilogue through the same buffer)
+#pragma unroll
+          for (int o = 0; o < (EPI == EPI_BIAS_GELU ? 2 : 1); ++o) {
+            if (store_thread) tma_store_wait_read<0>();   // the buffer's previous TMA store has finished reading it
+            named_bar_sync(bar_id, 128);
+            uint8_t* rowp = stg_set + row * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int chunk = q ^ (row & 7);
+              uint4 w4;
+              if (o == 0) w4 = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+              else w4 = make_uint4(hk[(q * 4) % (EPI == EPI_BIAS_GELU ? 32 : 1)], hk[(q * 4 + 1) % (EPI == EPI_BIAS_GELU ? 32 : 1)],
+                                   hk[(q * 4 + 2) % (EPI == EPI_BIAS_GELU ? 32 : 1)], hk[(q * 4 + 3) % (EPI == EPI_BIAS_GELU ? 32 : 1)]);
+              *reinterpret_cast<uint4*>(rowp + chunk * 16) = w4;
             }
-            tma_store_commit();
+            fence_proxy_async();
+            named_bar_sync(bar_id, 128);
+            if (store_thread) {
+              const int nn = n0 + sl * 64;
+              if (nn < p.N) tma_store_2d(o == 0 ? &tmC : &tmC2, stg_set, nn, m0);
+              tma_store_commit();
+            }
           }
-          sbuf ^= 1;
         }
       }
       if (++as == 2) { as = 0; aph ^= 1; }

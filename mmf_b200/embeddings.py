@@ -52,7 +52,7 @@ class _VLEmbedFn(torch.autograd.Function):
     """inputs: int32 index tensors (precomputed), region features [B*R, F] bf16; params via *params"""
 
     @staticmethod
-    def forward(ctx, runner, idx, dims, p_drop, training, feats, *params):
+    def forward(ctx, runner, idx, dims, p_drop, training, out_dtype, feats, *params):
         B, T, R, H = dims
         pk = runner.pack
         pk.refresh()
@@ -74,7 +74,7 @@ class _VLEmbedFn(torch.autograd.Function):
         ctx.saved = (fb, y, mean, rstd, bits, scale)
         ctx.feats_dtype = feats.dtype if feats is not None else None
         ctx.feats_shape = tuple(feats.shape) if feats is not None else None
-        return x.view(B, T + R, H)
+        return x.view(B, T + R, H).to(out_dtype)
 
     @staticmethod
     def backward(ctx, dout):
@@ -103,12 +103,12 @@ class _VLEmbedFn(torch.autograd.Function):
             F.colsum(dproj, proj_b.g)
             F.gemm(dproj, fb, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=proj_w.g,
                    splits=E.best_splits(proj_w.w.shape[0], proj_w.w.shape[1], B * R))
-            if ctx.needs_input_grad[5]:
+            if ctx.needs_input_grad[6]:
                 dfeats = F.gemm(dproj, proj_w.w, b_mn=True, epi=lib.EPI_BIAS).view(ctx.feats_shape).to(ctx.feats_dtype)
         ctx.saved = None
         if runner.grad_ready_hook is not None:
             runner.grad_ready_hook(0)
-        return (None, None, None, None, None, dfeats) + tuple(pk.autograd_grads(aliased))
+        return (None, None, None, None, None, None, dfeats) + tuple(pk.autograd_grads(aliased))
 
 
 class B200VisioLinguisticEmbeddings(nn.Module):
@@ -126,6 +126,7 @@ class B200VisioLinguisticEmbeddings(nn.Module):
         self.dropout = nn.Dropout(float(config.hidden_dropout_prob))
         self.projection = nn.Linear(config.visual_embedding_dim, H)
         _init_bert_weights(self, float(getattr(config, "initializer_range", 0.02)))
+        self.output_dtype = None
         self._runner = _EmbedRunner(
             [self.word_embeddings.weight, self.position_embeddings.weight, self.token_type_embeddings.weight,
              self.token_type_embeddings_visual.weight, self.position_embeddings_visual.weight],
@@ -168,5 +169,8 @@ class B200VisioLinguisticEmbeddings(nn.Module):
         R = visual_embeddings.shape[1] if use_img else 0
         idx = self.build_indices(input_ids, token_type_ids, visual_embeddings_type if use_img else None)
         feats = visual_embeddings if use_img else torch.zeros(0, device=input_ids.device)
+        # output dtype: the parameters' dtype like the reference; a trunk that feeds the B200 encoder directly sets
+        # `output_dtype = torch.bfloat16` to skip a bf16 -> fp32 -> bf16 round trip through HBM
+        out_dtype = self.output_dtype or self.word_embeddings.weight.dtype
         return _VLEmbedFn.apply(self._runner, idx, (B, T, R, self._runner.H), float(self.dropout.p), self.training,
-                                feats, *self._runner.pack.params)
+                                out_dtype, feats, *self._runner.pack.params)

@@ -37,6 +37,7 @@ class B200VisualBERTBase(nn.Module):
         super().__init__()
         self.config = config
         self.embeddings = B200VisioLinguisticEmbeddings(config)
+        self.embeddings.output_dtype = torch.bfloat16   # internal hand-over to the encoder stays bf16 in HBM
         self.encoder = B200BertEncoder(config)
         self.pooler = BertPooler(config.hidden_size)
         _init_bert_weights(self.pooler, float(getattr(config, "initializer_range", 0.02)))
@@ -57,7 +58,7 @@ class B200VisualBERTBase(nn.Module):
         emb = self.embeddings(input_ids, token_type_ids, visual_embeddings=visual_embeddings,
                               visual_embeddings_type=visual_embeddings_type,
                               image_text_alignment=image_text_alignment)
-        seq = self.encoder(emb, ext)[0]
+        seq = self.encoder(emb, ext)[0].to(next(self.pooler.parameters()).dtype)
         return seq, self.pooler(seq), []
 
 

@@ -45,8 +45,12 @@ def gelu_erf(x):
 
 
 def dropout(x, keep, p):
+    """keep: None (eval), a bool keep-mask (parity tests), or the string "rng" = draw like nn.Dropout does (used only
+    by the timed CPU baseline, where the reference's own fused dropout is the fair comparison)."""
     if keep is None or p == 0.0:
         return x
+    if isinstance(keep, str):
+        return F.dropout(x, p, True)
     return x * keep.to(x.dtype) / (1.0 - p)
 
 
