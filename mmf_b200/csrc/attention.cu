@@ -36,6 +36,8 @@ struct AttnFwdDev {
   const float* mask;      // [B, Skv] additive, or null
   bf16* ctx;              // [B*Sq, ldo]
   int64_t ldo;
+  float* ctx32;           // optional fp32 copy of ctx [B*Sq, H*D] (training): the backward's delta = rowsum(dO*O)
+                          // is taken from it, so bf16 rounding of O does not bias every dS of a row the same way
   float* lse2;            // [B, H, Sq]  log2-domain log-sum-exp of the scaled+masked scores
   const uint32_t* dmask;  // keep bits [B, H, Sq, W] (bit kv%32 of word kv/32) or null
   int W;
@@ -217,6 +219,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           o.z = pack_bf16x2(__uint_as_float(r[qd * 8 + 4]) * inv, __uint_as_float(r[qd * 8 + 5]) * inv);
           o.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * inv, __uint_as_float(r[qd * 8 + 7]) * inv);
           dst[qd] = o;
+        }
+        if (p.ctx32 != nullptr) {
+          float4* d32 = reinterpret_cast<float4*>(p.ctx32 + (static_cast<int64_t>(b) * p.Sq + q) * (p.H * D) + h * D + c * 32);
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd)
+            d32[qd] = make_float4(__uint_as_float(r[qd * 4 + 0]) * inv, __uint_as_float(r[qd * 4 + 1]) * inv,
+                                  __uint_as_float(r[qd * 4 + 2]) * inv, __uint_as_float(r[qd * 4 + 3]) * inv);
         }
       }
     }
@@ -506,7 +515,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d] : one warp per (token, head)
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
-                                  int64_t ld_o, float* __restrict__ delta, int B, int H, int Sq, int D) {
+                                  int64_t ld_o, const float* __restrict__ O32, float* __restrict__ delta, int B, int H,
+                                  int Sq, int D) {
   const int64_t gw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t total = static_cast<int64_t>(B) * Sq * H;
@@ -516,10 +526,19 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, co
   const bf16* a = dO + tok * ld_do + h * D;
   const bf16* o = O + tok * ld_o + h * D;
   float s = 0.0f;
-  for (int i = lane * 2; i < D; i += 64) {
-    const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
-    const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + i));
-    s += x.x * y.x + x.y * y.y;
+  if (O32 != nullptr) {
+    const float* o32 = O32 + tok * (static_cast<int64_t>(H) * D) + h * D;
+    for (int i = lane * 2; i < D; i += 64) {
+      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
+      const float2 y = *reinterpret_cast<const float2*>(o32 + i);
+      s += x.x * y.x + x.y * y.y;
+    }
+  } else {
+    for (int i = lane * 2; i < D; i += 64) {
+      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
+      const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + i));
+      s += x.x * y.x + x.y * y.y;
+    }
   }
   s = warp_sum(s);
   if (lane == 0) {
@@ -560,6 +579,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   p.mask = a.mask;
   p.ctx = reinterpret_cast<bf16*>(a.ctx); p.ldo = a.ldo;
   p.lse2 = a.lse2;
+  p.ctx32 = a.ctx32;
   p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
   p.scale2 = LOG2E / sqrtf(static_cast<float>(D));
   auto kern = attn_fwd_kernel<D>;
@@ -599,8 +619,8 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     const int threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
     attn_delta_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, a.delta, a.B,
-        a.heads, a.Sq, D);
+        reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, a.ctx32, a.delta,
+        a.B, a.heads, a.Sq, D);
     count_launch();
   }
   constexpr int DC = D / 64;
