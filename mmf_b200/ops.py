@@ -1,0 +1,130 @@
+"""Differentiable building blocks over the C-ABI kernels, for the front-ends around the encoder trunk
+(MMBT modal embeddings, MMFTransformer per-modality embeddings, ViLBERT image embeddings).
+
+Unlike the encoder/VisualBERT-embedding fast path (flat parameter pack, one autograd node per module), these are
+ordinary `torch.autograd.Function`s taking the parameters as inputs: the front-ends are a few percent of the block's
+FLOPs, so flexibility wins over launch count.  All arithmetic still runs in libmmfb200 kernels; activations bf16.
+"""
+import torch
+
+from . import functional as F
+from . import lib
+from .engine import best_splits
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM; backward: dgrad (MN-major W), split-K wgrad, column-sum bias gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xb, wb = _bf16(x), _bf16(weight)
+        bb = _bf16(bias) if bias is not None else None
+        y = F.gemm(xb, wb, epi=lib.EPI_BIAS, bias=bb)
+        ctx.save_for_backward(xb, wb)
+        ctx.dtypes = (x.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        dyb = dy.to(torch.bfloat16).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = F.gemm(dyb, wb, b_mn=True, epi=lib.EPI_BIAS).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(wb.shape, dtype=torch.float32, device=wb.device)
+            F.gemm(dyb, xb, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=dw,
+                   splits=best_splits(wb.shape[0], wb.shape[1], xb.shape[0]))
+            dw = dw.to(ctx.dtypes[1])
+        if ctx.dtypes[2] is not None and ctx.needs_input_grad[2]:
+            db = torch.zeros(wb.shape[0], dtype=torch.float32, device=wb.device)
+            F.colsum(dyb, db)
+            db = db.to(ctx.dtypes[2])
+        return dx, dw, db
+
+
+def linear(x2d, weight, bias=None):
+    """x2d [M, K] (any float dtype) -> bf16 [M, N].  K and N must be multiples of 8 (TMA row pitch)."""
+    return _Linear.apply(x2d, weight, bias)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        xb, g, b = _bf16(x), _bf16(weight), _bf16(bias)
+        y, mean, rstd = F.layernorm_fwd(xb, g, b, eps)
+        ctx.save_for_backward(xb, mean, rstd, g)
+        ctx.dtypes = (x.dtype, weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, mean, rstd, g = ctx.saved_tensors
+        dg = torch.zeros(g.shape, dtype=torch.float32, device=g.device)
+        db = torch.zeros_like(dg)
+        dx, _ = F.layernorm_bwd(dy.to(torch.bfloat16).contiguous(), xb, mean, rstd, g, dg, db)
+        return dx.to(ctx.dtypes[0]), dg.to(ctx.dtypes[1]), db.to(ctx.dtypes[2]), None
+
+
+def layer_norm(x2d, weight, bias, eps=1e-12):
+    return _LayerNorm.apply(x2d, weight, bias, eps)
+
+
+class _ComposeLN(torch.autograd.Function):
+    """out = dropout(LN(sum_k src_k[rows_k] + sum_k table_k[idx_k]))  - the embedding composer + LayerNorm.
+
+    inputs: n_src dense sources then n_tab tables then (ln_w, ln_b); index tensors are int32 [M] (negative = absent).
+    """
+
+    @staticmethod
+    def forward(ctx, meta, *tensors):
+        M, H, n_src, n_tab, rows, idxs, eps, bits, scale = meta
+        srcs = [_bf16(t) for t in tensors[:n_src]]
+        tabs = [_bf16(t) for t in tensors[n_src:n_src + n_tab]]
+        g, b = _bf16(tensors[-2]), _bf16(tensors[-1])
+        y = F.embed_compose(M, H, srcs=list(zip(srcs, rows)), tabs=list(zip(tabs, idxs)), device=g.device)
+        x, mean, rstd = F.layernorm_fwd(y, g, b, eps, drop_mask=bits, drop_scale=scale)
+        ctx.meta = meta
+        ctx.src_shapes = [tuple(t.shape) for t in srcs]
+        ctx.tab_shapes = [tuple(t.shape) for t in tabs]
+        ctx.dtypes = [t.dtype for t in tensors]
+        ctx.save_for_backward(y, mean, rstd, g)
+        return x
+
+    @staticmethod
+    def backward(ctx, dout):
+        M, H, n_src, n_tab, rows, idxs, eps, bits, scale = ctx.meta
+        y, mean, rstd, g = ctx.saved_tensors
+        d = dout.to(torch.bfloat16).contiguous()
+        if bits is not None:   # dropout sits after the LayerNorm
+            d = (d * F.unpack_keep_bits(bits, H) * scale).to(torch.bfloat16)
+        dg = torch.zeros(H, dtype=torch.float32, device=g.device)
+        db = torch.zeros_like(dg)
+        dy, _ = F.layernorm_bwd(d, y, mean, rstd, g, dg, db)
+        dsrcs = [torch.zeros(s, dtype=torch.bfloat16, device=g.device) for s in ctx.src_shapes]
+        dtabs = [torch.zeros(s, dtype=torch.float32, device=g.device) for s in ctx.tab_shapes]
+        F.embed_scatter(dy, dsrcs=list(zip(dsrcs, rows)), dtabs=list(zip(dtabs, idxs)))
+        grads = [t.to(dt) for t, dt in zip(dsrcs + dtabs + [dg, db], ctx.dtypes)]
+        return (None,) + tuple(grads)
+
+
+def compose_ln(M, H, srcs, tabs, ln_weight, ln_bias, eps=1e-12, p=0.0, training=False, dropout_state=None):
+    """srcs: up to 2 (tensor [*, H], int32 rows [M]); tabs: up to 3 (table [V, H], int32 idx [M]).
+    The same table may appear in several slots.  Returns bf16 [M, H]."""
+    if len(srcs) > 2 or len(tabs) > 3:
+        raise ValueError("compose_ln: at most 2 dense sources and 3 table slots")
+    bits, scale = None, 1.0
+    if training and p > 0.0:
+        from .modules import _fresh_dropout_state
+        ds = dropout_state or _fresh_dropout_state()
+        bits, scale = ds.bits((M,), H, p, ln_weight.device), 1.0 / (1.0 - p)
+    meta = (M, H, len(srcs), len(tabs), [r for _, r in srcs], [i for _, i in tabs], float(eps), bits, scale)
+    return _ComposeLN.apply(meta, *[t for t, _ in srcs], *[t for t, _ in tabs], ln_weight, ln_bias)
+
+
+def i32(t):
+    return t.reshape(-1).to(torch.int32).contiguous()

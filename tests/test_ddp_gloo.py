@@ -1,0 +1,73 @@
+"""world_size=2 gloo test of the gradient-bucket logic in mmf_b200.ddp on CPU: the flat gradient buffers of the two
+ranks end up equal to their mean, bucket slices cover the buffer exactly once, no_sync() skips communication.
+(No kernels run: gradients are written into the flat buffer by hand, the way the weight-gradient GEMMs do on the GPU.)"""
+import os
+import types
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, result):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmf_b200.ddp import B200DataParallel
+        from mmf_b200.engine import BertLayerW, ParamPack
+        from mmf_b200.modules import B200BertEncoder
+        torch.manual_seed(rank)   # different init per rank: the wrapper must broadcast rank 0's parameters
+        cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=3,
+                                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12)
+        enc = B200BertEncoder(cfg)
+        runner = enc._runner
+        # build the pack on CPU by hand (ensure() insists on CUDA)
+        params = []
+        for m in runner.layers:
+            params += BertLayerW.params(m)
+        runner.pack = ParamPack(params, "cpu")
+        per = len(BertLayerW.params(runner.layers[0]))
+        runner.layer_param_ranges = [(runner.pack.offsets[i * per], 0) for i in range(3)]
+        ddp = B200DataParallel(enc, bucket_bytes=1, overlap=False)
+        p0 = torch.cat([p.detach().reshape(-1) for p in enc.parameters()])
+        gathered = [torch.zeros_like(p0) for _ in range(world)]
+        dist.all_gather(gathered, p0)
+        assert torch.equal(gathered[0], gathered[1])                      # parameters were broadcast
+        # emulate a backward: layer 2, 1, 0 complete in turn
+        runner.pack.grad.copy_(torch.arange(runner.pack.total, dtype=torch.float32) * (rank + 1))
+        sent = []
+        orig = ddp._avg
+
+        def spy(flat):
+            sent.append((flat.data_ptr() - runner.pack.grad.data_ptr()) // 4)
+            sent.append(flat.numel())
+            orig(flat)
+        ddp._avg = spy
+        ddp._queue_finalize = lambda: None
+        for i in (2, 1, 0):
+            runner.grad_ready_hook(i)
+        expect = torch.arange(runner.pack.total, dtype=torch.float32) * 1.5
+        assert torch.allclose(runner.pack.grad, expect)
+        offs, lens = sent[0::2], sent[1::2]
+        assert sum(lens) == runner.pack.total and sorted(offs) == sorted(set(offs))   # every element sent exactly once
+        # no_sync: nothing is sent
+        sent.clear()
+        ddp._state.clear()
+        with ddp.no_sync():
+            for i in (2, 1, 0):
+                runner.grad_ready_hook(i)
+        assert not sent
+        ddp.reduce_now()
+        assert torch.allclose(runner.pack.grad, expect)
+        result[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucket_allreduce_world2():
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_worker, args=(2, port, result), nprocs=2, join=True)
+    assert result.get(0) and result.get(1)

@@ -106,3 +106,39 @@ def test_additive_mask_shapes():
     assert additive_mask_2d(None, 2, 5) is None
     with pytest.raises(ValueError):
         additive_mask_2d(torch.zeros(2, 1, 5, 5), 2, 5)
+
+
+def test_registry_and_sample_list_shims():
+    from mmf_b200.registry import registry
+    from mmf_b200.sample import SampleList
+    import mmf_b200.mmft_backend  # noqa: F401  (registers "b200")
+    assert registry.get_transformer_backend_class("b200").__name__ == "B200TransformerBackend"
+    assert registry.get_transformer_backend_class("nope") is None
+    sl = SampleList()
+    sl.input_ids = torch.zeros(3, 4, dtype=torch.long)
+    sl["image_info_0"] = {"max_features": torch.tensor([1, 2, 3])}
+    assert sl.get_batch_size() == 3 and sl.fields() == ["input_ids", "image_info_0"]
+    moved = sl.to("cpu")
+    assert torch.equal(moved.image_info_0["max_features"], torch.tensor([1, 2, 3]))
+    with pytest.raises(AttributeError):
+        sl.missing
+
+
+def test_patch_and_undo_restore_forward():
+    from transformers.models.bert.modeling_bert import BertEncoder
+    from mmf_b200.patch import replace_with_b200, undo_replace_with_b200
+    orig = BertEncoder.forward
+    replace_with_b200()
+    assert BertEncoder.forward is not orig
+    undo_replace_with_b200()
+    assert BertEncoder.forward is orig
+
+
+def test_mmbt_token_surgery_matches_reference_golden_cpu():
+    """integer path of MMBTBase.extract_modal_end_token is pure torch integer code: bit-exact on CPU too"""
+    from mmf_b200.mmbt import extract_modal_end_token
+    g = torch.load(os.path.join(GOLD, "mmbt.pt"), weights_only=False)
+    sl = {"input_ids": g["ids"].clone(), "input_mask": g["mask"].clone()}
+    end = extract_modal_end_token(sl)
+    assert torch.equal(end, g["end_token"])
+    assert torch.equal(sl["input_ids"], g["shifted_ids"]) and torch.equal(sl["input_mask"], g["shifted_mask"])
