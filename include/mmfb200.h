@@ -146,6 +146,12 @@ typedef struct {
 } mmfb_scatter_args;
 int mmfb_embed_scatter(const mmfb_scatter_args* args, mmfb_stream stream);
 
+/* table gradient with run aggregation: `sorted_idx` = the table indices in ascending order (negative = skip),
+ * `order[k]` = the row of dy that sorted position k came from.  dtab[sorted_idx[k]] += dy[order[k]].
+ * Equal indices are summed in registers first (one atomic per run of <= 32 rows instead of one per row). */
+int mmfb_embed_scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int32_t* sorted_idx, float* dtab,
+                              int M, int H, mmfb_stream stream);
+
 /* fp32 -> bf16 cast of a flat (parameter) buffer */
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream);
 

@@ -90,8 +90,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   } else {
+    // additive mask in the log2 domain; padded key columns get -inf so that exp2 yields exactly 0 without any
+    // per-element bounds test in the softmax loops
     for (int i = threadIdx.x; i < SK; i += 128)
-      sMask[i] = (i < p.Skv && p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f;
+      sMask[i] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -148,16 +150,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(s_ready, 0);
     tc_fence_after();
     float mx = -INFINITY;
+    const float4* sMask4 = reinterpret_cast<const float4*>(sMask);
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
       uint32_t r[32];
       tmem_ld32(trow + c * 32, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = c * 32 + j;
-        const float t = fmaf(__uint_as_float(r[j]), p.scale2, sMask[col < SK ? col : 0]);
-        if (col < p.Skv) mx = fmaxf(mx, t);
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 m = sMask4[c * 8 + q4];
+        mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 0]), p.scale2, m.x));
+        mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 1]), p.scale2, m.y));
+        mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 2]), p.scale2, m.z));
+        mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 3]), p.scale2, m.w));
       }
     }
     float sum = 0.0f;
@@ -174,12 +179,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         const uint32_t bits = dm ? __ldg(dm + c) : 0xFFFFFFFFu;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = c * 32 + j;
-          const float t = fmaf(__uint_as_float(r[j]), p.scale2, sMask[col < SK ? col : 0]);
-          const float ev = (col < p.Skv) ? exp2f(t - mx) : 0.0f;
-          sum += ev;
-          e[j] = ((bits >> j) & 1u) ? ev : 0.0f;
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 m = sMask4[c * 8 + q4];
+          const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = q4 * 4 + k;
+            const float ev = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale2, mm[k]) - mx);   // 0 for padded columns
+            sum += ev;
+            e[j] = ((bits >> j) & 1u) ? ev : 0.0f;
+          }
         }
       } else {
 #pragma unroll
@@ -258,7 +267,7 @@ struct AttnBwdDev {
 // rows: the operand pair that stays resident (R, Rg); cols: the looped pair (C, Cg)
 //   ROWS_ARE_Q :  R = Q_i, Rg = dO_i ; C = K_j, Cg = V_j ;  out0 = dQ_i = scale * sum_j dS' C
 //   !ROWS_ARE_Q:  R = K_j, Rg = V_j  ; C = Q_i, Cg = dO_i;  out0 = dK_j = scale * sum_i dS' C ; out1 = dV_j = sum_i P' Cg
-template <int D, bool ROWS_ARE_Q>
+template <int D, bool ROWS_ARE_Q, bool DROP>
 __global__ void __launch_bounds__(160, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRg,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCg, AttnBwdDev p) {
@@ -373,11 +382,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const int64_t bh = static_cast<int64_t>(b) * p.H + h;
     // per-row scalars
-    float rowA = 0.0f, rowB = 0.0f;
+    // validity is folded into the statistics so the inner loop needs no bounds tests: an invalid query gets
+    // lse = +inf, an invalid key gets mask = -inf; either way exp2(t - lse) = 0 exactly
+    float rowA, rowB = 0.0f;
     if (ROWS_ARE_Q) {
+      rowA = INFINITY;
       if (rvalid) { rowA = p.lse2[bh * p.Sq + ridx]; rowB = p.delta[bh * p.Sq + ridx]; }
     } else {
-      rowA = (rvalid && p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + ridx] * LOG2E : 0.0f;
+      rowA = rvalid ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + ridx] * LOG2E : 0.0f) : -INFINITY;
     }
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
@@ -388,7 +400,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
       float* sColB = sColA + 128;
       {
         const int cidx = col0 + row;
-        float a = 0.0f, bb = 0.0f;
+        float a = ROWS_ARE_Q ? -INFINITY : INFINITY, bb = 0.0f;
         if (cidx < S_cols) {
           if (ROWS_ARE_Q) {
             a = (p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + cidx] * LOG2E : 0.0f;
@@ -399,7 +411,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         }
         sColA[row] = a;
         sColB[row] = bb;
-        if (!ROWS_ARE_Q && p.dmask != nullptr) {
+        if (!ROWS_ARE_Q && DROP) {
           // keys-as-rows orientation: this CTA needs, for every query column of the block, the 4 words covering its
           // 128 key rows; staged once per block (coalesced 16-byte reads) instead of one global load per element
           uint32_t* dst = sBits + (it & 1) * 512 + row * 4;
@@ -423,35 +435,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         tmem_ld_wait();
         float pv[32], ds[32];
         uint32_t bits = 0xFFFFFFFFu;
-        if (ROWS_ARE_Q && p.dmask != nullptr && rvalid) {
+        if (ROWS_ARE_Q && DROP && rvalid) {
           const int w = (col0 >> 5) + c;
           if (w < p.W) bits = __ldg(p.dmask + (bh * p.Sq + ridx) * p.W + w);
         }
+        const float4* cA4 = reinterpret_cast<const float4*>(sColA) + c * 8;
+        const float4* cB4 = reinterpret_cast<const float4*>(sColB) + c * 8;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int cl = c * 32 + j;
-          const int cidx = col0 + cl;
-          float t, l2, dl;
-          if (ROWS_ARE_Q) {
-            t = fmaf(__uint_as_float(rs[j]), p.scale2, sColA[cl]);
-            l2 = rowA; dl = rowB;
-          } else {
-            t = fmaf(__uint_as_float(rs[j]), p.scale2, rowA);
-            l2 = sColA[cl]; dl = sColB[cl];
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 ca = cA4[q4];
+          const float ca_[4] = {ca.x, ca.y, ca.z, ca.w};
+          float cb_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          if (!ROWS_ARE_Q) {
+            const float4 cb = cB4[q4];
+            cb_[0] = cb.x; cb_[1] = cb.y; cb_[2] = cb.z; cb_[3] = cb.w;
           }
-          float pr = (cidx < S_cols && rvalid) ? exp2f(t - l2) : 0.0f;
-          float keep = 1.0f;
-          if (p.dmask != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = q4 * 4 + k;
+            const int cl = c * 32 + j;
+            float pr, dl;
             if (ROWS_ARE_Q) {
-              keep = ((bits >> j) & 1u) ? p.dscale : 0.0f;
+              pr = ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale2, ca_[k]) - rowA);
+              dl = rowB;
             } else {
-              const uint32_t wv = sBitsCur[cl * 4 + (row >> 5)];   // warp-uniform address: broadcast
-              keep = ((wv >> (row & 31)) & 1u) ? p.dscale : 0.0f;
+              pr = ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale2, rowA) - ca_[k]);
+              dl = cb_[k];
             }
+            float dp = __uint_as_float(rd[j]);
+            float pk = pr;
+            if (DROP) {
+              bool kp;
+              if (ROWS_ARE_Q) kp = (bits >> j) & 1u;
+              else kp = (sBitsCur[cl * 4 + (row >> 5)] >> (row & 31)) & 1u;   // warp-uniform address: broadcast
+              dp = kp ? dp * p.dscale : 0.0f;
+              pk = kp ? pr * p.dscale : 0.0f;
+            }
+            ds[j] = pr * (dp - dl);
+            pv[j] = pk;
           }
-          const float dp = __uint_as_float(rd[j]) * keep;
-          ds[j] = pr * (dp - dl);
-          pv[j] = pr * keep;
         }
         uint8_t* dsrow = sDS + (c >> 1) * 16384 + row * 128;
         uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
@@ -632,30 +654,34 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   p.scale = 1.0f / sqrtf(static_cast<float>(D));
   p.scale2 = LOG2E * p.scale;
   {
-    auto kern = attn_bwd_kernel<D, true>;
     static bool set = false;
     if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_bwd_kernel<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(dq) smem attr: %s", cudaGetErrorString(e));
       set = true;
     }
     p.out0 = reinterpret_cast<bf16*>(a.dq); p.ld0 = a.ld_dq; p.out1 = nullptr; p.ld1 = 0;
     dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
-    kern<<<grid, 160, smem, stream>>>(tmQ, tmdO, tmK, tmV, p);
+    if (p.dmask != nullptr) attn_bwd_kernel<D, true, true><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmK, tmV, p);
+    else attn_bwd_kernel<D, true, false><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmK, tmV, p);
     count_launch();
   }
   {
-    auto kern = attn_bwd_kernel<D, false>;
     static bool set = false;
     if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_bwd_kernel<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(dkv) smem attr: %s", cudaGetErrorString(e));
       set = true;
     }
     p.out0 = reinterpret_cast<bf16*>(a.dk); p.ld0 = a.ld_dk;
     p.out1 = reinterpret_cast<bf16*>(a.dv); p.ld1 = a.ld_dv;
     dim3 grid((a.Skv + 127) / 128, a.heads, a.B);
-    kern<<<grid, 160, smem, stream>>>(tmK, tmV, tmQ, tmdO, p);
+    if (p.dmask != nullptr) attn_bwd_kernel<D, false, true><<<grid, 160, smem, stream>>>(tmK, tmV, tmQ, tmdO, p);
+    else attn_bwd_kernel<D, false, false><<<grid, 160, smem, stream>>>(tmK, tmV, tmQ, tmdO, p);
     count_launch();
   }
   cudaError_t e = cudaGetLastError();

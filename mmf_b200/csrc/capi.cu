@@ -166,6 +166,12 @@ int mmfb_embed_scatter(const mmfb_scatter_args* args, mmfb_stream stream) {
   MMFB_REQUIRE_DEVICE();
   return scatter(*args, reinterpret_cast<cudaStream_t>(stream));
 }
+int mmfb_embed_scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int32_t* sorted_idx, float* dtab,
+                              int M, int H, mmfb_stream stream) {
+  if (!dy || !order || !sorted_idx || !dtab) return set_error(MMFB_ERR_ARG, "mmfb_embed_scatter_sorted: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return scatter_sorted(dy, lddy, order, sorted_idx, dtab, M, H, reinterpret_cast<cudaStream_t>(stream));
+}
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream) {
   if (!in || !out) return set_error(MMFB_ERR_ARG, "mmfb_cast_f32_bf16: null pointer");
   MMFB_REQUIRE_DEVICE();

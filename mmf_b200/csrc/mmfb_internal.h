@@ -40,5 +40,7 @@ int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, 
 int compose(const mmfb_compose_args& a, cudaStream_t s);
 int scatter(const mmfb_scatter_args& a, cudaStream_t s);
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s);
+int scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int32_t* sorted_idx, float* dtab, int M,
+                   int H, cudaStream_t s);
 
 }  // namespace mmfb

@@ -187,6 +187,117 @@ ln_bwd_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict_
   }
 }
 
+// Row-only LayerNorm backward (no column statistics): few registers, high occupancy.  dy, dz as above.
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_bwd_rows_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
+                   const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
+                   bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
+                   int M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float mu = mean[row], rs = rstd[row];
+  float dg[NV][8], xh[NV][8];
+  float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+      float d[8], yy[8], g[8];
+      ld8(dx + row * lddx + col, d);
+      if (dx2 != nullptr) {
+        float t[8];
+        ld8(dx2 + row * lddx2 + col, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += t[e];
+      }
+      ld8(y + row * ldy + col, yy);
+      ld8(gamma + col, g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[i][e] = (yy[e] - mu) * rs;
+        dg[i][e] = d[e] * g[e];
+        s1 += dg[i][e];
+        s2 += dg[i][e] * xh[i][e];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    if (col < H) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rs * (dg[i][e] - s1 - xh[i][e] * s2);
+      if (dy != nullptr) st8(dy + row * lddy + col, o);
+      if (dmask != nullptr) {
+        const uint32_t w = __ldg(dmask + row * ldmask + (col >> 5));
+        const uint32_t bits = (w >> (col & 31)) & 0xFFu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = ((bits >> e) & 1u) ? o[e] * dscale : 0.0f;
+        st8(dz + row * lddz + col, o);
+      } else if (dz != nullptr && dz != dy) {
+        st8(dz + row * lddz + col, o);
+      }
+    }
+  }
+}
+
+// Column statistics of the LayerNorm backward: dgamma += sum_r d*xhat, dbeta += sum_r d, dbias += sum_r dz, with
+// d = dx (+dx2).  Same access pattern as colsum: each thread owns 8 columns for a strided set of rows.
+__global__ void __launch_bounds__(256)
+ln_bwd_cols_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
+                   const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const bf16* __restrict__ dz, int64_t lddz,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float ag[8], ab[8], az[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { ag[e] = 0.0f; ab[e] = 0.0f; az[e] = 0.0f; }
+  if (col < H) {
+    for (int64_t row = static_cast<int64_t>(blockIdx.y) * 8 + warp; row < M; row += static_cast<int64_t>(gridDim.y) * 8) {
+      const float mu = mean[row], rs = rstd[row];
+      float d[8], yy[8];
+      ld8(dx + row * lddx + col, d);
+      if (dx2 != nullptr) {
+        float t[8];
+        ld8(dx2 + row * lddx2 + col, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += t[e];
+      }
+      ld8(y + row * ldy + col, yy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { ag[e] += d[e] * (yy[e] - mu) * rs; ab[e] += d[e]; }
+      if (dbias != nullptr) {
+        float z[8];
+        ld8(dz + row * lddz + col, z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) az[e] += z[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = which == 0 ? ag[e] : (which == 1 ? ab[e] : az[e]);
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < H) atomicAdd(dst + c, t);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // column sums (bias gradients):  out[n] += sum_m X[m, n]
 // ----------------------------------------------------------------------------------------------
@@ -320,6 +431,56 @@ scatter_kernel(ScatterDev c, const bf16* __restrict__ dy, int64_t lddy, int M, i
   }
 }
 
+// Table-gradient scatter over SORTED indices: warp w owns sorted positions [32w, 32w+32); rows with equal index are
+// summed in registers and flushed with one atomic per column per run, so an index shared by thousands of rows (type /
+// position embeddings) costs M/32 atomics per address instead of M.
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+scatter_sorted_kernel(const bf16* __restrict__ dy, int64_t lddy, const int32_t* __restrict__ order,
+                      const int32_t* __restrict__ sorted_idx, float* __restrict__ dtab, int M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
+  const int64_t p0 = w * 32;
+  if (p0 >= M) return;
+  float acc[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.0f;
+  int cur = -1;
+  const int n = (M - p0) < 32 ? static_cast<int>(M - p0) : 32;
+  for (int k = 0; k <= n; ++k) {
+    const int id = (k < n) ? sorted_idx[p0 + k] : -2;
+    if (id != cur) {
+      if (cur >= 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int col = i * 256 + lane * 8;
+          if (col < H) {
+            float* d = dtab + static_cast<int64_t>(cur) * H + col;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { atomicAdd(d + e, acc[i][e]); acc[i][e] = 0.0f; }
+          }
+        }
+      }
+      cur = id;
+    }
+    if (k < n && id >= 0) {
+      const int64_t r = order[p0 + k];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = i * 256 + lane * 8;
+        if (col < H) {
+          float t[8];
+          ld8(dy + r * lddy + col, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[i][e] += t[e];
+        }
+      }
+    }
+  }
+}
+
 // fp32 -> bf16 cast of the flat parameter buffer (done every forward, like autocast does)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
@@ -369,6 +530,35 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   if (rc) return rc;
   if (!a.dx || !a.y || !a.mean || !a.rstd || !a.gamma) return set_error(MMFB_ERR_ARG, "layernorm_bwd: null pointer");
   if (a.drop_mask && !a.dz) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dropout mask given without dz");
+  const int nv_ = (a.H + 255) / 256;
+  if (nv_ <= 4) {
+    // two kernels: a light row kernel (dy, dz) at high occupancy, then coalesced column statistics
+    const bool need_dz_buf = (a.drop_mask != nullptr) || (a.dz != nullptr && a.dz != a.dy);
+    const int rgrid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
+#define LN_ROWS(NV)                                                                                              \
+  ln_bwd_rows_kernel<NV><<<rgrid, ROW_WARPS * 32, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, \
+                                                          (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
+                                                          (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, \
+                                                          a.drop_scale, a.M, a.H)
+    if (nv_ <= 1) LN_ROWS(1); else if (nv_ == 2) LN_ROWS(2); else if (nv_ == 3) LN_ROWS(3); else LN_ROWS(4);
+#undef LN_ROWS
+    rc = launch_ok("layernorm_bwd(rows)");
+    if (rc) return rc;
+    if (a.dgamma || a.dbeta || a.dbias) {
+      const void* dzp = need_dz_buf ? a.dz : a.dy;
+      const int64_t lddz = need_dz_buf ? a.lddz : a.lddy;
+      if (a.dbias && !dzp) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dbias needs dy or dz to be materialised");
+      dim3 cgrid((a.H + 255) / 256, 1);
+      int rb = (a.M + 63) / 64;
+      const int cap2 = (num_sms() * 4 + cgrid.x - 1) / cgrid.x;
+      cgrid.y = rb < cap2 ? rb : cap2;
+      if (cgrid.y < 1) cgrid.y = 1;
+      ln_bwd_cols_kernel<<<cgrid, 256, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy,
+                                               a.mean, a.rstd, (const bf16*)dzp, lddz, a.dgamma, a.dbeta, a.dbias, a.M, a.H);
+      return launch_ok("layernorm_bwd(cols)");
+    }
+    return MMFB_OK;
+  }
   int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
   const int cap = num_sms() * 2;
   if (grid > cap) grid = cap;
@@ -422,6 +612,20 @@ int scatter(const mmfb_scatter_args& a, cudaStream_t s) {
   for (int k = 0; k < 3; ++k) { c.dtab[k] = a.dtab[k]; c.tidx[k] = a.tab_idx[k]; }
   scatter_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(c, (const bf16*)a.dy, a.lddy, a.M, a.H);
   return launch_ok("embed_scatter");
+}
+
+int scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int32_t* sorted_idx, float* dtab, int M,
+                   int H, cudaStream_t s) {
+  int rc = check_rows(M, H, "embed_scatter_sorted");
+  if (rc) return rc;
+  if (H > 1024) return set_error(MMFB_ERR_ARG, "embed_scatter_sorted: hidden size %d > 1024", H);
+  const int warps = (M + 31) / 32;
+  const int grid = (warps + ROW_WARPS - 1) / ROW_WARPS;
+  const int nv = (H + 255) / 256;
+#define SS(NV) scatter_sorted_kernel<NV><<<grid, ROW_WARPS * 32, 0, s>>>((const bf16*)dy, lddy, order, sorted_idx, dtab, M, H)
+  if (nv <= 1) SS(1); else if (nv == 2) SS(2); else if (nv == 3) SS(3); else SS(4);
+#undef SS
+  return launch_ok("embed_scatter_sorted");
 }
 
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s) {

@@ -96,8 +96,12 @@ class _VLEmbedFn(torch.autograd.Function):
         if R > 0:
             dproj = torch.empty(B * R, H, dtype=torch.bfloat16, device=pk.device)
             dsrcs = ((dproj, idx["src_row"]),)
-        F.embed_scatter(dy, dsrcs=dsrcs, dtabs=((runner.big_g, idx["i0"]), (runner.big_g, idx["i1"]),
-                                                (runner.big_g, idx["i2"])))
+        if dsrcs:
+            F.embed_scatter(dy, dsrcs=dsrcs)
+        for k in ("i0", "i1", "i2"):
+            if k + "_sorted" not in idx:      # indices are known in the forward; sorted lazily once per batch
+                idx[k + "_sorted"] = F.sort_indices(idx[k])
+            F.embed_scatter_sorted(dy, runner.big_g, *idx[k + "_sorted"])
         dfeats = None
         if R > 0:
             F.colsum(dproj, proj_b.g)

@@ -263,6 +263,21 @@ def embed_scatter(dy, dsrcs=(), dtabs=()):
     check(LIB.mmfb_embed_scatter(ctypes.byref(a), _stream_ptr()))
 
 
+def sort_indices(idx):
+    """(sorted_idx, order) int32 for embed_scatter_sorted; a stable device sort of the [M] index vector."""
+    sorted_idx, order = torch.sort(idx.to(torch.int64), stable=True)
+    return sorted_idx.to(torch.int32).contiguous(), order.to(torch.int32).contiguous()
+
+
+def embed_scatter_sorted(dy, dtab, sorted_idx, order):
+    """dtab[sorted_idx[k]] += dy[order[k]] with run aggregation (fp32 table gradient)."""
+    _req(dy, torch.bfloat16, "dy"); _req(dtab, torch.float32, "dtab")
+    _req(sorted_idx, torch.int32, "sorted_idx"); _req(order, torch.int32, "order")
+    M, H = dy.shape
+    check(LIB.mmfb_embed_scatter_sorted(dy.data_ptr(), dy.stride(0), order.data_ptr(), sorted_idx.data_ptr(),
+                                        dtab.data_ptr(), M, H, _stream_ptr()))
+
+
 def unpack_keep_bits(words, n):
     """int32 [..., W] -> bool [..., n] (test helper / oracle interop; runs on the words' device)."""
     w = words.to(torch.int64) & 0xFFFFFFFF

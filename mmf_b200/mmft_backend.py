@@ -63,9 +63,10 @@ class B200HuggingfaceEmbeddings(nn.Module):
             if _get(m, "type") == "text":
                 self.token_embeddings[idx] = transformer.embeddings.word_embeddings
                 self.layer_norms[idx] = transformer.embeddings.LayerNorm
-            src = transformer.embeddings.position_embeddings.weight.data
-            n = min(src.shape[0], self.pos_embeddings[idx].weight.shape[0])
-            self.pos_embeddings[idx].weight.data[:n].copy_(deepcopy(src[:n]))
+            # the reference REPLACES the table with a copy of the transformer's (so its shape becomes
+            # [max_position_embeddings, H] whatever position_dim said) - huggingface.py:109-112
+            self.pos_embeddings[idx].weight = nn.Parameter(
+                deepcopy(transformer.embeddings.position_embeddings.weight.data), requires_grad=True)
         tv = transformer.embeddings.token_type_embeddings.weight.shape[0]
         n = min(tv, len(mods))
         self.token_type_embeddings.weight.data[:n].copy_(transformer.embeddings.token_type_embeddings.weight.data[:n])

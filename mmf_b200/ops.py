@@ -107,7 +107,10 @@ class _ComposeLN(torch.autograd.Function):
         dy, _ = F.layernorm_bwd(d, y, mean, rstd, g, dg, db)
         dsrcs = [torch.zeros(s, dtype=torch.bfloat16, device=g.device) for s in ctx.src_shapes]
         dtabs = [torch.zeros(s, dtype=torch.float32, device=g.device) for s in ctx.tab_shapes]
-        F.embed_scatter(dy, dsrcs=list(zip(dsrcs, rows)), dtabs=list(zip(dtabs, idxs)))
+        if dsrcs:
+            F.embed_scatter(dy, dsrcs=list(zip(dsrcs, rows)))
+        for t, ix in zip(dtabs, idxs):
+            F.embed_scatter_sorted(dy, t, *F.sort_indices(ix))
         grads = [t.to(dt) for t, dt in zip(dsrcs + dtabs + [dg, db], ctx.dtypes)]
         return (None,) + tuple(grads)
 
