@@ -88,8 +88,10 @@ class B200DataParallel(nn.Module):
                     per_step.append(runner.pack.offsets[idx])
                     mods = {"t": runner.layer, "v": runner.v_layer, "c": runner.c_layer}[kind]
                     idx += len((ConnectionW if kind == "c" else BertLayerW).params(mods[i]))
-            else:
+            elif hasattr(runner, "layer_param_ranges"):
                 per_step = [r[0] for r in runner.layer_param_ranges]
+            else:                             # single-step runners (embedding front-end): one bucket
+                per_step = [0]
             runner.step_offsets = per_step
             ranges = per_step
         return ranges[step_index]
