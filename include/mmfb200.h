@@ -62,6 +62,7 @@ typedef struct {
   int epi;
   int splits;                    /* split-K factor, MMFB_EPI_ATOMIC_F32 only (0/1 = none) */
   int block_n;                   /* 0 = auto, else 128 or 256 */
+  int cluster;                   /* 0 = library default, 1 = single CTA, 2 = 2-CTA cluster sharing the B tile by TMA multicast */
 } mmfb_gemm_args;
 
 int mmfb_gemm(const mmfb_gemm_args* args, mmfb_stream stream);

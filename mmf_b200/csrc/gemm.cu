@@ -25,6 +25,8 @@
 // mmf/modules/hf_layers.py:169-180 (Q,K,V), HF BertSelfOutput/BertIntermediate/BertOutput invoked at
 // hf_layers.py:248,289-290, mmf/models/vilbert.py:77-79,127,144-145,396-412,504-509 and their
 // autograd backward (mmf/trainers/core/training_loop.py:211-213).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mmfb_internal.h"
 
@@ -48,11 +50,12 @@ struct GemmDev {
   float dscale;          // 1/(1-p)
 };
 
-template <int BN>
+template <int BN, bool MC = false>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  // MC (CTA pair, 2-SM MMA): each CTA stages only half of the B tile -> 32 KB per stage, deeper ring
+  static constexpr int STAGES = MC ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (MC ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STG_BYTES + 256 + 1024;
@@ -73,11 +76,11 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, GemmDev p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MC>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,28 +96,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
-  const int units = tiles_m * tiles_n * p.splits;
+  // MC: a CTA pair (cluster of two, one TPC) computes a 256 x BN tile with the 2-SM MMA (tcgen05 cta_group::2):
+  // each CTA stages its 128 rows of A and HALF of the B tile, the leader issues the MMAs, each CTA's TMEM receives
+  // its own 128 accumulator rows.  Halves the per-SM shared-memory traffic of the B operand.  Work units are pairs.
+  const int crank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int units = (MC ? (tiles_m + 1) / 2 : tiles_m) * tiles_n * p.splits;
+  const int u_first = MC ? (blockIdx.x >> 1) : blockIdx.x;
+  const int u_step = MC ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC_F32) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], MC ? 2 : 1);    // MC (leader's barrier): own producer (+expect_tx of both CTAs' bytes) + peer producer
+      mbar_init(&empty[s], 1);            // MC: released by the leader's multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 256);
+      mbar_init(&tempty[a], MC ? 512 : 256);   // MC (leader's barrier): both CTAs' epilogue threads
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (MC) { tmem_alloc_2sm(tmem_slot, C::TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -123,16 +133,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = u_first; u < units; u += u_step) {
         const int split = u % p.splits;
         const int t = u / p.splits;
-        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        const int m0 = (MC ? 2 * (t / tiles_n) + crank : (t / tiles_n)) * BM, n0 = (t % tiles_n) * BN;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
+          if (MC) {
+            // both CTAs' loads credit the LEADER's full barrier; the leader arms it for the pair's total bytes
+            if (crank == 0) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            else mbar_arrive_remote(&full[s], 0);
+            if (!A_MN) {
+              tma_load_2d_2sm(sa, &tmA, &full[s], kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int pnl = 0; pnl < BM / 64; ++pnl) tma_load_2d_2sm(sa + pnl * 8192, &tmA, &full[s], m0 + pnl * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_2sm(sb, &tmB, &full[s], kb * BK, n0 + crank * (BN / 2));
+            } else {
+#pragma unroll
+              for (int pnl = 0; pnl < BN / 128; ++pnl)
+                tma_load_2d_2sm(sb + pnl * 8192, &tmB, &full[s], n0 + (crank * (BN / 128) + pnl) * 64, kb * BK);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
@@ -152,13 +182,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && (!MC || crank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_bf16(MC ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = u_first; u < units; u += u_step) {
         const int split = u % p.splits;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
@@ -174,12 +204,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = A_MN ? umma_desc_sw128(sa + kk * 2048, 8192, 1024) : umma_desc_sw128(sa + kk * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024) : umma_desc_sw128(sb + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if (MC) umma_bf16_2sm(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          if (MC) umma_commit_2sm_mc(&empty[s], 3); else umma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if (MC) umma_commit_2sm_mc(&tfull[as], 3); else umma_commit(&tfull[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
@@ -194,9 +225,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int NSL = BN / 64;            // 64-column slices per tile; this set owns slices sl with (sl & 1) == set
     int as = 0;
     uint32_t aph = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = u_first; u < units; u += u_step) {
       const int t = u / p.splits;
-      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      const int m0 = (MC ? 2 * (t / tiles_n) + crank : (t / tiles_n)) * BM, n0 = (t % tiles_n) * BN;
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       mbar_wait(&tfull[as], aph);
@@ -224,7 +255,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[as]);
+        if (MC && crank != 0) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
       } else {
 #pragma unroll 1
         for (int sl = set; sl < NSL; sl += 2) {  // 64-column slices of this warp set
@@ -240,7 +271,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (sl + 2 >= NSL && h == 1) {
               // this thread has drained its share of the accumulator: hand the TMEM stage back to the MMA warp
               tc_fence_before();
-              mbar_arrive(&tempty[as]);
+              if (MC && crank != 0) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
             const int n = n0 + sl * 64 + h * 32;
             float v[32];
@@ -330,18 +361,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer may still multicast-commit onto this CTA's barriers until it is done too
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (MC) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool MC>
 static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MC>;
   CUtensorMap tmA, tmB, tmC, tmC2;
   // operand maps: K-major -> tensor [rows, K] (inner = K), box {64, rows_per_tile}
   //               MN-major -> tensor [K, rows] (inner = rows), box {64, 64}
@@ -349,7 +381,7 @@ static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
   if (!A_MN) rc = make_tmap_2d(&tmA, a.A, a.K, a.M, a.lda, 64, BM);
   else rc = make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, 64, 64);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap_2d(&tmB, a.B, a.K, a.N, a.ldb, 64, BN);
+  if (!B_MN) rc = make_tmap_2d(&tmB, a.B, a.K, a.N, a.ldb, 64, MC ? BN / 2 : BN);   // MC: each CTA loads half the rows
   else rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, 64, 64);
   if (rc) return rc;
   if (EPI != EPI_ATOMIC_F32) {
@@ -381,39 +413,69 @@ static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
   p.ldmask = a.ldmask;
   p.dscale = a.drop_scale;
 
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, MC>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * p.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
-  cudaError_t e = cudaGetLastError();
+  const int tiles_m = (a.M + BM - 1) / BM;
+  cudaError_t e;
+  if (MC) {
+    const int pairs = ((tiles_m + 1) / 2) * ((a.N + BN - 1) / BN) * p.splits;
+    const int max_clusters = num_sms() / 2;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p);
+  } else {
+    const int tiles = tiles_m * ((a.N + BN - 1) / BN) * p.splits;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return MMFB_OK;
 }
 
-template <int BN>
+template <int BN, bool MC>
 static int dispatch(const mmfb_gemm_args& a, cudaStream_t s) {
   const int key = (a.a_mn ? 100 : 0) + (a.b_mn ? 10 : 0) + a.epi;
   switch (key) {
-    case 0 + EPI_BIAS: return launch<BN, false, false, EPI_BIAS>(a, s);
-    case 0 + EPI_BIAS_GELU: return launch<BN, false, false, EPI_BIAS_GELU>(a, s);
-    case 0 + EPI_BIAS_DROP_RESID: return launch<BN, false, false, EPI_BIAS_DROP_RESID>(a, s);
-    case 10 + EPI_BIAS: return launch<BN, false, true, EPI_BIAS>(a, s);
-    case 10 + EPI_GELU_BWD: return launch<BN, false, true, EPI_GELU_BWD>(a, s);
-    case 10 + EPI_ADD_AUX: return launch<BN, false, true, EPI_ADD_AUX>(a, s);
-    case 110 + EPI_ATOMIC_F32: return launch<BN, true, true, EPI_ATOMIC_F32>(a, s);
+    case 0 + EPI_BIAS: return launch<BN, false, false, EPI_BIAS, MC>(a, s);
+    case 0 + EPI_BIAS_GELU: return launch<BN, false, false, EPI_BIAS_GELU, MC>(a, s);
+    case 0 + EPI_BIAS_DROP_RESID: return launch<BN, false, false, EPI_BIAS_DROP_RESID, MC>(a, s);
+    case 10 + EPI_BIAS: return launch<BN, false, true, EPI_BIAS, MC>(a, s);
+    case 10 + EPI_GELU_BWD: return launch<BN, false, true, EPI_GELU_BWD, MC>(a, s);
+    case 10 + EPI_ADD_AUX: return launch<BN, false, true, EPI_ADD_AUX, MC>(a, s);
+    case 110 + EPI_ATOMIC_F32: return launch<BN, true, true, EPI_ATOMIC_F32, MC>(a, s);
     // test-only layout combinations (kept small: plain store epilogue)
-    case 100 + EPI_BIAS: return launch<BN, true, false, EPI_BIAS>(a, s);
-    case 110 + EPI_BIAS: return launch<BN, true, true, EPI_BIAS>(a, s);
+    case 100 + EPI_BIAS: return launch<BN, true, false, EPI_BIAS, MC>(a, s);
+    case 110 + EPI_BIAS: return launch<BN, true, true, EPI_BIAS, MC>(a, s);
     default:
       return set_error(MMFB_ERR_ARG, "gemm: unsupported (a_mn=%d, b_mn=%d, epi=%d)", a.a_mn, a.b_mn, a.epi);
   }
+}
+
+static bool cluster_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMFB_GEMM_CLUSTER");   // default: CTA pairs (2-SM MMA); MMFB_GEMM_CLUSTER=0 forces single-CTA
+    v = (e == nullptr) ? 1 : (e[0] != '0');
+  }
+  return v != 0;
 }
 
 int gemm(const mmfb_gemm_args& a, cudaStream_t stream) {
@@ -427,8 +489,11 @@ int gemm(const mmfb_gemm_args& a, cudaStream_t stream) {
   if ((a.lda % 8) || (a.ldb % 8) || (a.epi != EPI_ATOMIC_F32 && (a.ldc % 8)))
     return set_error(MMFB_ERR_ARG, "gemm: leading dimensions must be multiples of 8 elements");
   const int bn = a.block_n > 0 ? a.block_n : (a.N >= 256 ? 256 : 128);
-  if (bn == 256) return dispatch<256>(a, stream);
-  if (bn == 128) return dispatch<128>(a, stream);
+  // cluster: 0 = library default (env MMFB_GEMM_CLUSTER), 1 = single-CTA MMA, 2 = CTA pair with the 2-SM MMA
+  bool mc = a.cluster == 2 || (a.cluster == 0 && cluster_default());
+  if ((a.M + BM - 1) / BM < 2 || num_sms() < 2) mc = false;
+  if (bn == 256) return mc ? dispatch<256, true>(a, stream) : dispatch<256, false>(a, stream);
+  if (bn == 128) return mc ? dispatch<128, true>(a, stream) : dispatch<128, false>(a, stream);
   return set_error(MMFB_ERR_ARG, "gemm: block_n must be 128 or 256");
 }
 

@@ -24,7 +24,7 @@ def _req(t, dtype, name):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=lib.EPI_BIAS, bias=None, aux=None, drop_mask=None,
-         drop_scale=1.0, out=None, out2=None, splits=1, block_n=0):
+         drop_scale=1.0, out=None, out2=None, splits=1, block_n=0, cluster=0):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T) on the tcgen05 GEMM.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True); bf16.
@@ -62,7 +62,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=lib.EPI_BIAS, bias=None, aux=None,
         args.drop_mask, args.ldmask = drop_mask.data_ptr(), drop_mask.stride(0)
     args.drop_scale = float(drop_scale)
     args.M, args.N, args.K = M, N, K
-    args.epi, args.splits, args.block_n = int(epi), int(splits), int(block_n)
+    args.epi, args.splits, args.block_n, args.cluster = int(epi), int(splits), int(block_n), int(cluster)
     check(LIB.mmfb_gemm(ctypes.byref(args), _stream_ptr()))
     if epi == lib.EPI_BIAS_GELU:
         return out, out2

@@ -32,6 +32,7 @@ class GemmArgs(ctypes.Structure):
         ("epi", ctypes.c_int),
         ("splits", ctypes.c_int),
         ("block_n", ctypes.c_int),
+        ("cluster", ctypes.c_int),
     ]
 
 

@@ -101,3 +101,41 @@ def test_gemm_bad_args():
     b = torch.zeros(16, 60, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         F.gemm(a, b)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 512, 256, 256), (384, 768, 1000, 256), (456, 2304, 768, 256),
+                                      (1160, 768, 3072, 128), (14592, 768, 768, 256)])
+def test_gemm_cluster_multicast(a_mn, b_mn, M, N, K, bn):
+    """2-CTA cluster variant (B tile TMA-multicast, cross-CTA slot release): even, odd (dummy second tile) and
+    many-tiles-per-cluster tile counts; must equal the single-CTA kernel bit for bit (same MMA order per tile)."""
+    from mmf_b200 import functional as F, lib
+    a_st, a = _mk(M, K, a_mn, 11)
+    b_st, b = _mk(N, K, b_mn, 12)
+    c1 = F.gemm(a_st, b_st, a_mn=a_mn, b_mn=b_mn, epi=lib.EPI_BIAS, block_n=bn, cluster=1)
+    c2 = F.gemm(a_st, b_st, a_mn=a_mn, b_mn=b_mn, epi=lib.EPI_BIAS, block_n=bn, cluster=2)
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2)
+    assert rel(c2, a.float() @ b.float().t()) < 1e-2
+
+
+def test_gemm_cluster_epilogues_and_splitk():
+    from mmf_b200 import functional as F, lib
+    M, N, K = 1000, 768, 768
+    _, a = _mk(M, K, False, 13)
+    _, w = _mk(N, K, False, 14)
+    bias = (torch.randn(N, device="cuda") * 0.5).to(torch.bfloat16)
+    resid = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    u1, h1 = F.gemm(a, w, epi=lib.EPI_BIAS_GELU, bias=bias, cluster=1)
+    u2, h2 = F.gemm(a, w, epi=lib.EPI_BIAS_GELU, bias=bias, cluster=2)
+    assert torch.equal(u1, u2) and torch.equal(h1, h2)
+    y1 = F.gemm(a, w, epi=lib.EPI_BIAS_DROP_RESID, bias=bias, aux=resid, cluster=1)
+    y2 = F.gemm(a, w, epi=lib.EPI_BIAS_DROP_RESID, bias=bias, aux=resid, cluster=2)
+    assert torch.equal(y1, y2)
+    _, dy = _mk(M, N, False, 15)
+    xin = torch.randn(M, 1024, device="cuda").to(torch.bfloat16)
+    ref = dy.float().t() @ xin.float()
+    for splits in (1, 3, 7):
+        dw = torch.zeros(N, 1024, device="cuda", dtype=torch.float32)
+        F.gemm(dy, xin, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=dw, splits=splits, cluster=2)
+        assert rel(dw, ref) < 1e-2

@@ -3,6 +3,11 @@ import sys, os, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mmf_b200 import functional as F, lib
+_orig_gemm = F.gemm
+def _gemm(*a, **k):
+    k.setdefault('cluster', int(os.environ.get('MMFB_SWEEP_CLUSTER', '0')))
+    return _orig_gemm(*a, **k)
+F.gemm = _gemm
 from mmf_b200.engine import best_splits
 
 B, S, H, I = int(os.environ.get("B", 64)), 228, 768, 3072
@@ -37,19 +42,21 @@ def timeit(fn, n=8):
     return statistics.median(ts)
 
 
+import functools
 for name, fn, fl in cases:
     out = []
-    for bn in (256, 128):
-        ms = timeit(lambda: fn(bn))
-        out.append("bn%d %6.1f us %6.0f TF" % (bn, ms * 1e3, fl / ms / 1e9))
+    for cl in (1, 2):
+        os.environ["MMFB_SWEEP_CLUSTER"] = str(cl)
+        ms = timeit(lambda: fn(256))
+        out.append("cluster=%d %6.1f us %6.0f TF" % (cl - 1, ms * 1e3, fl / ms / 1e9))
     print(name, " | ".join(out))
 for name, a, b in wg:
     Mo, No = a.shape[1], b.shape[1]
     g = torch.zeros(Mo, No, device=dev)
     fl = 2 * M * Mo * No
     out = []
-    for bn in (256, 128):
-        for sp in (best_splits(Mo, No, M, bn=bn), 1):
-            ms = timeit(lambda: F.gemm(a, b, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=g, splits=sp, block_n=bn))
-            out.append("bn%d s%d %6.1f us %5.0f TF" % (bn, sp, ms * 1e3, fl / ms / 1e9))
+    sp = best_splits(Mo, No, M)
+    for cl in (1, 2):
+        ms = timeit(lambda: F.gemm(a, b, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=g, splits=sp, cluster=cl))
+        out.append("cluster=%d s%d %6.1f us %5.0f TF" % (cl - 1, sp, ms * 1e3, fl / ms / 1e9))
     print(name, " | ".join(out))
