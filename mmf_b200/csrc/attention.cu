@@ -267,21 +267,25 @@ struct AttnBwdDev {
 // rows: the operand pair that stays resident (R, Rg); cols: the looped pair (C, Cg)
 //   ROWS_ARE_Q :  R = Q_i, Rg = dO_i ; C = K_j, Cg = V_j ;  out0 = dQ_i = scale * sum_j dS' C
 //   !ROWS_ARE_Q:  R = K_j, Rg = V_j  ; C = Q_i, Cg = dO_i;  out0 = dK_j = scale * sum_i dS' C ; out1 = dV_j = sum_i P' Cg
-template <int D, bool ROWS_ARE_Q, bool DROP>
-__global__ void __launch_bounds__(160, 1)
+// CB = width of the looped block (keys for dQ, queries for dK/dV).  CB = 64 keeps the CTA at 256 TMEM columns and
+// ~80 KB of shared memory for d = 64, so two CTAs share an SM and hide each other's TMA / MMA / barrier latencies.
+template <int D, bool ROWS_ARE_Q, bool DROP, int CB>
+__global__ void __launch_bounds__(160, (CB == 64) ? 2 : 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRg,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCg, AttnBwdDev p) {
   constexpr int DC = D / 64;
-  constexpr int TILE = DC * 16384;  // one [128 x D] bf16 operand tile
+  constexpr int TILE = DC * 16384;   // one [128 x D] bf16 resident-operand tile
+  constexpr int CTILE = DC * CB * 128;  // one [CB x D] bf16 looped-operand tile
+  constexpr int PBYTES = 128 * CB * 2;  // P' / dS' [128 x CB] bf16
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sR = smem;
   uint8_t* sRg = sR + TILE;
   uint8_t* sC = sRg + TILE;
-  uint8_t* sCg = sC + TILE;
-  uint8_t* sP = sCg + TILE;       // [128 x 128] bf16, 2 chunks of [128 x 128B]
-  uint8_t* sDS = sP + 32768;
-  float* sCol = reinterpret_cast<float*>(sDS + 32768);   // [2 buffers][2 stats][128] per-column statistics
+  uint8_t* sCg = sC + CTILE;
+  uint8_t* sP = sCg + CTILE;      // [128 x CB] bf16, CB/64 chunks of [128 x 128B]
+  uint8_t* sDS = sP + PBYTES;
+  float* sCol = reinterpret_cast<float*>(sDS + PBYTES);   // [2 buffers][2 stats][128] per-column statistics
   uint32_t* sBits = reinterpret_cast<uint32_t*>(sCol + 512);  // [2 buffers][128 cols][4 words] dropout keep bits
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBits + 1024);
   uint64_t* r_full = bars;
@@ -296,9 +300,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
   const int row0 = rt * 128;
   const int S_rows = ROWS_ARE_Q ? p.Sq : p.Skv;
   const int S_cols = ROWS_ARE_Q ? p.Skv : p.Sq;
-  const int n_it = (S_cols + 127) / 128;
-  constexpr uint32_t TMEM_COLS = (256 + (ROWS_ARE_Q ? D : 2 * D)) <= 256 ? 256 : 512;
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_O0 = 256, COL_O1 = 256 + D;
+  const int n_it = (S_cols + CB - 1) / CB;
+  constexpr uint32_t TMEM_COLS = (2 * CB + (ROWS_ARE_Q ? D : 2 * D)) <= 256 ? 256 : 512;
+  constexpr uint32_t COL_S = 0, COL_DP = CB, COL_O0 = 2 * CB, COL_O1 = 2 * CB + D;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -329,14 +333,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         tma_load_3d(sR + c * 16384, &tmR, r_full, h * D + c * 64, row0, b);
         tma_load_3d(sRg + c * 16384, &tmRg, r_full, h * D + c * 64, row0, b);
       }
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      const uint32_t idesc_s = umma_idesc_bf16(128, CB, false, false);
       const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
       for (int it = 0; it < n_it; ++it) {
         if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous accumulation MMAs have consumed C/Cg and P/dS
-        mbar_expect_tx(c_full, 2 * TILE);
+        mbar_expect_tx(c_full, 2 * CTILE);
         for (int c = 0; c < DC; ++c) {
-          tma_load_3d(sC + c * 16384, &tmC, c_full, h * D + c * 64, it * 128, b);
-          tma_load_3d(sCg + c * 16384, &tmCg, c_full, h * D + c * 64, it * 128, b);
+          tma_load_3d(sC + c * CB * 128, &tmC, c_full, h * D + c * 64, it * CB, b);
+          tma_load_3d(sCg + c * CB * 128, &tmCg, c_full, h * D + c * 64, it * CB, b);
         }
         if (it == 0) mbar_wait(r_full, 0);
         mbar_wait(c_full, it & 1);
@@ -344,31 +348,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          const uint32_t coff = (kk >> 2) * CB * 128 + (kk & 3) * 32;
           umma_bf16(tmem_base + COL_S, umma_desc_sw128(smem_u32(sR) + off, 16, 1024),
-                    umma_desc_sw128(smem_u32(sC) + off, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    umma_desc_sw128(smem_u32(sC) + coff, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          const uint32_t coff = (kk >> 2) * CB * 128 + (kk & 3) * 32;
           umma_bf16(tmem_base + COL_DP, umma_desc_sw128(smem_u32(sRg) + off, 16, 1024),
-                    umma_desc_sw128(smem_u32(sCg) + off, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    umma_desc_sw128(smem_u32(sCg) + coff, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(s_ready);
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
-        // accumulate over the 128 looped positions (K dimension of these MMAs), B operands MN-major
+        // accumulate over the CB looped positions (K dimension of these MMAs), B operands MN-major
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < CB / 16; ++kk) {
           const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
           umma_bf16(tmem_base + COL_O0, umma_desc_sw128(smem_u32(sDS) + aoff, 16, 1024),
-                    umma_desc_sw128(smem_u32(sC) + kk * 2048, 16384, 1024), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
+                    umma_desc_sw128(smem_u32(sC) + kk * 2048, CB * 128, 1024), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
         }
         if (!ROWS_ARE_Q) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < CB / 16; ++kk) {
             const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
             umma_bf16(tmem_base + COL_O1, umma_desc_sw128(smem_u32(sP) + aoff, 16, 1024),
-                      umma_desc_sw128(smem_u32(sCg) + kk * 2048, 16384, 1024), idesc_o,
+                      umma_desc_sw128(smem_u32(sCg) + kk * 2048, CB * 128, 1024), idesc_o,
                       (it > 0 || kk > 0) ? 1u : 0u);
           }
         }
@@ -393,7 +399,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
     }
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
-      const int col0 = it * 128;
+      const int col0 = it * CB;
       // per-column stats for this block; double-buffered: a thread can run at most one iteration ahead of the
       // slowest (the bar.sync below), so buffer it&1 is never rewritten while still being read
       float* sColA = sCol + (it & 1) * 256;
@@ -401,7 +407,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
       {
         const int cidx = col0 + row;
         float a = ROWS_ARE_Q ? -INFINITY : INFINITY, bb = 0.0f;
-        if (cidx < S_cols) {
+        if (row < CB && cidx < S_cols) {
           if (ROWS_ARE_Q) {
             a = (p.mask != nullptr) ? p.mask[static_cast<int64_t>(b) * p.Skv + cidx] * LOG2E : 0.0f;
           } else {
@@ -418,7 +424,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const int wi = (row0 >> 5) + w;
-            dst[w] = (cidx < S_cols && wi < p.W) ? __ldg(p.dmask + (bh * p.Sq + cidx) * p.W + wi) : 0u;
+            dst[w] = (row < CB && cidx < S_cols && wi < p.W) ? __ldg(p.dmask + (bh * p.Sq + cidx) * p.W + wi) : 0u;
           }
         }
       }
@@ -428,7 +434,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
       mbar_wait(s_ready, it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CB / 32; ++c) {
         uint32_t rs[32], rd[32];
         tmem_ld32(trow + COL_S + c * 32, rs);
         tmem_ld32(trow + COL_DP + c * 32, rd);
@@ -635,6 +641,15 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmdO, a.dctx, W, a.Sq, a.B, a.ld_dctx, a.ld_dctx * a.Sq, 64, 128))) return rc;
   if ((rc = make_tmap_3d(&tmK, a.k, W, a.Skv, a.B, a.ldk, a.ldk * a.Skv, 64, 128))) return rc;
   if ((rc = make_tmap_3d(&tmV, a.v, W, a.Skv, a.B, a.ldv, a.ldv * a.Skv, 64, 128))) return rc;
+  // the looped operand is fetched in [CB x 64] boxes, the resident one in [128 x 64] boxes
+  constexpr int CBH = (D == 64) ? 64 : 128;
+  CUtensorMap tmQc = tmQ, tmdOc = tmdO, tmKc = tmK, tmVc = tmV;
+  if (CBH != 128) {
+    if ((rc = make_tmap_3d(&tmQc, a.q, W, a.Sq, a.B, a.ldq, a.ldq * a.Sq, 64, CBH))) return rc;
+    if ((rc = make_tmap_3d(&tmdOc, a.dctx, W, a.Sq, a.B, a.ld_dctx, a.ld_dctx * a.Sq, 64, CBH))) return rc;
+    if ((rc = make_tmap_3d(&tmKc, a.k, W, a.Skv, a.B, a.ldk, a.ldk * a.Skv, 64, CBH))) return rc;
+    if ((rc = make_tmap_3d(&tmVc, a.v, W, a.Skv, a.B, a.ldv, a.ldv * a.Skv, 64, CBH))) return rc;
+  }
   // delta = rowsum(dO * O)
   {
     const int64_t warps = static_cast<int64_t>(a.B) * a.Sq * a.heads;
@@ -646,42 +661,36 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     count_launch();
   }
   constexpr int DC = D / 64;
-  const int smem = 4 * DC * 16384 + 2 * 32768 + 2048 + 4096 + 128 + 1024;
+  constexpr int CB = (D == 64) ? 64 : 128;   // d = 64: 64-wide looped blocks -> 256 TMEM columns, 2 CTAs per SM
+  const int smem = 2 * DC * 16384 + 2 * DC * CB * 128 + 2 * (128 * CB * 2) + 2048 + 4096 + 128 + 1024;
   AttnBwdDev p;
   p.B = a.B; p.H = a.heads; p.Sq = a.Sq; p.Skv = a.Skv;
   p.mask = a.mask; p.lse2 = a.lse2; p.delta = a.delta;
   p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
   p.scale = 1.0f / sqrtf(static_cast<float>(D));
   p.scale2 = LOG2E * p.scale;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, true, true, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<D, true, false, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<D, false, true, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<D, false, false, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd smem attr: %s", cudaGetErrorString(e));
+    set = true;
+  }
   {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_bwd_kernel<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(dq) smem attr: %s", cudaGetErrorString(e));
-      set = true;
-    }
     p.out0 = reinterpret_cast<bf16*>(a.dq); p.ld0 = a.ld_dq; p.out1 = nullptr; p.ld1 = 0;
     dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
-    if (p.dmask != nullptr) attn_bwd_kernel<D, true, true><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmK, tmV, p);
-    else attn_bwd_kernel<D, true, false><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmK, tmV, p);
+    if (p.dmask != nullptr) attn_bwd_kernel<D, true, true, CB><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmKc, tmVc, p);
+    else attn_bwd_kernel<D, true, false, CB><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmKc, tmVc, p);
     count_launch();
   }
   {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_bwd_kernel<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(dkv) smem attr: %s", cudaGetErrorString(e));
-      set = true;
-    }
     p.out0 = reinterpret_cast<bf16*>(a.dk); p.ld0 = a.ld_dk;
     p.out1 = reinterpret_cast<bf16*>(a.dv); p.ld1 = a.ld_dv;
     dim3 grid((a.Skv + 127) / 128, a.heads, a.B);
-    if (p.dmask != nullptr) attn_bwd_kernel<D, false, true><<<grid, 160, smem, stream>>>(tmK, tmV, tmQ, tmdO, p);
-    else attn_bwd_kernel<D, false, false><<<grid, 160, smem, stream>>>(tmK, tmV, tmQ, tmdO, p);
+    if (p.dmask != nullptr) attn_bwd_kernel<D, false, true, CB><<<grid, 160, smem, stream>>>(tmK, tmV, tmQc, tmdOc, p);
+    else attn_bwd_kernel<D, false, false, CB><<<grid, 160, smem, stream>>>(tmK, tmV, tmQc, tmdOc, p);
     count_launch();
   }
   cudaError_t e = cudaGetLastError();
