@@ -151,11 +151,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     float mx = -INFINITY;
     const float4* sMask4 = reinterpret_cast<const float4*>(sMask);
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-      uint32_t r[32];
-      tmem_ld32(trow + c * 32, r);
-      tmem_ld_wait();
+    // pass 1 (row max): TMEM loads are software-pipelined - chunk c+1 is in flight while chunk c is reduced
+    auto max_chunk = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const float4 m = sMask4[c * 8 + q4];
@@ -164,19 +161,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 2]), p.scale2, m.z));
         mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 3]), p.scale2, m.w));
       }
+    };
+    {
+      uint32_t ra[32], rb[32];
+      tmem_ld32(trow, ra);
+#pragma unroll 1
+      for (int c = 0; c < nch; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nch) tmem_ld32(trow + (c + 1) * 32, rb);
+        max_chunk(ra, c);
+        if (c + 1 < nch) {
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld32(trow + (c + 2) * 32, ra);
+          max_chunk(rb, c + 1);
+        }
+      }
     }
     float sum = 0.0f;
     const uint32_t* dm = (p.dmask != nullptr && valid)
                              ? p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W
                              : nullptr;
     uint8_t* prow = sP + row * 128;
-#pragma unroll 1
-    for (int c = 0; c < SK / 32; ++c) {
+    auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
       float e[32];
       if (c < nch) {
-        uint32_t r[32];
-        tmem_ld32(trow + c * 32, r);
-        tmem_ld_wait();
         const uint32_t bits = dm ? __ldg(dm + c) : 0xFFFFFFFFu;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
@@ -204,6 +212,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         o.z = pack_bf16x2(e[qd * 8 + 4], e[qd * 8 + 5]);
         o.w = pack_bf16x2(e[qd * 8 + 6], e[qd * 8 + 7]);
         *reinterpret_cast<uint4*>(chunk_base + chunk * 16) = o;
+      }
+    };
+    {
+      const int nall = SK / 32;   // even (SK is a multiple of 64)
+      uint32_t ra[32], rb[32];
+      tmem_ld32(trow, ra);
+#pragma unroll 1
+      for (int c = 0; c < nall; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nch) tmem_ld32(trow + (c + 1) * 32, rb);
+        exp_chunk(ra, c);
+        tmem_ld_wait();
+        if (c + 2 < nch) tmem_ld32(trow + (c + 2) * 32, ra);
+        exp_chunk(rb, c + 1);
       }
     }
     fence_proxy_async();
@@ -541,38 +563,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
   }
 }
 
-// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d] : one warp per (token, head)
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d].  One warp per token row, 16-byte vector loads; a head of D
+// elements is owned by D/8 consecutive lanes and reduced with shuffles (coalesced 512 B / 1 KB per warp access).
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
                                   int64_t ld_o, const float* __restrict__ O32, float* __restrict__ delta, int B, int H,
                                   int Sq, int D) {
-  const int64_t gw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t tok = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t total = static_cast<int64_t>(B) * Sq * H;
-  if (gw >= total) return;
-  const int h = gw % H;
-  const int64_t tok = gw / H;  // b*Sq + q
-  const bf16* a = dO + tok * ld_do + h * D;
-  const bf16* o = O + tok * ld_o + h * D;
-  float s = 0.0f;
-  if (O32 != nullptr) {
-    const float* o32 = O32 + tok * (static_cast<int64_t>(H) * D) + h * D;
-    for (int i = lane * 2; i < D; i += 64) {
-      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
-      const float2 y = *reinterpret_cast<const float2*>(o32 + i);
-      s += x.x * y.x + x.y * y.y;
+  if (tok >= static_cast<int64_t>(B) * Sq) return;
+  const int W = H * D;
+  const int lanes_per_head = D / 8;           // 8 (d=64) or 16 (d=128)
+  const int b = tok / Sq, q = tok % Sq;
+  for (int base = 0; base < W; base += 256) {   // warp-uniform trip count: every lane takes part in the shuffles
+    const int col = base + lane * 8;
+    const bool act = col < W;
+    float x[8];
+    float s = 0.0f;
+    if (act) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dO + tok * ld_do + col);
+      float2 t;
+      t = unpack_bf16x2(u.x); x[0] = t.x; x[1] = t.y;
+      t = unpack_bf16x2(u.y); x[2] = t.x; x[3] = t.y;
+      t = unpack_bf16x2(u.z); x[4] = t.x; x[5] = t.y;
+      t = unpack_bf16x2(u.w); x[6] = t.x; x[7] = t.y;
     }
-  } else {
-    for (int i = lane * 2; i < D; i += 64) {
-      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a + i));
-      const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + i));
-      s += x.x * y.x + x.y * y.y;
+    if (act && O32 != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(O32 + tok * static_cast<int64_t>(W) + col);
+      const float4 c4 = *reinterpret_cast<const float4*>(O32 + tok * static_cast<int64_t>(W) + col + 4);
+      s = x[0] * a.x + x[1] * a.y + x[2] * a.z + x[3] * a.w + x[4] * c4.x + x[5] * c4.y + x[6] * c4.z + x[7] * c4.w;
+    } else if (act) {
+      const uint4 u = *reinterpret_cast<const uint4*>(O + tok * ld_o + col);
+      float2 t;
+      t = unpack_bf16x2(u.x); s += x[0] * t.x + x[1] * t.y;
+      t = unpack_bf16x2(u.y); s += x[2] * t.x + x[3] * t.y;
+      t = unpack_bf16x2(u.z); s += x[4] * t.x + x[5] * t.y;
+      t = unpack_bf16x2(u.w); s += x[6] * t.x + x[7] * t.y;
     }
-  }
-  s = warp_sum(s);
-  if (lane == 0) {
-    const int64_t bq = tok;  // b*Sq + q
-    const int b = bq / Sq, q = bq % Sq;
-    delta[(static_cast<int64_t>(b) * H + h) * Sq + q] = s;
+    // reduce over the lanes of this head (lanes_per_head is a power of two dividing 32; W % 256 may leave idle lanes)
+    for (int o = lanes_per_head >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (act && (lane % lanes_per_head) == 0) delta[(static_cast<int64_t>(b) * H + col / D) * Sq + q] = s;
   }
 }
 
@@ -652,7 +681,7 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   }
   // delta = rowsum(dO * O)
   {
-    const int64_t warps = static_cast<int64_t>(a.B) * a.Sq * a.heads;
+    const int64_t warps = static_cast<int64_t>(a.B) * a.Sq;
     const int threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
     attn_delta_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(

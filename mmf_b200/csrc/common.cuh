@@ -273,14 +273,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
 }
 
 // --------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG: dropout masks are regenerated in backward from (seed, offset, index)
+// Philox4x32-7 counter RNG (7 rounds: the smallest variant that passes BigCrush) for the dropout keep-bits
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x243F6A88u,
            c3 = 0x85A308D3u;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < 7; ++i) {
     uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
     uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
     uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
