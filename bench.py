@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MMFB_BENCH_BATCH", "64")), help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MMFB_BENCH_BATCH", "166")), help="samples per GPU")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -222,8 +222,10 @@ def main():
                           "(BASELINE.json configs[1]); fwd+bwd of region projection + embeddings + 12 fusion layers",
               "batch_per_gpu": args.batch, "global_batch": args.batch * max(world, 1), "seq_len": S_LEN,
               "dropout": args.dropout, "parallelism": "dp%d" % max(world, 1),
-              "l2_policy": "activations+weights per step (~%d MB at batch %d) exceed the 126 MB L2" % (
-                  int(args.batch * 0.072 * 1000 / 64 * 64), args.batch)}
+              "batch_choice": "166 samples x 228 tokens = 147.8 -> 148 pair tiles of 256 rows: every GEMM of the block is "
+                              "an exact number of waves on 148 SMs (sweep in profiles/README.md)",
+              "l2_policy": "activations + weights touched per step (~%d MB at batch %d) exceed the 126 MB L2" % (
+                  int(args.batch * 72), args.batch)}
 
     if args.impl == "reference":
         if rank != 0:

@@ -50,15 +50,25 @@ struct GemmDev {
   float dscale;          // 1/(1-p)
 };
 
-template <int BN, bool MC = false>
+constexpr bool epi_uses_aux(int epi) { return epi == EPI_BIAS_DROP_RESID || epi == EPI_GELU_BWD || epi == EPI_ADD_AUX; }
+
+template <int BN, bool MC = false, int EPI = EPI_BIAS>
 struct Cfg {
+  // AUX_TMA: the residual / pre-activation tile the epilogue needs is prefetched by TMA into swizzled smem slices
+  // (2 sets x 2 buffers x 16 KB) one slice ahead, instead of strided global loads in the epilogue's critical path.
+  // Only in the CTA-pair mode, whose 32 KB stages leave room for it.
+  // Measured (profiles/README.md): a clear win for the GELU' dgrad (K = hidden: short mainloop, heavy epilogue: 107 -> 79 us);
+  // for the residual epilogues of the K = 3072 / 2304 GEMMs the ring shrinking from 6 to 4 stages costs more than
+  // the staging saves, so those keep the direct 16-byte global loads.
+  static constexpr bool AUX_TMA = MC && EPI == EPI_GELU_BWD;
+  static constexpr int AUX_BYTES = AUX_TMA ? 4 * STG_BYTES : 0;
   // MC (CTA pair, 2-SM MMA): each CTA stages only half of the B tile -> 32 KB per stage, deeper ring
-  static constexpr int STAGES = MC ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);
+  static constexpr int STAGES = MC ? (AUX_TMA ? ((BN == 256) ? 4 : 5) : ((BN == 256) ? 6 : 8)) : ((BN == 256) ? 4 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (MC ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STG_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STG_BYTES + AUX_BYTES + 256 + 1024;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
@@ -79,18 +89,21 @@ __device__ __forceinline__ void tma_store_wait_read() {
 template <int BN, bool A_MN, bool B_MN, int EPI, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, GemmDev p) {
-  using C = Cfg<BN, MC>;
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+            const __grid_constant__ CUtensorMap tmAux, GemmDev p) {
+  using C = Cfg<BN, MC, EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * STG_BYTES);
+  uint8_t* auxs = stg + 2 * STG_BYTES;     // [2 sets][2 buffers] 16 KB aux slices (AUX_TMA only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(auxs + C::AUX_BYTES);
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;    // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* auxfull = bars + 2 * STAGES + 4;  // [2 sets][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -108,10 +121,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC_F32) tma_prefetch_desc(&tmC);
+    if (C::AUX_TMA) tma_prefetch_desc(&tmAux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], MC ? 2 : 1);    // MC (leader's barrier): own producer (+expect_tx of both CTAs' bytes) + peer producer
       mbar_init(&empty[s], 1);            // MC: released by the leader's multicast tcgen05.commit
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&auxfull[a], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], MC ? 512 : 256);   // MC (leader's barrier): both CTAs' epilogue threads
@@ -223,8 +238,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int bar_id = 1 + set;
     uint8_t* stg_set = stg + set * STG_BYTES;   // one staging slice per warp set
     constexpr int NSL = BN / 64;            // 64-column slices per tile; this set owns slices sl with (sl & 1) == set
+    constexpr int SPT = NSL / 2;            // slices per tile for one set
     int as = 0;
     uint32_t aph = 0;
+    int gslice = 0;                         // running index of the slices this set has processed (aux double buffer)
+    // coordinates of this set's k-th slice, false past the end of the schedule
+    auto slice_coords = [&](int k, int& am0, int& an) -> bool {
+      const int u2 = u_first + (k / SPT) * u_step;
+      if (u2 >= units) return false;
+      const int t2 = u2 / p.splits;
+      am0 = (MC ? 2 * (t2 / tiles_n) + crank : (t2 / tiles_n)) * BM;
+      an = (t2 % tiles_n) * BN + (set + 2 * (k % SPT)) * 64;
+      return true;
+    };
+    auto aux_prefetch = [&](int k) {        // store_thread only
+      int am0, an;
+      if (slice_coords(k, am0, an)) {
+        uint64_t* bar = &auxfull[set * 2 + (k & 1)];
+        mbar_expect_tx(bar, STG_BYTES);
+        tma_load_2d(auxs + (set * 2 + (k & 1)) * STG_BYTES, &tmAux, bar, an, am0);
+      }
+    };
+    if (C::AUX_TMA && store_thread) aux_prefetch(0);
     for (int u = u_first; u < units; u += u_step) {
       const int t = u / p.splits;
       const int m0 = (MC ? 2 * (t / tiles_n) + crank : (t / tiles_n)) * BM, n0 = (t % tiles_n) * BN;
@@ -263,6 +298,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           //    The previous slice's TMA store drains the (single) staging buffer meanwhile.
           uint32_t pk[32];                       // this thread's 64 output columns, packed bf16 pairs
           uint32_t hk[EPI == EPI_BIAS_GELU ? 32 : 1];
+          const uint8_t* auxrow = nullptr;
+          if (C::AUX_TMA) {
+            // the slice after this one starts streaming in now (its buffer was last read two slices ago, and every
+            // thread of the set has passed that slice's staging barriers since)
+            if (store_thread) aux_prefetch(gslice + 1);
+            mbar_wait(&auxfull[set * 2 + (gslice & 1)], (gslice >> 1) & 1);
+            auxrow = auxs + (set * 2 + (gslice & 1)) * STG_BYTES + row * 128;
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
@@ -301,11 +344,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             if (EPI == EPI_BIAS_DROP_RESID || EPI == EPI_GELU_BWD || EPI == EPI_ADD_AUX) {
-              if (p.aux != nullptr && row_ok && n < p.N) {
-                const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(m) * p.ldaux + n);
+              if (C::AUX_TMA || (p.aux != nullptr && row_ok && n < p.N)) {
                 uint4 a4[4];
+                if (C::AUX_TMA) {
+                  // swizzled smem slice written by TMA (out-of-range rows / columns arrive as zeros)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a4[q] = (n + q * 8 < p.N) ? __ldg(ap + q) : make_uint4(0, 0, 0, 0);
+                  for (int q = 0; q < 4; ++q)
+                    a4[q] = *reinterpret_cast<const uint4*>(auxrow + (((h * 4 + q) ^ (row & 7)) * 16));
+                } else {
+                  const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(m) * p.ldaux + n);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) a4[q] = (n + q * 8 < p.N) ? __ldg(ap + q) : make_uint4(0, 0, 0, 0);
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   float x[8];
@@ -352,6 +402,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_store_commit();
             }
           }
+          ++gslice;
         }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -373,8 +424,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ----------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int EPI, bool MC>
 static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
-  using C = Cfg<BN, MC>;
-  CUtensorMap tmA, tmB, tmC, tmC2;
+  using C = Cfg<BN, MC, EPI>;
+  CUtensorMap tmA, tmB, tmC, tmC2, tmAux;
   // operand maps: K-major -> tensor [rows, K] (inner = K), box {64, rows_per_tile}
   //               MN-major -> tensor [K, rows] (inner = rows), box {64, 64}
   int rc;
@@ -396,6 +447,12 @@ static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
   } else {
     tmC = tmA;
     tmC2 = tmA;
+  }
+  tmAux = tmA;
+  if (C::AUX_TMA) {
+    if (a.aux == nullptr) return set_error(MMFB_ERR_ARG, "gemm: this epilogue needs the aux operand");
+    rc = make_tmap_2d(&tmAux, a.aux, a.N, a.M, a.ldaux, 64, BM);
+    if (rc) return rc;
   }
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -438,11 +495,11 @@ static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p);
+    e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmAux, p);
   } else {
     const int tiles = tiles_m * ((a.N + BN - 1) / BN) * p.splits;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, tmAux, p);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
