@@ -303,10 +303,30 @@ def main():
     for _ in range(2):
         float(step(to_device(host_sl, dev)).detach())
     barrier()
+    # Input pipeline as in the reference trainer (pinned SampleList + non_blocking copies, sample.py:326-370): the H2D of
+    # step i+1 is issued on a copy stream while step i computes.  Every step still copies its full inputs H2D and reads
+    # its loss back D2H inside the timed region.
+    copy_stream = torch.cuda.Stream()
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            batch = to_device(host_sl, dev)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return batch, ev
+
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        loss = step(to_device(host_sl, dev))
+    nxt = prefetch()
+    for i in range(args.steps):
+        batch, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        if i + 1 < args.steps:
+            nxt = prefetch()
+        loss = step(batch)
+        for v in batch.values():      # keep the copy-stream allocations alive until the compute stream has used them
+            for t in (v.values() if isinstance(v, dict) else [v]):
+                t.record_stream(torch.cuda.current_stream())
         _ = float(loss.detach())   # D2H read of the step's result
     f1.record()
     barrier()

@@ -45,8 +45,10 @@ struct AttnFwdDev {
   float scale2;           // log2(e)/sqrt(d)
 };
 
+// 288 threads: warps 0..7 = softmax / epilogue (TWO threads per query row: warp w owns TMEM lane quarter w & 3 and the
+// 32-column chunks of parity w >> 2; row max / sum are exchanged through shared memory), warp 8 = TMA + MMA issue.
 template <int D>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(288, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnFwdDev p) {
   constexpr int DC = D / 64;
@@ -60,7 +62,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sP = smem;                      // NB x [128 x 128B]   (aliases Q and K once S is complete)
   uint8_t* sV = smem + r0_bytes;           // DC x [SK x 128B]
   float* sMask = reinterpret_cast<float*>(sV + DC * SK * 128);  // [SK]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + SK);
+  float* sRed = sMask + SK;                                     // [2 stats][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
   uint64_t* qk_full = bars;
   uint64_t* v_full = bars + 1;
   uint64_t* s_ready = bars + 2;
@@ -74,7 +77,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int need_cols = SK > D ? SK : D;  // S occupies SK columns, O later reuses columns [0, D)
   const uint32_t tmem_cols = need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512));
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -82,7 +85,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(qk_full, 1);
       mbar_init(v_full, 1);
       mbar_init(s_ready, 1);
-      mbar_init(p_ready, 128);
+      mbar_init(p_ready, 256);
       mbar_init(o_ready, 1);
       fence_barrier_init();
     }
@@ -92,7 +95,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // additive mask in the log2 domain; padded key columns get -inf so that exp2 yields exactly 0 without any
     // per-element bounds test in the softmax loops
-    for (int i = threadIdx.x; i < SK; i += 128)
+    for (int i = threadIdx.x; i < SK; i += 256)
       sMask[i] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
   }
   tc_fence_before();
@@ -100,7 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ---- loads ----
       mbar_expect_tx(qk_full, DC * 16384 + DC * SK * 128);
@@ -142,11 +145,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ------------------------------ softmax + epilogue (thread == query row) ------------------------------
-    const int row = threadIdx.x;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
     const int q = q0 + row;
     const bool valid = q < p.Sq;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int nch = (p.Skv + 31) / 32;
+    const int nk1 = (nch - half + 1) / 2;      // this thread's chunks with data: c = half + 2k, k < nk1
+    const int nk2 = SK / 64;                   // this thread's chunks of the padded row: c = half + 2k, k < nk2
     mbar_wait(s_ready, 0);
     tc_fence_after();
     float mx = -INFINITY;
@@ -164,19 +170,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     {
       uint32_t ra[32], rb[32];
-      tmem_ld32(trow, ra);
+      if (nk1 > 0) tmem_ld32(trow + half * 32, ra);
 #pragma unroll 1
-      for (int c = 0; c < nch; c += 2) {
+      for (int k = 0; k < nk1; k += 2) {
         tmem_ld_wait();
-        if (c + 1 < nch) tmem_ld32(trow + (c + 1) * 32, rb);
-        max_chunk(ra, c);
-        if (c + 1 < nch) {
+        if (k + 1 < nk1) tmem_ld32(trow + (half + 2 * (k + 1)) * 32, rb);
+        max_chunk(ra, half + 2 * k);
+        if (k + 1 < nk1) {
           tmem_ld_wait();
-          if (c + 2 < nch) tmem_ld32(trow + (c + 2) * 32, ra);
-          max_chunk(rb, c + 1);
+          if (k + 2 < nk1) tmem_ld32(trow + (half + 2 * (k + 2)) * 32, ra);
+          max_chunk(rb, half + 2 * (k + 1));
         }
       }
     }
+    sRed[half * 128 + row] = mx;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    mx = fmaxf(sRed[row], sRed[128 + row]);
     float sum = 0.0f;
     const uint32_t* dm = (p.dmask != nullptr && valid)
                              ? p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W
@@ -214,29 +223,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         *reinterpret_cast<uint4*>(chunk_base + chunk * 16) = o;
       }
     };
-    {
-      const int nall = SK / 32;   // even (SK is a multiple of 64)
-      uint32_t ra[32], rb[32];
-      tmem_ld32(trow, ra);
+    // (pass 2 keeps a single TMEM buffer: with 288 threads and two CTAs per SM the budget is 112 registers)
 #pragma unroll 1
-      for (int c = 0; c < nall; c += 2) {
+    for (int k = 0; k < nk2; ++k) {
+      const int c = half + 2 * k;
+      uint32_t r[32];
+      if (c < nch) {
+        tmem_ld32(trow + c * 32, r);
         tmem_ld_wait();
-        if (c + 1 < nch) tmem_ld32(trow + (c + 1) * 32, rb);
-        exp_chunk(ra, c);
-        tmem_ld_wait();
-        if (c + 2 < nch) tmem_ld32(trow + (c + 2) * 32, ra);
-        exp_chunk(rb, c + 1);
       }
+      exp_chunk(r, c);
     }
+    sRed[256 + half * 128 + row] = sum;
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(p_ready);
-    if (valid) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = mx + log2f(sum);
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    sum = sRed[256 + row] + sRed[256 + 128 + row];
+    if (valid && half == 0) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = mx + log2f(sum);
     const float inv = p.dscale / sum;
     mbar_wait(o_ready, 0);
     tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = half; c < D / 32; c += 2) {
       uint32_t r[32];
       tmem_ld32(trow + c * 32, r);
       tmem_ld_wait();
@@ -263,7 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -630,7 +639,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   constexpr int DC = D / 64;
   const int SK = (a.Skv + 63) & ~63, NB = SK / 64;
   const int r0 = NB * 16384 > DC * 16384 + DC * SK * 128 ? NB * 16384 : DC * 16384 + DC * SK * 128;
-  const int smem = r0 + DC * SK * 128 + SK * 4 + 128 + 1024;
+  const int smem = r0 + DC * SK * 128 + SK * 4 + 2048 + 128 + 1024;
   AttnFwdDev p;
   p.B = a.B; p.H = a.heads; p.Sq = a.Sq; p.Skv = a.Skv;
   p.mask = a.mask;
@@ -647,7 +656,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     smem_set = smem;
   }
   dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
-  kern<<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd launch: %s", cudaGetErrorString(e));
   count_launch();

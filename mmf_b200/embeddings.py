@@ -164,9 +164,10 @@ class B200VisioLinguisticEmbeddings(nn.Module):
 
     def forward(self, input_ids, token_type_ids=None, visual_embeddings=None, visual_embeddings_type=None,
                 image_text_alignment=None):
-        if image_text_alignment is not None:
-            raise NotImplementedError("image_text_alignment (embeddings.py:375-410) is not implemented on the B200 path yet")
         _require_cuda(input_ids, "input_ids")
+        if image_text_alignment is not None and visual_embeddings is not None and visual_embeddings_type is not None:
+            return self._forward_with_alignment(input_ids, token_type_ids, visual_embeddings, visual_embeddings_type,
+                                                image_text_alignment)
         self._runner.ensure(input_ids.device)
         B, T = input_ids.shape
         use_img = visual_embeddings is not None and visual_embeddings_type is not None
@@ -178,3 +179,39 @@ class B200VisioLinguisticEmbeddings(nn.Module):
         out_dtype = self.output_dtype or self.word_embeddings.weight.dtype
         return _VLEmbedFn.apply(self._runner, idx, (B, T, R, self._runner.H), float(self.dropout.p), self.training,
                                 out_dtype, feats, *self._runner.pack.params)
+
+    def _forward_with_alignment(self, input_ids, token_type_ids, visual_embeddings, visual_embeddings_type,
+                                image_text_alignment):
+        """get_position_embeddings_visual with image_text_alignment (embeddings.py:375-410): each region's position
+        embedding is the mean of the position embeddings of the words it is aligned to (-1 = padding) plus
+        position_embeddings_visual[0].  LayerNorm is per row, so text rows and image rows are composed by two
+        composer + LN launches sharing the LayerNorm parameters; the alignment gather/mean itself is integer indexing
+        plus a tiny torch reduction whose gradient flows into position_embeddings.weight through autograd."""
+        from . import ops
+        B, T = input_ids.shape
+        R = visual_embeddings.shape[1]
+        H = self.LayerNorm.weight.shape[0]
+        dev = input_ids.device
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        pos = torch.arange(T, device=dev).unsqueeze(0).expand(B, T)
+        p_drop = float(self.dropout.p)
+        text = ops.compose_ln(B * T, H, [], [(self.word_embeddings.weight, ops.i32(input_ids)),
+                                             (self.position_embeddings.weight, ops.i32(pos)),
+                                             (self.token_type_embeddings.weight, ops.i32(token_type_ids))],
+                              self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, p_drop, self.training)
+        am = (image_text_alignment != -1).long()
+        ali = am * image_text_alignment
+        pv = (self.position_embeddings.weight[ali] * am.unsqueeze(-1)).sum(2)
+        cnt = am.sum(2)
+        cnt = torch.where(cnt == 0, torch.ones_like(cnt), cnt)
+        pv = (pv / cnt.unsqueeze(-1)).reshape(B * R, H)
+        proj = ops.linear(visual_embeddings.reshape(B * R, -1), self.projection.weight, self.projection.bias)
+        rows = torch.arange(B * R, device=dev, dtype=torch.int32)
+        zeros = torch.zeros(B * R, device=dev, dtype=torch.int32)
+        img = ops.compose_ln(B * R, H, [(proj, rows), (pv, rows)],
+                             [(self.token_type_embeddings_visual.weight, ops.i32(visual_embeddings_type)),
+                              (self.position_embeddings_visual.weight, zeros)],
+                             self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, p_drop, self.training)
+        out = torch.cat([text.view(B, T, H), img.view(B, R, H)], dim=1)
+        return out.to(self.output_dtype or self.word_embeddings.weight.dtype)

@@ -35,8 +35,17 @@ def test_visio_linguistic_embeddings_vs_reference_golden():
     e2 = rel(out_t, g["out_text"])
     print("embeddings vs golden: text+image %.2e text-only %.2e" % (e1, e2))
     assert e1 < 1e-2 and e2 < 1e-2
-    with pytest.raises(NotImplementedError):
-        mod(ids, seg, feats, vtype, g["alignment"].cuda())
+    # image_text_alignment: position of a region = mean of its aligned words' position embeddings (+ pos_visual[0]);
+    # one region of the fixture is aligned to nothing (divide-by-zero guard, embeddings.py:396-399)
+    out_a = mod(ids, seg, feats, vtype, g["alignment"].cuda())
+    e3 = rel(out_a, g["out_alignment"])
+    print("embeddings with image_text_alignment vs golden: %.2e" % e3)
+    assert e3 < 1e-2
+    mod.zero_grad()
+    mod.train()
+    x = mod(ids, seg, feats, vtype, g["alignment"].cuda())
+    (x.float() ** 2).sum().backward()
+    assert mod.position_embeddings.weight.grad is not None and torch.isfinite(mod.position_embeddings.weight.grad).all()
 
 
 def test_embeddings_backward_vs_oracle():
