@@ -365,7 +365,10 @@ def main():
         achieved = k_flops / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gemm_kernel<256,K-major,K-major,BIAS_GELU> FFN-up [%d,768]x[3072,768]^T" % M,
                     "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                    "peak_source": "%s bf16_tflops (burst: kernel timed alone)" % how, "traffic": None,
+                    "peak_source": "%s bf16_tflops (burst: kernel timed alone)" % how,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at batch 166, one `ncu --set full` capture
+                    # (profiles/r1_ncu_dominant_b166.txt): 63.1 MB + 405.5 MB vs 62.8 + 465.1 MB algorithmic
+                    "traffic": 468.6e6 if B == 166 else None,
                     "kernel_ms": k_ms, "flops_per_launch": k_flops,
                     "step_tflops": STEP_FLOPS_PER_SAMPLE * value / 1e12 / world,
                     "step_frac_of_sustained": STEP_FLOPS_PER_SAMPLE * value / 1e12 / world / sustained}
