@@ -212,3 +212,75 @@ def test_cpu_input_raises():
     enc = B200BertEncoder(bert_cfg(128, 2, 256, 1))
     with pytest.raises(RuntimeError):
         enc(torch.zeros(1, 4, 128))
+
+
+def test_vilbert_encoder_real_widths_vs_oracle():
+    """BASELINE config 3 widths: text 768/12h/3072, image 1024/8h/1024, co-attention 1024/8h (d=128), T=R=36;
+    a short schedule (2 text, 1 image, 1 connection layer) keeps the oracle fast."""
+    from mmf_b200.modules import B200ViLBertEncoder
+    torch.manual_seed(0)
+    c = dict(hidden_size=768, num_attention_heads=12, intermediate_size=3072, num_hidden_layers=2,
+             v_hidden_size=1024, v_num_attention_heads=8, v_intermediate_size=1024, v_num_hidden_layers=1,
+             bi_hidden_size=1024, bi_num_attention_heads=8, v_biattention_id=[0], t_biattention_id=[1])
+    cfg = types.SimpleNamespace(hidden_dropout_prob=0.0, v_hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                v_attention_probs_dropout_prob=0.0, **c)
+    enc = B200ViLBertEncoder(cfg).cuda().eval()
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.02)
+    B, T, R = 4, 36, 36
+    g = torch.Generator(device="cuda").manual_seed(1)
+    txt = torch.randn(B, T, 768, generator=g, device="cuda")
+    img = torch.randn(B, R, 1024, generator=g, device="cuda")
+    tmask = (torch.arange(T, device="cuda")[None] < torch.tensor([36, 20, 30, 9], device="cuda")[:, None]).long()
+    imask = (torch.arange(R, device="cuda")[None] < torch.tensor([36, 36, 12, 25], device="cuda")[:, None]).long()
+    tadd, iadd = O.extended_attention_mask(tmask), O.extended_attention_mask(imask)
+    wt = torch.randn(B, T, 768, generator=g, device="cuda")
+    wv = torch.randn(B, R, 1024, generator=g, device="cuda")
+    tg, ig = txt.clone().requires_grad_(True), img.clone().requires_grad_(True)
+    tl, vl, _ = enc(tg, ig, tadd, tadd, iadd, None, output_all_encoded_layers=False)
+    ((tl[-1] * wt).sum() + (vl[-1] * wv).sum()).backward()
+    sd = {k: v.detach().to(torch.bfloat16).float().requires_grad_(True) for k, v in enc.state_dict().items()}
+    tf = txt.to(torch.bfloat16).float().requires_grad_(True)
+    vf = img.to(torch.bfloat16).float().requires_grad_(True)
+    to, vo = O.vilbert_encoder(tf, vf, tadd, iadd, sd, "", c)
+    ((to * wt).sum() + (vo * wv).sum()).backward()
+    errs = {"t_out": rel(tl[-1], to), "v_out": rel(vl[-1], vo), "dtxt": rel(tg.grad, tf.grad), "dimg": rel(ig.grad, vf.grad)}
+    print("vilbert real widths:", " ".join("%s=%.2e" % kv for kv in errs.items()))
+    assert max(errs.values()) < 1.5e-2
+    ref = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    unused = [n for n, p in enc.named_parameters() if n not in ref]
+    assert all("q_dense" in n for n in unused)
+    worst, wn = check_param_grads(enc.named_parameters(), ref, 2e-2, skip=unused)
+    print("   worst dW %.2e (%s)" % (worst, wn))
+    # train mode with the reference's dropout probabilities runs and stays finite
+    enc.train()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.1
+    tl, vl, _ = enc(txt, img, tadd, tadd, iadd, None)
+    assert torch.isfinite(tl[-1]).all() and torch.isfinite(vl[-1]).all()
+
+
+def test_bert_encoder_mmft_sequence_length():
+    """BASELINE config 4: 128 text + 196 patch tokens = 324 -> three 128-row query tiles, 384 padded key columns"""
+    from mmf_b200.modules import B200BertEncoder
+    torch.manual_seed(0)
+    B, S, H, heads, I = 2, 324, 768, 12, 3072
+    enc = B200BertEncoder(bert_cfg(H, heads, I, 1)).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(B, S, H, generator=g, device="cuda")
+    mask = torch.ones(B, S, dtype=torch.long, device="cuda")
+    mask[1, 300:] = 0
+    add = O.extended_attention_mask(mask)
+    w_rand = torch.randn(B, S, H, generator=g, device="cuda")
+    xg = x.clone().requires_grad_(True)
+    out = enc(xg, add)[0]
+    (out * w_rand).sum().backward()
+    sd = {k: v.to(torch.bfloat16).float() for k, v in enc.state_dict().items()}
+    o_out, o_dx, o_g = _oracle_run(sd, x.to(torch.bfloat16).float(), add, 1, heads, w_rand)
+    e_out, e_dx = rel(out, o_out), rel(xg.grad, o_dx)
+    print("S=324: out %.2e dx %.2e" % (e_out, e_dx))
+    assert e_out < 1e-2 and e_dx < 1.5e-2
+    check_param_grads(enc.named_parameters(), o_g, 2e-2)
