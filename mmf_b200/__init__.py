@@ -21,7 +21,6 @@ _LAZY = {
     "replace_with_b200": ("patch", "replace_with_b200"),
     "undo_replace_with_b200": ("patch", "undo_replace_with_b200"),
     "attach_encoder": ("patch", "attach_encoder"),
-    "registry": ("registry", "registry"),
     "SampleList": ("sample", "SampleList"),
 }
 
