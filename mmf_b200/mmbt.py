@@ -124,16 +124,18 @@ class B200MMBTModel(nn.Module):
 
 
 def extract_modal_end_token(sample_list):
-    """MMBTBase.extract_modal_end_token (mmbt.py:349-374): returns [SEP] per sample and rewrites input_ids /
-    input_mask in `sample_list` (text shifted left by one) exactly as the reference does."""
-    gather_index = sample_list["input_mask"].sum(1, keepdim=True) - 1
-    modal_end_token = torch.gather(sample_list["input_ids"], 1, gather_index).squeeze(1).clone().detach()
-    batch_size = sample_list["input_ids"].size(0)
-    device = sample_list["input_ids"].device
-    sample_list["input_ids"] = torch.cat([sample_list["input_ids"][:, 1:], sample_list["input_ids"][:, -1:]], dim=1)
-    sample_list["input_mask"] = torch.cat(
-        [sample_list["input_mask"][:, 1:], torch.zeros([batch_size, 1], dtype=torch.long, device=device)], dim=1)
-    return modal_end_token
+    """Semantics of MMBTBase.extract_modal_end_token (mmbt.py:349-374): per sample, the id of the last unmasked
+    token (the [SEP]) is returned, and the text is shifted left by one position in place - the leading [CLS] moves to
+    the modal block, the last id is repeated, the mask gains a trailing 0.  Pure integer indexing (bit-exact)."""
+    ids, mask = sample_list["input_ids"], sample_list["input_mask"]
+    last = mask.sum(dim=1) - 1                                   # index of the last attended token
+    end_token = ids[torch.arange(ids.size(0), device=ids.device), last].clone()
+    sample_list["input_ids"] = torch.roll(ids, shifts=-1, dims=1).index_copy(
+        1, torch.tensor([ids.size(1) - 1], device=ids.device), ids[:, -1:])
+    shifted_mask = torch.roll(mask, shifts=-1, dims=1)
+    shifted_mask[:, -1] = 0
+    sample_list["input_mask"] = shifted_mask
+    return end_token
 
 
 class B200MMBTBase(nn.Module):
@@ -152,18 +154,16 @@ class B200MMBTBase(nn.Module):
         if "modal_token_type_ids" in sample_list:
             modal_tt = sample_list["modal_token_type_ids"]
         else:
-            token_value = 0
+            # segment id given to the modal block (mmbt.py:393-414): with a single text segment it is "the other one"
+            # (1 if the text uses 0, else 0); with several, the last segment unless the text already ends there
             seg = sample_list["segment_ids"]
-            max_id, min_id = seg.max(), seg.min()
-            if max_id == min_id:
-                if max_id == 0:
-                    token_value = 1
+            lo, hi = int(seg.min()), int(seg.max())
+            if lo == hi:
+                token_value = 1 if hi == 0 else 0
             else:
-                max_segment = self.num_max_segment - 1
-                if max_id != max_segment:
-                    token_value = max_segment
-            modal_tt = torch.full((input_modal.size(0), 1), fill_value=token_value, dtype=torch.long,
-                                  device=input_modal.device)
+                top = self.num_max_segment - 1
+                token_value = top if hi != top else 0
+            modal_tt = torch.full((input_modal.size(0), 1), token_value, dtype=torch.long, device=input_modal.device)
         if input_modal.dim() == 2:
             input_modal = input_modal.unsqueeze(dim=1)
         return self.mmbt(input_modal, input_ids=sample_list["input_ids"], modal_start_tokens=start,
