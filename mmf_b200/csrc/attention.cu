@@ -308,23 +308,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
   constexpr int TILE = DC * 16384;   // one [128 x D] bf16 resident-operand tile
   constexpr int CTILE = DC * CB * 128;  // one [CB x D] bf16 looped-operand tile
   constexpr int PBYTES = 128 * CB * 2;  // P' / dS' [128 x CB] bf16
+  constexpr int NCBUF = (CB == 64) ? 2 : 1;   // prefetch the next looped tiles while this iteration computes
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sR = smem;
   uint8_t* sRg = sR + TILE;
   uint8_t* sC = sRg + TILE;
-  uint8_t* sCg = sC + CTILE;
-  uint8_t* sP = sCg + CTILE;      // [128 x CB] bf16, CB/64 chunks of [128 x 128B]
+  uint8_t* sCg = sC + NCBUF * CTILE;   // looped tiles are double-buffered when NCBUF == 2: [buf][tile]
+  uint8_t* sP = sCg + NCBUF * CTILE;   // [128 x CB] bf16, CB/64 chunks of [128 x 128B]
   uint8_t* sDS = sP + PBYTES;
   float* sCol = reinterpret_cast<float*>(sDS + PBYTES);   // [2 buffers][2 stats][128] per-column statistics
   uint32_t* sBits = reinterpret_cast<uint32_t*>(sCol + 512);  // [2 buffers][128 cols][4 words] dropout keep bits
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBits + 1024);
   uint64_t* r_full = bars;
-  uint64_t* c_full = bars + 1;
-  uint64_t* s_ready = bars + 2;
-  uint64_t* p_ready = bars + 3;
-  uint64_t* acc_done = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* c_full = bars + 1;    // [2]
+  uint64_t* s_ready = bars + 3;
+  uint64_t* p_ready = bars + 4;
+  uint64_t* acc_done = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -342,7 +343,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
       tma_prefetch_desc(&tmC);
       tma_prefetch_desc(&tmCg);
       mbar_init(r_full, 1);
-      mbar_init(c_full, 1);
+      mbar_init(&c_full[0], 1);
+      mbar_init(&c_full[1], 1);
       mbar_init(s_ready, 1);
       mbar_init(p_ready, 128);
       mbar_init(acc_done, 1);
@@ -366,31 +368,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
       }
       const uint32_t idesc_s = umma_idesc_bf16(128, CB, false, false);
       const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
-      for (int it = 0; it < n_it; ++it) {
-        if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous accumulation MMAs have consumed C/Cg and P/dS
-        mbar_expect_tx(c_full, 2 * CTILE);
+      auto load_c = [&](int it_, int buf) {
+        mbar_expect_tx(&c_full[buf], 2 * CTILE);
         for (int c = 0; c < DC; ++c) {
-          tma_load_3d(sC + c * CB * 128, &tmC, c_full, h * D + c * 64, it * CB, b);
-          tma_load_3d(sCg + c * CB * 128, &tmCg, c_full, h * D + c * 64, it * CB, b);
+          tma_load_3d(sC + buf * CTILE + c * CB * 128, &tmC, &c_full[buf], h * D + c * 64, it_ * CB, b);
+          tma_load_3d(sCg + buf * CTILE + c * CB * 128, &tmCg, &c_full[buf], h * D + c * 64, it_ * CB, b);
+        }
+      };
+      if (NCBUF == 2) load_c(0, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int cb = (NCBUF == 2) ? (it & 1) : 0;
+        const uint32_t sCb = smem_u32(sC + cb * CTILE), sCgb = smem_u32(sCg + cb * CTILE);
+        if (NCBUF == 1) {
+          if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous accumulation MMAs have consumed C/Cg and P/dS
+          load_c(it, 0);
         }
         if (it == 0) mbar_wait(r_full, 0);
-        mbar_wait(c_full, it & 1);
+        mbar_wait(&c_full[cb], (NCBUF == 2) ? ((it >> 1) & 1) : (it & 1));
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
           const uint32_t coff = (kk >> 2) * CB * 128 + (kk & 3) * 32;
           umma_bf16(tmem_base + COL_S, umma_desc_sw128(smem_u32(sR) + off, 16, 1024),
-                    umma_desc_sw128(smem_u32(sC) + coff, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    umma_desc_sw128(sCb + coff, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
           const uint32_t coff = (kk >> 2) * CB * 128 + (kk & 3) * 32;
           umma_bf16(tmem_base + COL_DP, umma_desc_sw128(smem_u32(sRg) + off, 16, 1024),
-                    umma_desc_sw128(smem_u32(sCg) + coff, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    umma_desc_sw128(sCgb + coff, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(s_ready);
+        if (NCBUF == 2) {
+          // the other buffer was last read by the accumulation MMAs of iteration it-1 (issued before the S'/dP' MMAs of
+          // this iteration, so normally long complete): once they are done, stream the next tiles into it
+          if (it > 0) mbar_wait(acc_done, (it - 1) & 1);
+          if (it + 1 < n_it) load_c(it + 1, cb ^ 1);
+        }
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
         // accumulate over the CB looped positions (K dimension of these MMAs), B operands MN-major
@@ -398,14 +414,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
         for (int kk = 0; kk < CB / 16; ++kk) {
           const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
           umma_bf16(tmem_base + COL_O0, umma_desc_sw128(smem_u32(sDS) + aoff, 16, 1024),
-                    umma_desc_sw128(smem_u32(sC) + kk * 2048, CB * 128, 1024), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
+                    umma_desc_sw128(sCb + kk * 2048, CB * 128, 1024), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
         }
         if (!ROWS_ARE_Q) {
 #pragma unroll
           for (int kk = 0; kk < CB / 16; ++kk) {
             const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
             umma_bf16(tmem_base + COL_O1, umma_desc_sw128(smem_u32(sP) + aoff, 16, 1024),
-                      umma_desc_sw128(smem_u32(sCg) + kk * 2048, CB * 128, 1024), idesc_o,
+                      umma_desc_sw128(sCgb + kk * 2048, CB * 128, 1024), idesc_o,
                       (it > 0 || kk > 0) ? 1u : 0u);
           }
         }
@@ -700,7 +716,7 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   }
   constexpr int DC = D / 64;
   constexpr int CB = (D == 64) ? 64 : 128;   // d = 64: 64-wide looped blocks -> 256 TMEM columns, 2 CTAs per SM
-  const int smem = 2 * DC * 16384 + 2 * DC * CB * 128 + 2 * (128 * CB * 2) + 2048 + 4096 + 128 + 1024;
+  const int smem = 2 * DC * 16384 + (CB == 64 ? 2 : 1) * 2 * DC * CB * 128 + 2 * (128 * CB * 2) + 2048 + 4096 + 128 + 1024;
   AttnBwdDev p;
   p.B = a.B; p.H = a.heads; p.Sq = a.Sq; p.Skv = a.Skv;
   p.mask = a.mask; p.lse2 = a.lse2; p.delta = a.delta;
