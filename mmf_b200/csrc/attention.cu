@@ -21,6 +21,8 @@
 // In both, thread r owns row r of the 128x128 S'/dP' tiles in TMEM, writes P'/dS' (bf16) to shared
 // memory as K-major A operands and the looped operand tile is re-read MN-major as the B operand of
 // the accumulation MMA - no transposes, no atomics, deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mmfb_internal.h"
 
@@ -588,6 +590,266 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// fused backward (d = 64, Sq, Skv <= 256): one CTA per (batch, head)
+//
+// Q, dO, K, V of the head stay resident in shared memory (8 tiles of [128 x 64]).  For every 128x128 block pair
+// (query block i, key block j) the scores S = Q_i K_j^T and dP = dO_i V_j^T are computed ONCE (the two-kernel path
+// recomputes them, and the exp / dropout / dS arithmetic, in both launches); thread == query row turns them into
+// P' and dS' (bf16, K-major [q][kv] in smem) and three accumulations consume the same two buffers:
+//     dQ_i += dS' K_j        A = dS' K-major  (M = q),   B = K_j  MN-major
+//     dK_j += dS'^T Q_i      A = dS' MN-major (M = kv),  B = Q_i  MN-major      (transposed view, no data movement)
+//     dV_j += P'^T dO_i      A = P'  MN-major (M = kv),  B = dO_i MN-major
+// TMEM (512 columns): S 128 | dP 128 | dQ_0 64 | dQ_1 64 | dK_j 64 | dV_j 64.
+// 288 threads: warps 0..7 compute (two threads per row, alternate 32-column chunks), warp 8 = TMA + MMA issue.
+// ----------------------------------------------------------------------------------------------
+struct AttnBwdFusedDev {
+  int B, H, Sq, Skv;
+  const float* mask;
+  const float* lse2;
+  const float* delta;
+  const uint32_t* dmask;
+  int W;
+  float dscale, scale2, scale;
+  bf16* dq; int64_t ld_dq;
+  bf16* dk; int64_t ld_dk;
+  bf16* dv; int64_t ld_dv;
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(288, 1)
+attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      AttnBwdFusedDev p) {
+  constexpr int D = 64;
+  constexpr int TILE = 16384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // [2][128 x 128B]
+  uint8_t* sdO = sQ + 2 * TILE;
+  uint8_t* sK = sdO + 2 * TILE;
+  uint8_t* sV = sK + 2 * TILE;
+  uint8_t* sP = sV + 2 * TILE;        // [128 q x 128 kv] bf16 = 2 chunks of [128 x 128B]
+  uint8_t* sDS = sP + 2 * TILE;
+  float* sLse = reinterpret_cast<float*>(sDS + 2 * TILE);   // [256] per query: lse (log2 domain), +inf if invalid
+  float* sDel = sLse + 256;                                 // [256] per query: delta
+  float* sMsk = sDel + 256;                                 // [256] per key: additive mask * log2e, -inf if invalid
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMsk + 256);
+  uint64_t* r_full = bars;
+  uint64_t* s_ready = bars + 1;
+  uint64_t* p_ready = bars + 2;
+  uint64_t* acc_done = bars + 3;
+  uint64_t* kv_read = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ni = (p.Sq + 127) / 128, nj = (p.Skv + 127) / 128;
+  const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      mbar_init(r_full, 1);
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, 256);
+      mbar_init(acc_done, 1);
+      mbar_init(kv_read, 256);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else {
+    for (int i = threadIdx.x; i < 256; i += 256) {
+      const bool qv = i < p.Sq, kv = i < p.Skv;
+      sLse[i] = qv ? p.lse2[bh * p.Sq + i] : INFINITY;
+      sDel[i] = qv ? p.delta[bh * p.Sq + i] : 0.0f;
+      sMsk[i] = kv ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, (2 * ni + 2 * nj) * TILE);
+      for (int i = 0; i < ni; ++i) {
+        tma_load_3d(sQ + i * TILE, &tmQ, r_full, h * D, i * 128, b);
+        tma_load_3d(sdO + i * TILE, &tmdO, r_full, h * D, i * 128, b);
+      }
+      for (int j = 0; j < nj; ++j) {
+        tma_load_3d(sK + j * TILE, &tmK, r_full, h * D, j * 128, b);
+        tma_load_3d(sV + j * TILE, &tmV, r_full, h * D, j * 128, b);
+      }
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      const uint32_t idesc_q = umma_idesc_bf16(128, D, false, true);   // A K-major,  B MN-major
+      const uint32_t idesc_t = umma_idesc_bf16(128, D, true, true);    // A MN-major, B MN-major
+      mbar_wait(r_full, 0);
+      int pair = 0;
+      for (int j = 0; j < nj; ++j) {
+        for (int i = 0; i < ni; ++i, ++pair) {
+          tc_fence_after();
+          const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
+          const uint32_t aK = smem_u32(sK + j * TILE), aV = smem_u32(sV + j * TILE);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + COL_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
+                      idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + COL_DP, umma_desc_sw128(adO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024),
+                      idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(s_ready);
+          mbar_wait(p_ready, pair & 1);
+          // dK_j / dV_j of the previous key block must have been read out before the first pair of this block overwrites them
+          if (i == 0 && j > 0) mbar_wait(kv_read, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {   // K dimension = the 128 keys of block j
+            const uint32_t aoff = (kk >> 2) * TILE + (kk & 3) * 32;
+            umma_bf16(tmem_base + COL_DQ + i * D, umma_desc_sw128(smem_u32(sDS) + aoff, 16, 1024),
+                      umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {   // K dimension = the 128 queries of block i; A = transposed views
+            umma_bf16(tmem_base + COL_DK, umma_desc_sw128(smem_u32(sDS) + kk * 2048, TILE, 1024),
+                      umma_desc_sw128(aQ + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + COL_DV, umma_desc_sw128(smem_u32(sP) + kk * 2048, TILE, 1024),
+                      umma_desc_sw128(adO + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(acc_done);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    int pair = 0;
+    for (int j = 0; j < nj; ++j) {
+      for (int i = 0; i < ni; ++i, ++pair) {
+        const int q = i * 128 + row;
+        const float l2 = sLse[q], dl = sDel[q];
+        if (pair > 0) mbar_wait(acc_done, (pair - 1) & 1);   // P'/dS' buffers are free again
+        mbar_wait(s_ready, pair & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half; c < 4; c += 2) {
+          uint32_t rs[32], rd[32];
+          tmem_ld32(trow + COL_S + c * 32, rs);
+          tmem_ld32(trow + COL_DP + c * 32, rd);
+          tmem_ld_wait();
+          uint32_t bits = 0xFFFFFFFFu;
+          if (DROP && q < p.Sq) {
+            const int w = j * 4 + c;
+            if (w < p.W) bits = __ldg(p.dmask + (bh * p.Sq + q) * p.W + w);
+          }
+          const float4* m4 = reinterpret_cast<const float4*>(sMsk + j * 128 + c * 32);
+          float pv[32], ds[32];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 m = m4[q4];
+            const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int jx = q4 * 4 + k;
+              const float pr = ex2_approx(fmaf(__uint_as_float(rs[jx]), p.scale2, mm[k]) - l2);
+              float dp = __uint_as_float(rd[jx]);
+              float pk = pr;
+              if (DROP) {
+                const bool kp = (bits >> jx) & 1u;
+                dp = kp ? dp * p.dscale : 0.0f;
+                pk = kp ? pr * p.dscale : 0.0f;
+              }
+              ds[jx] = pr * (dp - dl);
+              pv[jx] = pk;
+            }
+          }
+          uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
+          uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
+            uint4 o;
+            o.x = pack_bf16x2(ds[qd * 8 + 0], ds[qd * 8 + 1]);
+            o.y = pack_bf16x2(ds[qd * 8 + 2], ds[qd * 8 + 3]);
+            o.z = pack_bf16x2(ds[qd * 8 + 4], ds[qd * 8 + 5]);
+            o.w = pack_bf16x2(ds[qd * 8 + 6], ds[qd * 8 + 7]);
+            *reinterpret_cast<uint4*>(dsrow + chunk * 16) = o;
+            o.x = pack_bf16x2(pv[qd * 8 + 0], pv[qd * 8 + 1]);
+            o.y = pack_bf16x2(pv[qd * 8 + 2], pv[qd * 8 + 3]);
+            o.z = pack_bf16x2(pv[qd * 8 + 4], pv[qd * 8 + 5]);
+            o.w = pack_bf16x2(pv[qd * 8 + 6], pv[qd * 8 + 7]);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+      // ---- dK_j, dV_j are complete: rows = keys of block j; this thread stores 32 of the 64 columns of each ----
+      mbar_wait(acc_done, (pair - 1) & 1);
+      tc_fence_after();
+      {
+        const int kvr = j * 128 + row;
+        uint32_t rk[32], rv[32];
+        tmem_ld32(trow + COL_DK + half * 32, rk);
+        tmem_ld32(trow + COL_DV + half * 32, rv);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(kv_read);
+        if (kvr < p.Skv) {
+          uint4* dk4 = reinterpret_cast<uint4*>(p.dk + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dk + h * D + half * 32);
+          uint4* dv4 = reinterpret_cast<uint4*>(p.dv + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dv + h * D + half * 32);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(rk[qd * 8 + 0]) * p.scale, __uint_as_float(rk[qd * 8 + 1]) * p.scale);
+            o.y = pack_bf16x2(__uint_as_float(rk[qd * 8 + 2]) * p.scale, __uint_as_float(rk[qd * 8 + 3]) * p.scale);
+            o.z = pack_bf16x2(__uint_as_float(rk[qd * 8 + 4]) * p.scale, __uint_as_float(rk[qd * 8 + 5]) * p.scale);
+            o.w = pack_bf16x2(__uint_as_float(rk[qd * 8 + 6]) * p.scale, __uint_as_float(rk[qd * 8 + 7]) * p.scale);
+            dk4[qd] = o;
+            o.x = pack_bf16x2(__uint_as_float(rv[qd * 8 + 0]), __uint_as_float(rv[qd * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(rv[qd * 8 + 2]), __uint_as_float(rv[qd * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(rv[qd * 8 + 4]), __uint_as_float(rv[qd * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(rv[qd * 8 + 6]), __uint_as_float(rv[qd * 8 + 7]));
+            dv4[qd] = o;
+          }
+        }
+      }
+    }
+    // ---- dQ_i: rows = queries ----
+    for (int i = 0; i < ni; ++i) {
+      const int q = i * 128 + row;
+      uint32_t rq[32];
+      tmem_ld32(trow + COL_DQ + i * D + half * 32, rq);
+      tmem_ld_wait();
+      if (q < p.Sq) {
+        uint4* dq4 = reinterpret_cast<uint4*>(p.dq + (static_cast<int64_t>(b) * p.Sq + q) * p.ld_dq + h * D + half * 32);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(rq[qd * 8 + 0]) * p.scale, __uint_as_float(rq[qd * 8 + 1]) * p.scale);
+          o.y = pack_bf16x2(__uint_as_float(rq[qd * 8 + 2]) * p.scale, __uint_as_float(rq[qd * 8 + 3]) * p.scale);
+          o.z = pack_bf16x2(__uint_as_float(rq[qd * 8 + 4]) * p.scale, __uint_as_float(rq[qd * 8 + 5]) * p.scale);
+          o.w = pack_bf16x2(__uint_as_float(rq[qd * 8 + 6]) * p.scale, __uint_as_float(rq[qd * 8 + 7]) * p.scale);
+          dq4[qd] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d].  One warp per token row, 16-byte vector loads; a head of D
 // elements is owned by D/8 consecutive lanes and reduced with shuffles (coalesced 512 B / 1 KB per warp access).
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
@@ -713,6 +975,38 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
         reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, a.ctx32, a.delta,
         a.B, a.heads, a.Sq, D);
     count_launch();
+  }
+  // d = 64 and both sequences within two 128-row blocks: single fused kernel, S/dP/exp computed once per block pair
+  static int use_fused = -1;
+  if (use_fused < 0) {
+    const char* e = getenv("MMFB_ATTN_FUSED_BWD");
+    use_fused = (e == nullptr) ? 1 : (e[0] != '0');
+  }
+  if (D == 64 && use_fused && a.Sq <= 256 && a.Skv <= 256) {
+    const int smem = 12 * 16384 + 3 * 1024 + 128 + 1024;
+    AttnBwdFusedDev f;
+    f.B = a.B; f.H = a.heads; f.Sq = a.Sq; f.Skv = a.Skv;
+    f.mask = a.mask; f.lse2 = a.lse2; f.delta = a.delta;
+    f.dmask = a.drop_mask; f.W = (a.Skv + 31) / 32; f.dscale = a.drop_mask ? a.drop_scale : 1.0f;
+    f.scale = 1.0f / sqrtf(static_cast<float>(D));
+    f.scale2 = LOG2E * f.scale;
+    f.dq = reinterpret_cast<bf16*>(a.dq); f.ld_dq = a.ld_dq;
+    f.dk = reinterpret_cast<bf16*>(a.dk); f.ld_dk = a.ld_dk;
+    f.dv = reinterpret_cast<bf16*>(a.dv); f.ld_dv = a.ld_dv;
+    static bool fset = false;
+    if (!fset) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd_fused smem attr: %s", cudaGetErrorString(e));
+      fset = true;
+    }
+    dim3 grid(a.heads, a.B);
+    if (f.dmask != nullptr) attn_bwd_fused_kernel<true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+    else attn_bwd_fused_kernel<false><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd_fused launch: %s", cudaGetErrorString(e));
+    return MMFB_OK;
   }
   constexpr int DC = D / 64;
   constexpr int CB = (D == 64) ? 64 : 128;   // d = 64: 64-wide looped blocks -> 256 TMEM columns, 2 CTAs per SM
