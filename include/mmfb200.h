@@ -45,7 +45,8 @@ enum {
   MMFB_EPI_BIAS_DROP_RESID = 2, /* C = dropout(acc + bias) + aux       BertSelfOutput/BertOutput pre-LN */
   MMFB_EPI_GELU_BWD = 3,        /* C = acc * gelu_erf'(aux)            dgrad through BertIntermediate */
   MMFB_EPI_ADD_AUX = 4,         /* C = acc + aux                       dgrad + residual gradient     */
-  MMFB_EPI_ATOMIC_F32 = 5       /* C(fp32) += acc                      split-K weight gradient       */
+  MMFB_EPI_ATOMIC_F32 = 5,      /* C(fp32) += acc                      split-K weight gradient       */
+  MMFB_EPI_BIAS_RELU = 6        /* C = relu(acc + bias)                FinetuneFasterRcnnFpnFc7, encoders.py:176-179 */
 };
 
 /* C[M,N] = epi( A[M,K] * B[N,K]^T ).  a_mn/b_mn = 0: operand stored [rows,K] (K contiguous);
@@ -152,6 +153,9 @@ int mmfb_embed_scatter(const mmfb_scatter_args* args, mmfb_stream stream);
  * Equal indices are summed in registers first (one atomic per run of <= 32 rows instead of one per row). */
 int mmfb_embed_scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int32_t* sorted_idx, float* dtab,
                               int M, int H, mmfb_stream stream);
+
+/* dz = dy where y > 0 else 0 (backward of the ReLU epilogue); contiguous bf16 buffers of n elements */
+int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_stream stream);
 
 /* fp32 -> bf16 cast of a flat (parameter) buffer */
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream);

@@ -172,6 +172,11 @@ int mmfb_embed_scatter_sorted(const void* dy, int64_t lddy, const int32_t* order
   MMFB_REQUIRE_DEVICE();
   return scatter_sorted(dy, lddy, order, sorted_idx, dtab, M, H, reinterpret_cast<cudaStream_t>(stream));
 }
+int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_stream stream) {
+  if (!dy || !y || !dz) return set_error(MMFB_ERR_ARG, "mmfb_relu_bwd: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return relu_bwd(dy, y, dz, n, reinterpret_cast<cudaStream_t>(stream));
+}
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream) {
   if (!in || !out) return set_error(MMFB_ERR_ARG, "mmfb_cast_f32_bf16: null pointer");
   MMFB_REQUIRE_DEVICE();

@@ -320,7 +320,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RESID) {
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RESID || EPI == EPI_BIAS_RELU) {
               if (p.bias != nullptr && n < p.N) {
                 const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n);
 #pragma unroll
@@ -335,6 +335,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   }
                 }
               }
+            }
+            if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
             if (EPI == EPI_BIAS_DROP_RESID) {
               if (p.dmask != nullptr && row_ok && n < p.N) {
@@ -514,6 +518,7 @@ static int dispatch(const mmfb_gemm_args& a, cudaStream_t s) {
     case 0 + EPI_BIAS: return launch<BN, false, false, EPI_BIAS, MC>(a, s);
     case 0 + EPI_BIAS_GELU: return launch<BN, false, false, EPI_BIAS_GELU, MC>(a, s);
     case 0 + EPI_BIAS_DROP_RESID: return launch<BN, false, false, EPI_BIAS_DROP_RESID, MC>(a, s);
+    case 0 + EPI_BIAS_RELU: return launch<BN, false, false, EPI_BIAS_RELU, MC>(a, s);
     case 10 + EPI_BIAS: return launch<BN, false, true, EPI_BIAS, MC>(a, s);
     case 10 + EPI_GELU_BWD: return launch<BN, false, true, EPI_GELU_BWD, MC>(a, s);
     case 10 + EPI_ADD_AUX: return launch<BN, false, true, EPI_ADD_AUX, MC>(a, s);

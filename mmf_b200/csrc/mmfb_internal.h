@@ -14,7 +14,8 @@ enum {
   EPI_BIAS_DROP_RESID = MMFB_EPI_BIAS_DROP_RESID,
   EPI_GELU_BWD = MMFB_EPI_GELU_BWD,
   EPI_ADD_AUX = MMFB_EPI_ADD_AUX,
-  EPI_ATOMIC_F32 = MMFB_EPI_ATOMIC_F32
+  EPI_ATOMIC_F32 = MMFB_EPI_ATOMIC_F32,
+  EPI_BIAS_RELU = MMFB_EPI_BIAS_RELU
 };
 
 // records a thread-local error message and returns `code`
@@ -40,6 +41,7 @@ int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, 
 int compose(const mmfb_compose_args& a, cudaStream_t s);
 int scatter(const mmfb_scatter_args& a, cudaStream_t s);
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s);
+int relu_bwd(const void* dy, const void* y, void* dz, int64_t n, cudaStream_t s);
 int scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int32_t* sorted_idx, float* dtab, int M,
                    int H, cudaStream_t s);
 

@@ -481,6 +481,21 @@ scatter_sorted_kernel(const bf16* __restrict__ dy, int64_t lddy, const int32_t* 
   }
 }
 
+// backward of the ReLU epilogue: dz = (y > 0) ? dy : 0, 16-byte vectors
+__global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ dz, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float a[8], b[8];
+    ld8(dy + i, a);
+    ld8(y + i, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = b[e] > 0.0f ? a[e] : 0.0f;
+    st8(dz + i, a);
+  } else {
+    for (int64_t j = i; j < n; ++j) dz[j] = __bfloat162float(y[j]) > 0.0f ? dy[j] : __float2bfloat16_rn(0.0f);
+  }
+}
+
 // fp32 -> bf16 cast of the flat parameter buffer (done every forward, like autocast does)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
@@ -628,6 +643,15 @@ int scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int
   if (nv <= 1) SS(1); else if (nv == 2) SS(2); else if (nv == 3) SS(3); else SS(4);
 #undef SS
   return launch_ok("embed_scatter_sorted");
+}
+
+int relu_bwd(const void* dy, const void* y, void* dz, int64_t n, cudaStream_t s) {
+  if (n <= 0) return set_error(MMFB_ERR_ARG, "relu_bwd: empty");
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dz)) & 15)
+    return set_error(MMFB_ERR_ARG, "relu_bwd: buffers must be 16-byte aligned");
+  const int64_t thr = (n + 7) / 8;
+  relu_bwd_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)y, (bf16*)dz, n);
+  return launch_ok("relu_bwd");
 }
 
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s) {

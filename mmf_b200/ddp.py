@@ -64,6 +64,8 @@ class B200DataParallel(nn.Module):
             self._queue_finalize()
             pack = runner.pack
             st = self._state.setdefault(id(runner), {"hi": None})
+            if pack.on_reentry is None:
+                pack.on_reentry = lambda: self._reenter(runner)
             if st["hi"] is None:
                 st["hi"] = pack.total
             lo = self._step_offset(runner, step_index)
@@ -72,6 +74,18 @@ class B200DataParallel(nn.Module):
                 self._all_reduce(pack.grad[lo:st["hi"]])
                 st["hi"] = lo
         return hook
+
+    def _reenter(self, runner):
+        """The runner backs a second autograd node of the SAME backward pass (module applied twice in the graph): its
+        kernels are about to add local gradients on top of regions that were already averaged.  Let the in-flight
+        all-reduces land, then send every region again as the second node completes it: the mean over ranks of
+        (already-averaged part + local part) is the mean of the total, the averaged part being equal on all ranks."""
+        if self._comm_stream is not None and self._pending:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._pending = []
+        st = self._state.get(id(runner))
+        if st is not None:
+            st["hi"] = None
 
     @staticmethod
     def _step_offset(runner, step_index):

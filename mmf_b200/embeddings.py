@@ -100,7 +100,7 @@ class _VLEmbedFn(torch.autograd.Function):
             F.embed_scatter(dy, dsrcs=dsrcs)
         for k in ("i0", "i1", "i2"):
             if k + "_sorted" not in idx:      # indices are known in the forward; sorted lazily once per batch
-                idx[k + "_sorted"] = F.sort_indices(idx[k])
+                idx[k + "_sorted"] = F.sort_indices(idx.get(k + "_bwd", idx[k]))
             F.embed_scatter_sorted(dy, runner.big_g, *idx[k + "_sorted"])
         dfeats = None
         if R > 0:
@@ -121,7 +121,8 @@ class B200VisioLinguisticEmbeddings(nn.Module):
     def __init__(self, config):
         super().__init__()
         H = config.hidden_size
-        self.word_embeddings = nn.Embedding(config.vocab_size, H)
+        # HF BertEmbeddings: padding_idx = pad_token_id, i.e. the [PAD] row gets no gradient
+        self.word_embeddings = nn.Embedding(config.vocab_size, H, padding_idx=getattr(config, "pad_token_id", 0))
         self.position_embeddings = nn.Embedding(config.max_position_embeddings, H)
         self.token_type_embeddings = nn.Embedding(config.type_vocab_size, H)
         self.token_type_embeddings_visual = nn.Embedding(config.type_vocab_size, H)
@@ -160,7 +161,12 @@ class B200VisioLinguisticEmbeddings(nn.Module):
         src = torch.cat([torch.full((B, T), -1, dtype=torch.long, device=dev)] +
                         ([torch.arange(B * R, device=dev).view(B, R)] if R else []), dim=1)
         to32 = lambda t: t.reshape(-1).to(torch.int32).contiguous()
-        return {"i0": to32(i0), "i1": to32(i1), "i2": to32(i2), "src_row": to32(src)}
+        out = {"i0": to32(i0), "i1": to32(i1), "i2": to32(i2), "src_row": to32(src)}
+        pad = self.word_embeddings.padding_idx
+        if pad is not None:   # nn.Embedding(padding_idx=): the row is read but gets no gradient
+            ids_b = torch.where(input_ids == pad, torch.full_like(input_ids, -1), input_ids + o_word)
+            out["i0_bwd"] = to32(torch.cat([ids_b] + ([visual_embeddings_type + o_tvis] if R else []), dim=1))
+        return out
 
     def forward(self, input_ids, token_type_ids=None, visual_embeddings=None, visual_embeddings_type=None,
                 image_text_alignment=None):
@@ -196,7 +202,7 @@ class B200VisioLinguisticEmbeddings(nn.Module):
             token_type_ids = torch.zeros_like(input_ids)
         pos = torch.arange(T, device=dev).unsqueeze(0).expand(B, T)
         p_drop = float(self.dropout.p)
-        text = ops.compose_ln(B * T, H, [], [(self.word_embeddings.weight, ops.i32(input_ids)),
+        text = ops.compose_ln(B * T, H, [], [(self.word_embeddings.weight, ops.i32(input_ids), self.word_embeddings.padding_idx),
                                              (self.position_embeddings.weight, ops.i32(pos)),
                                              (self.token_type_embeddings.weight, ops.i32(token_type_ids))],
                               self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, p_drop, self.training)

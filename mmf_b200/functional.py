@@ -217,6 +217,16 @@ def dropout_bits(shape_rows, ncols, p, seed, offset, device):
     return out
 
 
+def relu_bwd(dy, y):
+    """dz = dy where y > 0 else 0 (bf16, contiguous)."""
+    _req(dy, torch.bfloat16, "dy"); _req(y, torch.bfloat16, "y")
+    if not (dy.is_contiguous() and y.is_contiguous()) or dy.numel() != y.numel():
+        raise ValueError("relu_bwd: contiguous, equally sized buffers required")
+    dz = torch.empty_like(dy)
+    check(LIB.mmfb_relu_bwd(dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), _stream_ptr()))
+    return dz
+
+
 def cast_f32_bf16(src, dst):
     _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
     if src.numel() != dst.numel() or not src.is_contiguous() or not dst.is_contiguous():

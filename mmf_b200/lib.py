@@ -17,6 +17,7 @@ EPI_BIAS_DROP_RESID = 2
 EPI_GELU_BWD = 3
 EPI_ADD_AUX = 4
 EPI_ATOMIC_F32 = 5
+EPI_BIAS_RELU = 6
 
 
 class GemmArgs(ctypes.Structure):
@@ -109,6 +110,7 @@ def _load():
                                       ctypes.c_float, ctypes.c_void_p]
     lib.mmfb_embed_scatter_sorted.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.mmfb_relu_bwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.mmfb_cast_f32_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     return lib
 

@@ -22,7 +22,8 @@ class _BertEmbeddingsHolder(nn.Module):
     def __init__(self, config):
         super().__init__()
         H = config.hidden_size
-        self.word_embeddings = nn.Embedding(config.vocab_size, H)
+        # HF BertEmbeddings: padding_idx = pad_token_id, i.e. the [PAD] row gets no gradient
+        self.word_embeddings = nn.Embedding(config.vocab_size, H, padding_idx=getattr(config, "pad_token_id", 0))
         self.position_embeddings = nn.Embedding(config.max_position_embeddings, H)
         self.token_type_embeddings = nn.Embedding(config.type_vocab_size, H)
         self.LayerNorm = nn.LayerNorm(H, eps=float(getattr(config, "layer_norm_eps", 1e-12)))
@@ -109,7 +110,7 @@ class B200MMBTModel(nn.Module):
         typ = torch.cat([type_m, token_type_ids], dim=1)
         S = L + T
         x = ops.compose_ln(B * S, H, srcs=[(proj, ops.i32(src))],
-                           tabs=[(emb.word_embeddings.weight, ops.i32(word)), (emb.position_embeddings.weight, ops.i32(pos)),
+                           tabs=[(emb.word_embeddings.weight, ops.i32(word), emb.word_embeddings.padding_idx), (emb.position_embeddings.weight, ops.i32(pos)),
                                  (emb.token_type_embeddings.weight, ops.i32(typ))],
                            ln_weight=emb.LayerNorm.weight, ln_bias=emb.LayerNorm.bias, eps=emb.LayerNorm.eps,
                            p=float(emb.dropout.p), training=self.training).view(B, S, H)

@@ -88,7 +88,7 @@ class B200HuggingfaceEmbeddings(nn.Module):
             srcs, tabs = [], []
             te = self.token_embeddings[idx]
             if isinstance(te, nn.Embedding):
-                tabs.append((te.weight, ops.i32(tok)))
+                tabs.append((te.weight, ops.i32(tok), te.padding_idx))
             else:
                 lin, ln_in = te[0], te[1]
                 x = ops.linear(tok.reshape(B * N, -1), lin.weight, lin.bias)

@@ -52,6 +52,40 @@ def linear(x2d, weight, bias=None):
     return _Linear.apply(x2d, weight, bias)
 
 
+class _LinearReLU(torch.autograd.Function):
+    """y = relu(x W^T + b): GEMM with the ReLU epilogue; backward masks dy with (y > 0) and reuses the Linear backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xb, wb, bb = _bf16(x), _bf16(weight), _bf16(bias)
+        y = F.gemm(xb, wb, epi=lib.EPI_BIAS_RELU, bias=bb)
+        ctx.save_for_backward(xb, wb, y)
+        ctx.dtypes = (x.dtype, weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb, y = ctx.saved_tensors
+        dz = F.relu_bwd(dy.to(torch.bfloat16).contiguous(), y)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = F.gemm(dz, wb, b_mn=True, epi=lib.EPI_BIAS).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(wb.shape, dtype=torch.float32, device=wb.device)
+            F.gemm(dz, xb, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=dw,
+                   splits=best_splits(wb.shape[0], wb.shape[1], xb.shape[0]))
+            dw = dw.to(ctx.dtypes[1])
+        if ctx.needs_input_grad[2]:
+            db = torch.zeros(wb.shape[0], dtype=torch.float32, device=wb.device)
+            F.colsum(dz, db)
+            db = db.to(ctx.dtypes[2])
+        return dx, dw, db
+
+
+def linear_relu(x2d, weight, bias):
+    return _LinearReLU.apply(x2d, weight, bias)
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
@@ -86,7 +120,7 @@ class _ComposeLN(torch.autograd.Function):
         srcs = [_bf16(t) for t in tensors[:n_src]]
         tabs = [_bf16(t) for t in tensors[n_src:n_src + n_tab]]
         g, b = _bf16(tensors[-2]), _bf16(tensors[-1])
-        y = F.embed_compose(M, H, srcs=list(zip(srcs, rows)), tabs=list(zip(tabs, idxs)), device=g.device)
+        y = F.embed_compose(M, H, srcs=list(zip(srcs, rows)), tabs=list(zip(tabs, idxs[0])), device=g.device)
         x, mean, rstd = F.layernorm_fwd(y, g, b, eps, drop_mask=bits, drop_scale=scale)
         ctx.meta = meta
         ctx.src_shapes = [tuple(t.shape) for t in srcs]
@@ -109,14 +143,14 @@ class _ComposeLN(torch.autograd.Function):
         dtabs = [torch.zeros(s, dtype=torch.float32, device=g.device) for s in ctx.tab_shapes]
         if dsrcs:
             F.embed_scatter(dy, dsrcs=list(zip(dsrcs, rows)))
-        for t, ix in zip(dtabs, idxs):
-            F.embed_scatter_sorted(dy, t, *F.sort_indices(ix))
+        for t, ix in zip(dtabs, idxs[1]):
+            F.embed_scatter_sorted(dy, t, *F.sort_indices(ix))   # idxs already carry -1 at padding_idx rows
         grads = [t.to(dt) for t, dt in zip(dsrcs + dtabs + [dg, db], ctx.dtypes)]
         return (None,) + tuple(grads)
 
 
 def compose_ln(M, H, srcs, tabs, ln_weight, ln_bias, eps=1e-12, p=0.0, training=False, dropout_state=None):
-    """srcs: up to 2 (tensor [*, H], int32 rows [M]); tabs: up to 3 (table [V, H], int32 idx [M]).
+    """srcs: up to 2 (tensor [*, H], int32 rows [M]); tabs: up to 3 (table [V, H], int32 idx [M][, padding_idx]).
     The same table may appear in several slots.  Returns bf16 [M, H]."""
     if len(srcs) > 2 or len(tabs) > 3:
         raise ValueError("compose_ln: at most 2 dense sources and 3 table slots")
@@ -125,8 +159,13 @@ def compose_ln(M, H, srcs, tabs, ln_weight, ln_bias, eps=1e-12, p=0.0, training=
         from .modules import _fresh_dropout_state
         ds = dropout_state or _fresh_dropout_state()
         bits, scale = ds.bits((M,), H, p, ln_weight.device), 1.0 / (1.0 - p)
-    meta = (M, H, len(srcs), len(tabs), [r for _, r in srcs], [i for _, i in tabs], float(eps), bits, scale)
-    return _ComposeLN.apply(meta, *[t for t, _ in srcs], *[t for t, _ in tabs], ln_weight, ln_bias)
+    # a table slot may be (table, idx, padding_idx): the row is read in the forward but, like nn.Embedding(padding_idx=),
+    # receives no gradient - the backward index gets -1 (= absent) there
+    fwd_idx = [t[1] for t in tabs]
+    bwd_idx = [t[1] if len(t) < 3 or t[2] is None else torch.where(t[1] == t[2], torch.full_like(t[1], -1), t[1])
+               for t in tabs]
+    meta = (M, H, len(srcs), len(tabs), [r for _, r in srcs], (fwd_idx, bwd_idx), float(eps), bits, scale)
+    return _ComposeLN.apply(meta, *[t for t, _ in srcs], *[t[0] for t in tabs], ln_weight, ln_bias)
 
 
 def i32(t):

@@ -48,7 +48,7 @@ class B200BertTextEmbeddings(_BertEmbeddingsHolder):
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
         H = self.LayerNorm.weight.shape[0]
-        y = ops.compose_ln(B * T, H, [], [(self.word_embeddings.weight, ops.i32(input_ids)),
+        y = ops.compose_ln(B * T, H, [], [(self.word_embeddings.weight, ops.i32(input_ids), self.word_embeddings.padding_idx),
                                           (self.position_embeddings.weight, ops.i32(position_ids)),
                                           (self.token_type_embeddings.weight, ops.i32(token_type_ids))],
                            self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, float(self.dropout.p),

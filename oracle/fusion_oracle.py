@@ -230,7 +230,7 @@ def visio_linguistic_embeddings(input_ids, token_type_ids, visual_embeddings, vi
     pos = torch.arange(T, dtype=torch.long, device=input_ids.device).unsqueeze(0).expand_as(input_ids)
     if token_type_ids is None:
         token_type_ids = torch.zeros_like(input_ids)
-    text = (sd[prefix + ".word_embeddings.weight"][input_ids] + sd[prefix + ".position_embeddings.weight"][pos]
+    text = (embedding(sd[prefix + ".word_embeddings.weight"], input_ids, 0) + sd[prefix + ".position_embeddings.weight"][pos]
             + sd[prefix + ".token_type_embeddings.weight"][token_type_ids])
     if visual_embeddings is not None and visual_embeddings_type is not None:
         v = linear(visual_embeddings, sd, prefix + ".projection")
@@ -263,16 +263,50 @@ def visual_bert_masks(input_mask, max_features, num_regions):
     return image_mask, visual_embeddings_type, attention_mask
 
 
-def bert_embeddings(input_ids, token_type_ids, sd, prefix, position_ids=None, keep=None, p=0.0):
+def embedding(table, ids, padding_idx=None):
+    """nn.Embedding lookup; with padding_idx the row is read but receives no gradient (HF BertEmbeddings builds
+    word_embeddings with padding_idx=config.pad_token_id=0; huggingface.py:70-75 does the same)."""
+    out = table[ids]
+    if padding_idx is None:
+        return out
+    return torch.where((ids == padding_idx).unsqueeze(-1), out.detach(), out)
+
+
+def bert_embeddings(input_ids, token_type_ids, sd, prefix, position_ids=None, keep=None, p=0.0, padding_idx=0):
     """BertEmbeddingsJit.forward, mmf/modules/hf_layers.py:107-135."""
     B, T = input_ids.shape
     if position_ids is None:
         position_ids = torch.arange(T, dtype=torch.long, device=input_ids.device).unsqueeze(0).expand(B, T)
     if token_type_ids is None:
         token_type_ids = torch.zeros_like(input_ids)
-    e = (sd[prefix + ".word_embeddings.weight"][input_ids] + sd[prefix + ".position_embeddings.weight"][position_ids]
+    e = (embedding(sd[prefix + ".word_embeddings.weight"], input_ids, padding_idx) + sd[prefix + ".position_embeddings.weight"][position_ids]
          + sd[prefix + ".token_type_embeddings.weight"][token_type_ids])
     return dropout(layer_norm(e, sd, prefix + ".LayerNorm"), keep, p)
+
+
+def fc7_encoder(image, sd, prefix):
+    """FinetuneFasterRcnnFpnFc7.forward: relu(lc(image)), mmf/modules/encoders.py:176-179."""
+    return torch.relu(linear(image, sd, prefix + ".lc" if prefix else "lc"))
+
+
+def widen_segment_table(old, num_segments, fresh):
+    """TransformerEncoder._init_segment_embeddings, mmf/modules/encoders.py:563-575: rows 0,1 copied, rows
+    2..n-2 = mean of the old table, the last row keeps its fresh nn.Embedding init (`fresh` [n,H])."""
+    new = fresh.clone()
+    new[:2] = old[:2]
+    for idx in range(2, num_segments - 1):
+        new[idx] = old.mean(dim=0)
+    return new
+
+
+def transformer_encoder(input_ids, attention_mask, token_type_ids, sd, prefix, num_layers, heads, return_sequence=False):
+    """TransformerEncoder.forward (mmf/modules/encoders.py:582-585) over BertModelJit.forward
+    (mmf/modules/hf_layers.py:358-475): embeddings -> encoder -> pooler; pooled output unless return_sequence."""
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    emb = bert_embeddings(input_ids, token_type_ids, sd, prefix + ".embeddings")
+    seq = bert_encoder(emb, extended_attention_mask(attention_mask, emb.dtype), sd, prefix + ".encoder", num_layers, heads)
+    return seq if return_sequence else bert_pooler(seq, sd, prefix + ".pooler")
 
 
 def extract_modal_end_token(input_ids, input_mask):
@@ -305,9 +339,9 @@ def modal_embeddings(input_modal, start_token, end_token, token_type_ids, sd, em
     proj_prefix: `proj_embeddings`.  token_type_ids [B,1] broadcasts over the modal sequence."""
     tok = linear(input_modal, sd, proj_prefix)
     if start_token is not None:
-        tok = torch.cat([sd[emb_prefix + ".word_embeddings.weight"][start_token].unsqueeze(1), tok], dim=1)
+        tok = torch.cat([embedding(sd[emb_prefix + ".word_embeddings.weight"], start_token, 0).unsqueeze(1), tok], dim=1)
     if end_token is not None:
-        tok = torch.cat([tok, sd[emb_prefix + ".word_embeddings.weight"][end_token].unsqueeze(1)], dim=1)
+        tok = torch.cat([tok, embedding(sd[emb_prefix + ".word_embeddings.weight"], end_token, 0).unsqueeze(1)], dim=1)
     B, L = tok.shape[:2]
     pos = torch.arange(L, dtype=torch.long, device=tok.device).unsqueeze(0).expand(B, L)
     if token_type_ids is None:
@@ -344,7 +378,7 @@ def hf_multimodal_embeddings(tokens, position_ids, segment_ids, sd, prefix, moda
     for i, m in enumerate(modalities):
         key = m["key"]
         if m["type"] == "text":
-            e = sd["%s.token_embeddings.%d.weight" % (prefix, i)][tokens[key]]
+            e = embedding(sd["%s.token_embeddings.%d.weight" % (prefix, i)], tokens[key], m.get("pad_token_id", 0))
         else:
             e = linear(tokens[key], sd, "%s.token_embeddings.%d.0" % (prefix, i))
             e = layer_norm(e, sd, "%s.token_embeddings.%d.1" % (prefix, i), m.get("layer_norm_eps", LN_EPS))

@@ -226,6 +226,69 @@ def golden_mmft_embeddings():
     })
 
 
+def golden_encoders():
+    """encoders.py row a13: fc7 relu(Linear) and TransformerEncoder (BertModelJit + widened segment table).
+    Both constructors read the network / pickles, so the objects are assembled around the reference's own
+    `forward` / `_init_segment_embeddings` (the code under test) without running `__init__`."""
+    from transformers import BertConfig
+    enc = R.encoders()
+    hl = R.hf_layers()
+    g = torch.Generator().manual_seed(61)
+    # --- FinetuneFasterRcnnFpnFc7.forward (encoders.py:176-179)
+    fc7 = enc.FinetuneFasterRcnnFpnFc7.__new__(enc.FinetuneFasterRcnnFpnFc7)
+    torch.nn.Module.__init__(fc7)
+    fc7.lc = torch.nn.Linear(256, 128)
+    fc7.out_dim = 128
+    _perturb(fc7, 62)
+    feat = torch.randn(3, 10, 256, generator=g, requires_grad=True)
+    y = fc7(feat)
+    wy = torch.randn(y.shape, generator=g)
+    (y * wy).sum().backward()
+    # legacy `module.` prefix handling (encoders.py:151-174)
+    legacy = {"module.lc.weight": fc7.lc.weight.detach().clone(), "module.lc.bias": fc7.lc.bias.detach().clone()}
+    fc7.load_state_dict(dict(legacy))
+    # --- TransformerEncoder: BertModelJit (hf_layers.py:358-475) + _init_segment_embeddings (encoders.py:563-575)
+    cfg = BertConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2,
+                     vocab_size=50, max_position_embeddings=32)
+    te = enc.TransformerEncoder.__new__(enc.TransformerEncoder)
+    torch.nn.Module.__init__(te)
+    te.module = hl.BertModelJit(cfg)
+    _perturb(te.module, 63)
+    pre_types = te.module.embeddings.token_type_embeddings.weight.detach().clone()
+    te.embeddings = te.module.embeddings
+
+    class _Cfg(dict):
+        __getattr__ = dict.__getitem__
+    te.original_config = _Cfg(num_segments=5)
+    te.config = cfg
+    torch.manual_seed(64)
+    te._init_segment_embeddings()
+    te.eval()
+    B, T = 3, 12
+    ids = torch.randint(0, 50, (B, T), generator=g)
+    mask = torch.ones(B, T, dtype=torch.long)
+    mask[1, 7:] = 0
+    seg = torch.randint(0, 5, (B, T), generator=g)
+    pooled = te(ids, mask, seg)
+    seq = te(ids, mask, seg, return_sequence=True)
+    w = torch.randn(seq.shape, generator=g)
+    wp = torch.randn(pooled.shape, generator=g)
+    ((seq * w).sum() + (pooled * wp).sum()).backward()
+    names = [n for n, _ in te.named_parameters()]
+    _save("encoders", {
+        "fc7": {"state_dict": {k: v.detach().clone() for k, v in fc7.state_dict().items()}, "feat": feat.detach(),
+                "out": y.detach(), "w_rand": wy, "dfeat": feat.grad.detach(),
+                "grads": {"lc.weight": fc7.lc.weight.grad.clone(), "lc.bias": fc7.lc.bias.grad.clone()},
+                "legacy_keys": sorted(legacy.keys())},
+        "transformer": {"cfg": {"hidden": 128, "heads": 2, "inter": 256, "layers": 2, "vocab": 50, "max_pos": 32,
+                                "num_segments": 5},
+                        "pre_types": pre_types,
+                        "state_dict": {k: v.detach().clone() for k, v in te.state_dict().items()},
+                        "ids": ids, "mask": mask, "seg": seg, "seq": seq.detach(), "pooled": pooled.detach(),
+                        "w_seq": w, "w_pooled": wp, "grads": _grads(te, names)},
+    })
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -234,6 +297,7 @@ def main():
     golden_embeddings()
     golden_mmbt()
     golden_mmft_embeddings()
+    golden_encoders()
 
 
 if __name__ == "__main__":

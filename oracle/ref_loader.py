@@ -124,3 +124,15 @@ def mmbt():
 def hf_backend():
     hf_layers()
     return load("mmf/models/transformers/backends/huggingface.py", "mmf.models.transformers.backends.huggingface")
+
+
+def encoders():
+    """mmf/modules/encoders.py: needs the pre-4.0 module paths of transformers' Auto classes as aliases."""
+    _install()
+    import transformers.models.auto.configuration_auto as ca
+    import transformers.models.auto.modeling_auto as ma
+    sys.modules.setdefault("transformers.configuration_auto", ca)
+    sys.modules.setdefault("transformers.modeling_auto", ma)
+    hf_layers()
+    embeddings()
+    return load("mmf/modules/encoders.py", "mmf.modules.encoders")

@@ -51,6 +51,15 @@ def _worker(rank, world, port, result):
         assert torch.allclose(runner.pack.grad, expect)
         offs, lens = sent[0::2], sent[1::2]
         assert sum(lens) == runner.pack.total and sorted(offs) == sorted(set(offs))   # every element sent exactly once
+        # the same encoder behind a second autograd node of the same backward pass: its local gradients land on top
+        # of the averaged ones and every region is sent again -> still the mean of the totals
+        local2 = torch.arange(runner.pack.total, dtype=torch.float32).flip(0) * (rank + 1)
+        runner.pack.on_reentry()
+        runner.pack.grad.add_(local2)
+        for i in (2, 1, 0):
+            runner.grad_ready_hook(i)
+        assert torch.allclose(runner.pack.grad, expect + torch.arange(runner.pack.total, dtype=torch.float32).flip(0) * 1.5)
+        runner.pack.grad.copy_(expect)
         # no_sync: nothing is sent
         sent.clear()
         ddp._state.clear()

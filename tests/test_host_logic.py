@@ -58,6 +58,39 @@ def test_param_pack_views_and_grad_handover():
         pack.handle(params[0], params[2])   # not adjacent
 
 
+def test_param_pack_two_nodes_in_one_backward_pass():
+    # the same pack behind two autograd nodes of one graph (an encoder applied twice before a single backward):
+    # the second node must accumulate into the flat buffer instead of zeroing the first node's result
+    from mmf_b200.engine import ParamPack
+    w = torch.nn.Parameter(torch.randn(16, 8))
+    pack = ParamPack([w], "cpu")
+
+    class Scale(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w_):
+            ctx.save_for_backward(x)
+            return x @ w_.detach().t()
+
+        @staticmethod
+        def backward(ctx, dy):
+            (x,) = ctx.saved_tensors
+            aliased = pack.prepare_grads()
+            pack.grad_view(w).add_(dy.t() @ x)            # kernels accumulate into the flat buffer
+            return dy @ w.detach(), pack.autograd_grads(aliased)[0]
+
+    x1, x2 = torch.randn(4, 8), torch.randn(4, 8)
+    (Scale.apply(x1, w).sum() + 3.0 * Scale.apply(x2, w).sum()).backward()
+    expect = torch.ones(4, 16).t() @ x1 + 3.0 * torch.ones(4, 16).t() @ x2
+    assert torch.allclose(w.grad, expect, atol=1e-5)
+    assert w.grad.data_ptr() == pack.grad.data_ptr()        # adopted without a copy
+    # next pass, gradient accumulation (p.grad kept) and then zero_grad(set_to_none)
+    Scale.apply(x1, w).sum().backward()
+    assert torch.allclose(w.grad, expect + torch.ones(4, 16).t() @ x1, atol=1e-5)
+    w.grad = None
+    Scale.apply(x2, w).sum().backward()
+    assert torch.allclose(w.grad, torch.ones(4, 16).t() @ x2, atol=1e-5)
+
+
 def test_vilbert_schedule_matches_oracle():
     from mmf_b200.modules import vilbert_schedule
     from oracle.fusion_oracle import vilbert_schedule as oracle_schedule
@@ -122,6 +155,30 @@ def test_registry_and_sample_list_shims():
     assert torch.equal(moved.image_info_0["max_features"], torch.tensor([1, 2, 3]))
     with pytest.raises(AttributeError):
         sl.missing
+
+
+def test_encoder_plugins_registered_with_reference_names_and_keys():
+    # mmf/modules/encoders.py:116,183,513 register these names; state-dict keys are the reference's
+    import mmf_b200.encoders as enc
+    from mmf_b200.registry import registry
+    assert registry.get_encoder_class("finetune_faster_rcnn_fpn_fc7") is enc.B200FinetuneFasterRcnnFpnFc7
+    assert registry.get_encoder_class("identity") is enc.B200IdentityEncoder
+    assert registry.get_encoder_class("transformer") is enc.B200TransformerEncoder
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "encoders.pt"), weights_only=False)
+    c = g["transformer"]["cfg"]
+    te = enc.B200TransformerEncoder(dict(hidden_size=c["hidden"], num_hidden_layers=c["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                         vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                         num_segments=c["num_segments"]))
+    assert set(te.state_dict().keys()) == set(g["transformer"]["state_dict"].keys())
+    assert te.embeddings is te.module.embeddings
+    fc7 = enc.B200FinetuneFasterRcnnFpnFc7({"in_dim": 256, "out_dim": 128})
+    assert set(fc7.state_dict().keys()) == set(g["fc7"]["state_dict"].keys())
+    ident = enc.B200IdentityEncoder({"in_dim": 64})
+    x = torch.randn(2, 64)
+    assert ident(x) is x and ident.out_dim == 64
+    with pytest.raises(RuntimeError):      # no CPU fallback
+        fc7(torch.randn(2, 256))
 
 
 def test_patch_and_undo_restore_forward():
