@@ -130,3 +130,125 @@ class B200TransformerEncoder(nn.Module):
     def forward(self, *args, return_sequence=False, **kwargs):
         output = self.module(*args, **kwargs)
         return output[0] if return_sequence else output[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# factories / builders (mmf/modules/encoders.py:59-113, mmf/utils/build.py:495-546)
+# ------------------------------------------------------------------------------------------------
+class _Projection(nn.Module):
+    """ImageFeatureEncoderFactory type "projection" with module "linear" (ProjectionEmbedding -> nn.Linear,
+    mmf/modules/embeddings.py ProjectionEmbedding) on the GEMM of the C ABI."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.layers = nn.Linear(in_dim, out_dim)
+        self.out_dim = out_dim
+
+    def forward(self, x):
+        _require_cuda(x, "x")
+        shape = x.shape
+        y = ops.linear(x.reshape(-1, shape[-1]), self.layers.weight, self.layers.bias)
+        return y.view(*shape[:-1], self.out_dim).to(x.dtype)
+
+
+class B200ImageFeatureEncoderFactory(nn.Module):
+    """ImageFeatureEncoderFactory (encoders.py:79-113): {type, params} -> .module, .out_dim"""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__()
+        encoder_type = _get(config, "type")
+        encoder_type = getattr(encoder_type, "value", encoder_type)
+        params = _get(config, "params")
+        if params is None or _get(params, "in_dim") is None:
+            raise AssertionError("ImageFeatureEncoder require 'in_dim' param in config")
+        if encoder_type in ("default", "identity"):
+            self.module = nn.Identity()
+            self.module.in_dim = _get(params, "in_dim")
+            self.module.out_dim = _get(params, "in_dim")
+        elif encoder_type == "projection":
+            if _get(params, "module", "linear") != "linear":
+                raise NotImplementedError("projection module %r is not on the B200 path" % _get(params, "module"))
+            self.module = _Projection(_get(params, "in_dim"), _get(params, "out_dim"))
+        elif encoder_type == "finetune_faster_rcnn_fpn_fc7":
+            self.module = B200FinetuneFasterRcnnFpnFc7(params)
+        else:
+            raise NotImplementedError("Unknown Image Encoder: %s" % encoder_type)
+        self.out_dim = self.module.out_dim
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+class B200TextEncoderFactory(nn.Module):
+    """TextEncoderFactory (encoders.py:454-485): identity / transformer (the `embedding` type wraps MMF's LSTM/attention
+    text embeddings, which are not on the fusion path)."""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__()
+        self._type = getattr(_get(config, "type"), "value", _get(config, "type"))
+        if self._type == "identity":
+            self.module = nn.Identity()
+        elif self._type == "transformer":
+            self._module = B200TransformerEncoder(_get(config, "params"))
+            self.module = self._module.module          # the reference keeps the bare BertModel here (encoders.py:470-472)
+        else:
+            raise NotImplementedError("Unknown Text Encoder %s" % self._type)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+def build_text_encoder(config, *args, **kwargs):
+    return B200TextEncoderFactory(config, *args, **kwargs).module
+
+
+def build_image_encoder(config, direct_features=False, **kwargs):
+    if not direct_features:
+        raise NotImplementedError("raw-image encoders (ResNet / detectron) are upstream of the fusion path: "
+                                  "use direct_features_input")
+    return B200ImageFeatureEncoderFactory(config).module
+
+
+def build_encoder(config):
+    """build_encoder (mmf/utils/build.py:517-546): `{type, params}` or a structured config with `name`."""
+    if _get(config, "type") is not None:
+        name = getattr(_get(config, "type"), "value", _get(config, "type"))
+        params = _get(config, "params", None)
+    else:
+        name, params = _get(config, "name"), config
+    cls = registry.get_encoder_class(name)
+    if cls is None:
+        raise KeyError("no encoder registered under %r" % name)
+    return cls(params if params is not None else {})
+
+
+class B200MultiModalEncoderBase(nn.Module):
+    """MultiModalEncoderBase (encoders.py:588-646): builds `text_encoder` / `modal_encoder` from the config."""
+
+    def __init__(self, config, *args, **kwargs):
+        super().__init__()
+        self.config = config
+        self._modal_encoder_config = _get(config, "modal_encoder", None)
+        self._is_direct_features_input = _get(config, "direct_features_input", False)
+        self.build()
+        self.modal_hidden_size = _get(config, "modal_hidden_size", None)
+        self.text_hidden_size = _get(config, "text_hidden_size", None)
+
+    def build(self):
+        self.text_encoder, self.modal_encoder = self._build_encoders(self.config)
+        self._encoder_config = self.text_encoder.config if self.text_encoder is not None else None
+
+    @property
+    def encoder_config(self):
+        return self._encoder_config
+
+    def _build_encoders(self, config):
+        text_encoder = modal_encoder = None
+        if _get(config, "text_encoder", None):
+            text_encoder = build_text_encoder(_get(config, "text_encoder"))
+        if _get(config, "modal_encoder", None):
+            modal_encoder = self._build_modal_encoder(_get(config, "modal_encoder"))
+        return text_encoder, modal_encoder
+
+    def _build_modal_encoder(self, config):
+        return build_image_encoder(config, direct_features=self._is_direct_features_input)

@@ -55,16 +55,22 @@ class _ModalEmbeddingsHolder(nn.Module):
 
 
 class B200MMBTModel(nn.Module):
-    def __init__(self, config, modal_encoder=None):
+    def __init__(self, config, modal_encoder=None, transformer=None):
+        """`transformer`: an already built text encoder with children embeddings / encoder / pooler (what
+        MMBTModel(config, transformer, encoder) receives, mmbt.py:148-156); built here when None."""
         super().__init__()
         self.config = config
         self.is_decoder = getattr(config, "is_decoder", False)
         if self.is_decoder:
             raise NotImplementedError("decoder (causal) MMBT is not on the B200 path")
         self.num_hidden_layers = config.num_hidden_layers
-        self.transformer = _BertModelHolder(config)
+        fresh = transformer is None
+        self.transformer = _BertModelHolder(config) if fresh else transformer
         self.modal_encoder = _ModalEmbeddingsHolder(config, modal_encoder or nn.Identity(), self.transformer.embeddings)
-        _init_bert_weights(self, float(getattr(config, "initializer_range", 0.02)))
+        std = float(getattr(config, "initializer_range", 0.02))
+        if fresh:
+            _init_bert_weights(self.transformer, std)
+        _init_bert_weights(self.modal_encoder.proj_embeddings, std)     # passed-in encoders keep their weights
 
     def forward(self, input_modal, input_ids, modal_start_tokens=None, modal_end_tokens=None, attention_mask=None,
                 token_type_ids=None, modal_token_type_ids=None, position_ids=None, modal_position_ids=None,
@@ -142,11 +148,30 @@ def extract_modal_end_token(sample_list):
 class B200MMBTBase(nn.Module):
     """MMBTBase.forward (mmbt.py:376-444) for direct feature input."""
 
-    def __init__(self, config, use_modal_start_token=True, use_modal_end_token=True, num_max_segment=2):
+    def __init__(self, config, use_modal_start_token=True, use_modal_end_token=True, num_max_segment=2,
+                 modal_encoder=None, transformer=None):
         super().__init__()
-        self.mmbt = B200MMBTModel(config)
+        self.mmbt = B200MMBTModel(config, modal_encoder=modal_encoder, transformer=transformer)
         self.use_modal_start_token, self.use_modal_end_token = use_modal_start_token, use_modal_end_token
         self.num_max_segment = num_max_segment
+
+    @classmethod
+    def from_config(cls, config):
+        """The reference's construction route (MMBTBase.build, mmbt.py:333-347): `text_encoder` / `modal_encoder`
+        factory configs -> encoders (mmf_b200.encoders) -> MMBTModel(mmbt_config, text_encoder, modal_encoder).
+        Only `direct_features_input: true` is on the fusion path (e.g. configs/models/mmbt/with_features.yaml)."""
+        import types
+        from .encoders import B200MultiModalEncoderBase, _get
+        enc = B200MultiModalEncoderBase(config)
+        if enc.text_encoder is None or not hasattr(enc.text_encoder, "config"):
+            raise ValueError("MMBT needs a transformer text_encoder")
+        mm = types.SimpleNamespace(**vars(enc.encoder_config))
+        mm.modal_hidden_size = _get(config, "modal_hidden_size", 2048)      # MMBTConfig (mmbt.py:338-342)
+        mm.num_labels = _get(config, "num_labels", None)
+        te_params = _get(_get(config, "text_encoder"), "params")
+        return cls(mm, _get(config, "use_modal_start_token", True), _get(config, "use_modal_end_token", True),
+                   _get(te_params, "num_segments", None) or 2, modal_encoder=enc.modal_encoder,
+                   transformer=enc.text_encoder)
 
     def forward(self, sample_list):
         input_modal = sample_list["input_modal"] if "input_modal" in sample_list else sample_list["image_feature_0"]

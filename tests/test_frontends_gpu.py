@@ -45,6 +45,39 @@ def test_mmbt_vs_reference_golden_and_integer_paths():
     assert e1 < 1e-2 and e2 < 1e-2
 
 
+def test_mmbt_with_fc7_modal_encoder_built_from_config():
+    # configs/models/mmbt/with_features.yaml: region features -> fc7 relu(Linear) -> MMBT, built the reference's way
+    from mmf_b200.mmbt import B200MMBTBase
+    torch.manual_seed(3)
+    cfg = dict(direct_features_input=True, modal_hidden_size=128, num_labels=2,
+               text_encoder=dict(type="transformer",
+                                 params=dict(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, vocab_size=50,
+                                             max_position_embeddings=64, num_segments=2, hidden_dropout_prob=0.0,
+                                             attention_probs_dropout_prob=0.0)),
+               modal_encoder=dict(type="finetune_faster_rcnn_fpn_fc7", params=dict(in_dim=64, out_dim=128)))
+    base = B200MMBTBase.from_config(cfg).cuda().eval()
+    B, T, R = 2, 10, 7
+    ids = torch.randint(3, 50, (B, T), device="cuda")
+    mask = torch.ones(B, T, dtype=torch.long, device="cuda")
+    mask[1, 6:] = 0
+    seg = torch.zeros(B, T, dtype=torch.long, device="cuda")
+    feats = torch.randn(B, R, 64, device="cuda")
+    sl = {"input_ids": ids.clone(), "input_mask": mask.clone(), "segment_ids": seg, "image_feature_0": feats}
+    seq, pooled, _ = base(sl)
+    w = torch.randn_like(seq)
+    (seq * w).sum().backward()
+    sd = {k: v.detach().to(torch.bfloat16).float().requires_grad_(True) for k, v in base.mmbt.state_dict().items()}
+    fc7 = O.fc7_encoder(feats.to(torch.bfloat16).float(), sd, "modal_encoder.encoder")
+    oseq, opooled, _ = O.mmbt_forward(fc7, ids, mask, seg, sd, {"num_hidden_layers": 1, "num_attention_heads": 2})
+    (oseq * w).sum().backward()
+    assert rel(seq, oseq) < 1e-2 and rel(pooled, opooled) < 1e-2
+    named = dict(base.mmbt.named_parameters())
+    assert rel(named["modal_encoder.proj_embeddings.weight"].grad, sd["modal_encoder.proj_embeddings.weight"].grad) < 2e-2
+    # the fc7 weight gradient crosses the ReLU kink: a few pre-activations flip side in bf16 (test_encoders_gpu.py)
+    assert rel(named["modal_encoder.encoder.lc.weight"].grad, sd["modal_encoder.encoder.lc.weight"].grad) < 6e-2
+    assert rel(named["modal_encoder.encoder.lc.bias"].grad, sd["modal_encoder.encoder.lc.bias"].grad) < 6e-2
+
+
 def test_mmbt_backward_vs_oracle():
     from mmf_b200.mmbt import B200MMBTBase
     torch.manual_seed(0)

@@ -181,6 +181,43 @@ def test_encoder_plugins_registered_with_reference_names_and_keys():
         fc7(torch.randn(2, 256))
 
 
+def test_encoder_factories_and_mmbt_construction_route():
+    # build_encoder / factories / MultiModalEncoderBase (mmf/utils/build.py:495-546, encoders.py:79-113,454-485,588-646)
+    import mmf_b200.encoders as enc
+    from mmf_b200.mmbt import B200MMBTBase
+    assert isinstance(enc.build_encoder({"type": "identity", "params": {"in_dim": 256}}), enc.B200IdentityEncoder)
+    fc7 = enc.build_encoder({"type": "finetune_faster_rcnn_fpn_fc7", "params": {"in_dim": 64, "out_dim": 32}})
+    assert isinstance(fc7, enc.B200FinetuneFasterRcnnFpnFc7) and fc7.out_dim == 32
+    with pytest.raises(KeyError):
+        enc.build_encoder({"type": "resnet152", "params": {}})
+    f = enc.B200ImageFeatureEncoderFactory({"type": "default", "params": {"in_dim": 2048}})
+    assert isinstance(f.module, torch.nn.Identity) and f.out_dim == 2048
+    assert enc.B200ImageFeatureEncoderFactory({"type": "projection", "params": {"in_dim": 64, "out_dim": 16}}).out_dim == 16
+    with pytest.raises(AssertionError):
+        enc.B200ImageFeatureEncoderFactory({"type": "default", "params": {}})
+    with pytest.raises(NotImplementedError):
+        enc.B200ImageFeatureEncoderFactory({"type": "spatial", "params": {"in_dim": 4}})
+    with pytest.raises(NotImplementedError):
+        enc.build_image_encoder({"type": "resnet152", "params": {}}, direct_features=False)
+    te_params = dict(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, vocab_size=50,
+                     max_position_embeddings=160, num_segments=2)
+    cfg = dict(direct_features_input=True, modal_hidden_size=64, num_labels=2,
+               text_encoder=dict(type="transformer", params=te_params),
+               modal_encoder=dict(type="finetune_faster_rcnn_fpn_fc7", params=dict(in_dim=64, out_dim=64)))
+    base = enc.B200MultiModalEncoderBase(cfg)
+    assert base.encoder_config.hidden_size == 128 and base.modal_hidden_size == 64
+    assert isinstance(base.modal_encoder, enc.B200FinetuneFasterRcnnFpnFc7)
+    m = B200MMBTBase.from_config(cfg)
+    keys = set(m.state_dict().keys())
+    # the reference's key layout: MMBTModel.{transformer, modal_encoder.{encoder, proj_embeddings, shared tables}}
+    for k in ("mmbt.modal_encoder.encoder.lc.weight", "mmbt.modal_encoder.proj_embeddings.weight",
+              "mmbt.transformer.embeddings.word_embeddings.weight", "mmbt.transformer.pooler.dense.weight",
+              "mmbt.transformer.encoder.layer.0.attention.self.query.weight", "mmbt.modal_encoder.word_embeddings.weight"):
+        assert k in keys, k
+    assert m.mmbt.modal_encoder.word_embeddings is m.mmbt.transformer.embeddings.word_embeddings
+    assert m.mmbt.modal_encoder.proj_embeddings.in_features == 64 and m.num_max_segment == 2
+
+
 def test_patch_and_undo_restore_forward():
     from transformers.models.bert.modeling_bert import BertEncoder
     from mmf_b200.patch import replace_with_b200, undo_replace_with_b200
