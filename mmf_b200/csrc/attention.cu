@@ -55,7 +55,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, AttnFwdDev p) {
   constexpr int DC = D / 64;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const int SK = (p.Skv + 63) & ~63;
   const int NB = SK / 64;
   const int r0_bytes = max(NB * 16384, DC * 16384 + DC * SK * 128);
@@ -312,7 +312,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__
   constexpr int PBYTES = 128 * CB * 2;  // P' / dS' [128 x CB] bf16
   constexpr int NCBUF = (CB == 64) ? 2 : 1;   // prefetch the next looped tiles while this iteration computes
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sR = smem;
   uint8_t* sRg = sR + TILE;
   uint8_t* sC = sRg + TILE;
@@ -624,7 +624,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   constexpr int D = 64;
   constexpr int TILE = 16384;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem;                 // [2][128 x 128B]
   uint8_t* sdO = sQ + 2 * TILE;
   uint8_t* sK = sdO + 2 * TILE;

@@ -20,6 +20,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// First 1024-byte aligned address of the dynamic shared-memory window (SW128 tiles need it).  Pure pointer arithmetic
+// on the __shared__ array - an integer round trip would make every later access a generic LD.E/ST.E with 64-bit
+// address arithmetic instead of LDS/STS.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -94,7 +94,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using C = Cfg<BN, MC, EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* stg = smem + STAGES * C::STAGE_BYTES;
   uint8_t* auxs = stg + 2 * STG_BYTES;     // [2 sets][2 buffers] 16 KB aux slices (AUX_TMA only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(auxs + C::AUX_BYTES);

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "csrc", "libmmfb200.so")
+# MMFB_LIB: measure another build of the SAME ABI (A/B runs of kernel changes on one box); never a fallback
+_LIB_PATH = os.environ.get("MMFB_LIB") or os.path.join(_HERE, "csrc", "libmmfb200.so")
 
 MMFB_OK, MMFB_ERR_ARG, MMFB_ERR_CUDA, MMFB_ERR_DEVICE = 0, 1, 2, 3
 
