@@ -161,6 +161,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float4* sMask4 = reinterpret_cast<const float4*>(sMask);
     // pass 1 (row max): TMEM loads are software-pipelined - chunk c+1 is in flight while chunk c is reduced
     auto max_chunk = [&](const uint32_t (&r)[32], int c) {
+#if MMFB_F32X2
+      const uint64_t sc2 = pk2(p.scale2, p.scale2);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 m = sMask4[c * 8 + q4];
+        float a0, a1, a2, a3;
+        upk2(fma2(pk2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])), sc2, pk2(m.x, m.y)), a0, a1);
+        upk2(fma2(pk2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])), sc2, pk2(m.z, m.w)), a2, a3);
+        mx = fmaxf(fmaxf(mx, a0), a1);      // one 3-input FMNMX per pair
+        mx = fmaxf(fmaxf(mx, a2), a3);
+      }
+#else
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const float4 m = sMask4[c * 8 + q4];
@@ -169,6 +181,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 2]), p.scale2, m.z));
         mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 3]), p.scale2, m.w));
       }
+#endif
     };
     {
       uint32_t ra[32], rb[32];
@@ -189,6 +202,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("bar.sync 2, 256;" ::: "memory");
     mx = fmaxf(sRed[row], sRed[128 + row]);
     float sum = 0.0f;
+#if MMFB_F32X2
+    uint64_t sum2 = pk2(0.0f, 0.0f);
+#endif
     const uint32_t* dm = (p.dmask != nullptr && valid)
                              ? p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W
                              : nullptr;
@@ -197,6 +213,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float e[32];
       if (c < nch) {
         const uint32_t bits = dm ? __ldg(dm + c) : 0xFFFFFFFFu;
+#if MMFB_F32X2
+        // the same arithmetic two lanes at a time (FFMA2 / FADD2); the row sum is kept as two interleaved partial sums
+        const uint64_t sc2 = pk2(p.scale2, p.scale2), nmx2 = pk2(-mx, -mx);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 m = sMask4[c * 8 + q4];
+          const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int k = 0; k < 4; k += 2) {
+            const int j = q4 * 4 + k;
+            float a0, a1;
+            upk2(add2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, pk2(mm[k], mm[k + 1])), nmx2), a0, a1);
+            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);      // 0 for padded columns
+            sum2 = add2(sum2, pk2(e0, e1));
+            e[j] = ((bits >> j) & 1u) ? e0 : 0.0f;
+            e[j + 1] = ((bits >> (j + 1)) & 1u) ? e1 : 0.0f;
+          }
+        }
+#else
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 m = sMask4[c * 8 + q4];
@@ -209,6 +244,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             e[j] = ((bits >> j) & 1u) ? ev : 0.0f;
           }
         }
+#endif
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) e[j] = 0.0f;
@@ -236,6 +272,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       exp_chunk(r, c);
     }
+#if MMFB_F32X2
+    {
+      float s0, s1;
+      upk2(sum2, s0, s1);
+      sum = s0 + s1;
+    }
+#endif
     sRed[256 + half * 128 + row] = sum;
     fence_proxy_async();
     tc_fence_before();
@@ -750,6 +793,32 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           const float4* m4 = reinterpret_cast<const float4*>(sMsk + j * 128 + c * 32);
           float pv[32], ds[32];
+#if MMFB_F32X2
+          // two lanes per FMA-pipe slot; dropout enters as the factor kf = keep ? 1/(1-p) : 0, so that
+          // dS' = P (dP kf - delta) is one FFMA2 + one FMUL2 and P' = P kf one FMUL2 per pair
+          const uint64_t sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-l2, -l2), ndl2 = pk2(-dl, -dl);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 m = m4[q4];
+            const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+              const int jx = q4 * 4 + k;
+              float a0, a1;
+              upk2(add2(fma2(pk2(__uint_as_float(rs[jx]), __uint_as_float(rs[jx + 1])), sc2, pk2(mm[k], mm[k + 1])), nl2), a0, a1);
+              const uint64_t pr = pk2(ex2_approx(a0), ex2_approx(a1));
+              const uint64_t dp = pk2(__uint_as_float(rd[jx]), __uint_as_float(rd[jx + 1]));
+              if (DROP) {
+                const uint64_t kf = pk2(((bits >> jx) & 1u) ? p.dscale : 0.0f, ((bits >> (jx + 1)) & 1u) ? p.dscale : 0.0f);
+                upk2(mul2(pr, fma2(dp, kf, ndl2)), ds[jx], ds[jx + 1]);
+                upk2(mul2(pr, kf), pv[jx], pv[jx + 1]);
+              } else {
+                upk2(mul2(pr, add2(dp, ndl2)), ds[jx], ds[jx + 1]);
+                upk2(pr, pv[jx], pv[jx + 1]);
+              }
+            }
+          }
+#else
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 m = m4[q4];
@@ -769,6 +838,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               pv[jx] = pk;
             }
           }
+#endif
           uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
           uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
 #pragma unroll

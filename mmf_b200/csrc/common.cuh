@@ -340,6 +340,69 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = gelu_phi_parts(x, e);
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per FMA-pipe issue slot) ----
+// Lane results are bit-identical to the scalar fmaf / * / + (round-to-nearest, no ftz), so a packed epilogue is a pure
+// issue-slot optimisation.  Built in when MMFB_F32X2=1 (csrc/build.py), see gelu_erf2 / gelu_erf_grad2.
+#ifndef MMFB_F32X2
+#define MMFB_F32X2 0
+#endif
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// Phi(x) and exp(-x^2/2) for the pair (x0, x1): the arithmetic of gelu_phi_parts, two lanes at a time (the negated
+// polynomial coefficients give -(poly) exactly, so -poly*t needs no separate negation)
+__device__ __forceinline__ uint64_t gelu_phi_parts2(float x0, float x1, uint64_t x, uint64_t& e) {
+  const uint64_t den = fma2(pk2(fabsf(x0), fabsf(x1)), pk2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f),
+                            pk2(1.0f, 1.0f));
+  float d0, d1;
+  upk2(den, d0, d1);
+  const uint64_t t = pk2(rcp_approx(d0), rcp_approx(d1));
+  const uint64_t arg = mul2(mul2(x, x), pk2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  float a0, a1;
+  upk2(arg, a0, a1);
+  e = pk2(ex2_approx(a0), ex2_approx(a1));
+  uint64_t np = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));
+  np = fma2(np, t, pk2(-1.421413741f, -1.421413741f));
+  np = fma2(np, t, pk2(0.284496736f, 0.284496736f));
+  np = fma2(np, t, pk2(-0.254829592f, -0.254829592f));
+  const uint64_t erf_abs = fma2(mul2(np, t), e, pk2(1.0f, 1.0f));
+  float r0, r1;
+  upk2(erf_abs, r0, r1);
+  return fma2(pk2(0.5f, 0.5f), pk2(copysignf(r0, x0), copysignf(r1, x1)), pk2(0.5f, 0.5f));
+}
+__device__ __forceinline__ void gelu_erf2(float x0, float x1, float& y0, float& y1) {
+  const uint64_t x = pk2(x0, x1);
+  uint64_t e;
+  upk2(mul2(x, gelu_phi_parts2(x0, x1, x, e)), y0, y1);
+}
+// (v0, v1) *= GELU'(x0), GELU'(x1)
+__device__ __forceinline__ void gelu_erf_grad_mul2(float x0, float x1, float& v0, float& v1) {
+  const uint64_t x = pk2(x0, x1);
+  uint64_t e;
+  const uint64_t cdf = gelu_phi_parts2(x0, x1, x, e);
+  const uint64_t g = fma2(mul2(x, pk2(0.3989422804014327f, 0.3989422804014327f)), e, cdf);
+  upk2(mul2(pk2(v0, v1), g), v0, v1);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -368,11 +368,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   f = unpack_bf16x2(a4[q].y); x[2] = f.x; x[3] = f.y;
                   f = unpack_bf16x2(a4[q].z); x[4] = f.x; x[5] = f.y;
                   f = unpack_bf16x2(a4[q].w); x[6] = f.x; x[7] = f.y;
+#if MMFB_F32X2
+                  if (EPI == EPI_GELU_BWD) {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) gelu_erf_grad_mul2(x[e], x[e + 1], v[q * 8 + e], v[q * 8 + e + 1]);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[q * 8 + e] += x[e];
+                  }
+#else
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     if (EPI == EPI_GELU_BWD) v[q * 8 + e] *= gelu_erf_grad(x[e]);
                     else v[q * 8 + e] += x[e];
                   }
+#endif
                 }
               }
             }
@@ -380,7 +390,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 16; ++j) pk[h * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) hk[h * 16 + j] = pack_bf16x2(gelu_erf(v[2 * j]), gelu_erf(v[2 * j + 1]));
+              for (int j = 0; j < 16; ++j) {
+#if MMFB_F32X2
+                float g0, g1;
+                gelu_erf2(v[2 * j], v[2 * j + 1], g0, g1);
+                hk[h * 16 + j] = pack_bf16x2(g0, g1);
+#else
+                hk[h * 16 + j] = pack_bf16x2(gelu_erf(v[2 * j]), gelu_erf(v[2 * j + 1]));
+#endif
+              }
             }
           }
           // 2) stage + TMA store (C, then C2 for the GELU epilogue through the same buffer)
