@@ -187,6 +187,127 @@ ln_bwd_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict_
   }
 }
 
+// Single-pass LayerNorm backward, lean variant (staged: selected with MMFB_LN_BWD=lean, not the default until it is
+// measured).  Same results as ln_bwd_kernel, built for two 256-thread blocks per SM: the row is held as the PACKED
+// bf16 words that were loaded (d, y: 8 registers per 256-column slab instead of 16 floats) and unpacked again in the
+// second phase; gamma is re-read from L1 per row.  Only the three column-sum sets stay in registers across rows, so
+// the row tensors are read from HBM once (the rows + cols pair reads d and y twice and dz once more).
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
+ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
+                   const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
+                   bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  __shared__ float red[ROW_WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[NV][8], ab[NV][8], az[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ag[i][e] = 0.0f; ab[i][e] = 0.0f; az[i][e] = 0.0f; }
+
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + warp; row < M;
+       row += static_cast<int64_t>(gridDim.x) * ROW_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    uint4 dw[NV], yw[NV];      // packed bf16 rows of dx and y, kept across the two phases
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        dw[i] = *reinterpret_cast<const uint4*>(dx + row * lddx + col);
+        yw[i] = *reinterpret_cast<const uint4*>(y + row * ldy + col);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        float d[8], yy[8], g[8];
+        unpack8(dw[i], d);
+        if (dx2 != nullptr) {
+          // d = dx + dx2 is formed in fp32; re-packing the sum to bf16 would change the result, so the second
+          // stream is not kept but re-read in phase 2 (an L1 hit)
+          float t[8];
+          ld8(dx2 + row * lddx2 + col, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] += t[e];
+        }
+        unpack8(yw[i], yy);
+        ld8(gamma + col, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (yy[e] - mu) * rs;
+          const float dg = d[e] * g[e];
+          s1 += dg;
+          s2 += dg * xh;
+          ag[i][e] += d[e] * xh;
+          ab[i][e] += d[e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        float d[8], yy[8], g[8], o[8];
+        unpack8(dw[i], d);
+        if (dx2 != nullptr) {
+          float t[8];
+          ld8(dx2 + row * lddx2 + col, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] += t[e];
+        }
+        unpack8(yw[i], yy);
+        ld8(gamma + col, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (d[e] * g[e] - s1 - ((yy[e] - mu) * rs) * s2);
+        if (dy != nullptr) st8(dy + row * lddy + col, o);
+        if (dmask != nullptr) {
+          const uint32_t w = __ldg(dmask + row * ldmask + (col >> 5));
+          const uint32_t bits = (w >> (col & 31)) & 0xFFu;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = ((bits >> e) & 1u) ? o[e] * dscale : 0.0f;
+          st8(dz + row * lddz + col, o);
+        } else if (dz != nullptr && dz != dy) {
+          st8(dz + row * lddz + col, o);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) az[i][e] += o[e];
+      }
+    }
+  }
+  // block reduction of the three column-sum sets, 256 columns at a time, then one atomic per column
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 256 >= H) break;
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = which == 0 ? ag[i][e] : (which == 1 ? ab[i][e] : az[i][e]);
+      __syncthreads();
+      const int c = threadIdx.x;  // 256 threads <-> 256 columns
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < ROW_WARPS; ++w) t += red[w][c];
+      if (i * 256 + c < H) atomicAdd(dst + i * 256 + c, t);
+    }
+  }
+}
+
 // Row-only LayerNorm backward (no column statistics): few registers, high occupancy.  dy, dz as above.
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
@@ -546,6 +667,20 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   if (!a.dx || !a.y || !a.mean || !a.rstd || !a.gamma) return set_error(MMFB_ERR_ARG, "layernorm_bwd: null pointer");
   if (a.drop_mask && !a.dz) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dropout mask given without dz");
   const int nv_ = (a.H + 255) / 256;
+  static const bool lean = [] { const char* e = getenv("MMFB_LN_BWD"); return e != nullptr && e[0] == 'l'; }();
+  if (lean && nv_ <= 4) {
+    int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
+    const int cap = num_sms() * 2;      // two resident blocks per SM, rows strided over them
+    if (grid > cap) grid = cap;
+#define LN_LEAN(NV)                                                                                                  \
+  ln_bwd_lean_kernel<NV><<<grid, ROW_WARPS * 32, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
+                                                         (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
+                                                         (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask,         \
+                                                         a.ldmask, a.drop_scale, a.dgamma, a.dbeta, a.dbias, a.M, a.H)
+    if (nv_ <= 1) LN_LEAN(1); else if (nv_ == 2) LN_LEAN(2); else if (nv_ == 3) LN_LEAN(3); else LN_LEAN(4);
+#undef LN_LEAN
+    return launch_ok("layernorm_bwd(lean)");
+  }
   if (nv_ <= 4) {
     // two kernels: a light row kernel (dy, dz) at high occupancy, then coalesced column statistics.  (Measured
     // alternatives: one fused kernel with register accumulators - 188 registers, one block per SM, 51 us; one fused

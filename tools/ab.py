@@ -2,6 +2,8 @@
 
 Here (no GPU):    python tools/ab.py build x2 -DMMFB_F32X2=1        -> mmf_b200/csrc/libmmfb200_x2.so (travels with gpurun)
 On the GPU box:   python tools/ab.py run x2 [--tests] [--steps 12]   (one gpurun call)
+                  python tools/ab.py run lnlean --env MMFB_LN_BWD=lean [--tests]     (run-time switch, product library;
+                  --env may be repeated and combined with a variant library of that name if one was built)
     1. (--tests) the whole `-m gpu` suite with MMFB_LIB pointing at the variant: parity first
     2. bench.py with the product library, then with the variant, back to back on the same box / clocks
     3. one line per arm + the ratio; the two bench JSON lines are kept in gpurun_out/ab_<name>_{base,variant}.json
@@ -43,11 +45,18 @@ def main():
         print(build(variant=name, defines=[a for a in sys.argv[3:] if a.startswith("-D")]))
         return
     variant = lib_path(name)
-    if not os.path.exists(variant):
+    extra = {}
+    for i, a in enumerate(sys.argv):
+        if a == "--env":
+            k, v = sys.argv[i + 1].split("=", 1)
+            extra[k] = v
+    if not os.path.exists(variant) and not extra:
         raise SystemExit("%s is missing: run `python tools/ab.py build %s -D...` before gpurun" % (variant, name))
     steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 12
-    env_v = dict(os.environ, MMFB_LIB=variant)
-    env_b = {k: v for k, v in os.environ.items() if k != "MMFB_LIB"}
+    env_v = dict(os.environ, **extra)
+    if os.path.exists(variant):
+        env_v["MMFB_LIB"] = variant
+    env_b = {k: v for k, v in os.environ.items() if k != "MMFB_LIB" and k not in extra}
     if "--tests" in sys.argv:
         r = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q", "-x"], env=env_v, cwd=ROOT)
         if r.returncode != 0:
