@@ -12,6 +12,8 @@ their own forward is never called.
 The same runners can be attached to an EXISTING HuggingFace / MMF module tree (mmf_b200.patch), which is how
 VisualBERT / MMBT / MMFTransformer pick the engine up without any registry indirection.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -30,10 +32,22 @@ def _require_cuda(t, what):
 _SEED_COUNTER = [0]
 
 
-def _fresh_dropout_state():
-    """One Philox stream per forward, derived from torch's seed so `torch.manual_seed` makes runs repeatable."""
+_ASYNC_DROPOUT = os.environ.get("MMFB_DROPOUT_ASYNC", "0") not in ("", "0")
+_RNG_STREAMS = {}
+
+
+def _fresh_dropout_state(prefetchable=False):
+    """One Philox stream per forward, derived from torch's seed so `torch.manual_seed` makes runs repeatable.
+    `prefetchable`: the caller announces its sites one layer ahead (EncoderRunner); with MMFB_DROPOUT_ASYNC=1 it then gets
+    the side-stream generator (staged, see engine.AsyncDropoutState)."""
     _SEED_COUNTER[0] += 1
-    return E.DropoutState(torch.initial_seed() * 1000003 + _SEED_COUNTER[0])
+    seed = torch.initial_seed() * 1000003 + _SEED_COUNTER[0]
+    if prefetchable and _ASYNC_DROPOUT and torch.cuda.is_available():
+        dev = torch.cuda.current_device()
+        if dev not in _RNG_STREAMS:
+            _RNG_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        return E.AsyncDropoutState(seed, _RNG_STREAMS[dev])
+    return E.DropoutState(seed)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -75,13 +89,22 @@ class EncoderRunner:
         B, S, H = x.shape
         h = x.reshape(B * S, H)
         saved = []
-        ds = _fresh_dropout_state() if training else None
+        ds = _fresh_dropout_state(prefetchable=True) if training else None
         last_layer = len(self.layers) if last_layer is None else last_layer
         hiddens = []
+        ahead = isinstance(ds, E.AsyncDropoutState)
+
+        def sites(i):      # the three dropout sites of layer i, in the order bert_layer_fwd draws them
+            pa_, ph_ = self._probs(self.layers[i])
+            return [((B, self.weights[i].heads, S), S, pa_), ((B * S,), H, ph_), ((B * S,), H, ph_)]
+        if ahead and first_layer < last_layer:
+            ds.prefetch(sites(first_layer), x.device)
         for i in range(first_layer, last_layer):
             m = self.layers[i]
             pa, ph = self._probs(m) if training else (0.0, 0.0)
             hiddens.append(h)
+            if ahead and i + 1 < last_layer:
+                ds.prefetch(sites(i + 1), x.device)      # generated while layer i runs
             h, s = E.bert_layer_fwd(h, add_mask, self.weights[i], B, S, pa, ph, ds)
             saved.append(s if need_grad else None)
         return h, saved, hiddens
