@@ -116,6 +116,7 @@ class EncoderRunner:
             d = E.bert_layer_bwd(d, saved[j], add_mask, self.weights[i], B, S)
             saved[j] = None
             if self.grad_ready_hook is not None:
+                E.join_side(d.device)
                 self.grad_ready_hook(i)
         return d
 
@@ -379,6 +380,7 @@ class VilbertRunner:
                 dimg, dtxt = E.connection_bwd(dimg, dtxt, saved[j], imask, tmask, w, B, R, T)
             saved[j] = None
             if self.grad_ready_hook is not None:
+                E.join_side()
                 self.grad_ready_hook(j)
         return dtxt, dimg
 
