@@ -1,0 +1,254 @@
+"""Host orchestration of the fusion block on the CPU: mmf_b200.engine run over tests/fake_kernels.py (a torch restatement
+of every kernel's CONTRACT) must reproduce the oracle - forward, input gradient and every parameter gradient in the flat
+buffer - for a BERT layer stack and a ViLBERT connection layer, with and without dropout (same explicit masks on both
+sides).  This pins which operand goes to which kernel, what is saved, and where gradients accumulate; the kernels
+themselves are checked on the B200 (`-m gpu`)."""
+import types
+
+import pytest
+import torch
+
+from mmf_b200 import engine as E
+from oracle import fusion_oracle as O
+
+import fake_kernels as FK
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    monkeypatch.setattr(E, "F", FK)
+    yield FK
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-3 * b.numel() ** 0.5)).item()
+
+
+def _bf16_round_(module):
+    with torch.no_grad():
+        for p in module.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+
+
+def _cfg(p):
+    return types.SimpleNamespace(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_hidden_layers=2,
+                                 hidden_dropout_prob=p, attention_probs_dropout_prob=p, layer_norm_eps=1e-12)
+
+
+class _RecordingDropout(E.DropoutState):
+    """hands out the keep bits and remembers them in draw order, so that the oracle can be given the same masks"""
+
+    def __init__(self):
+        super().__init__(7)
+        self.drawn = []
+
+    def bits(self, rows_shape, ncols, p, device):
+        w = super().bits(rows_shape, ncols, p, device)
+        self.drawn.append((w, ncols))
+        return w
+
+
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_bert_layer_stack_wiring_matches_oracle(fake, p):
+    from mmf_b200.modules import B200BertEncoder
+    torch.manual_seed(0)
+    enc = B200BertEncoder(_cfg(p))
+    with torch.no_grad():
+        for prm in enc.parameters():
+            if prm.dim() == 1:
+                prm.add_(torch.randn_like(prm) * 0.05)
+    _bf16_round_(enc)
+    params = []
+    for m in enc.layer:
+        params += E.BertLayerW.params(m)
+    pack = E.ParamPack(params, "cpu")
+    pack.refresh()
+    weights = [E.BertLayerW(pack, m) for m in enc.layer]
+    B, S, H = 3, 10, 64
+    x = torch.randn(B, S, H).to(torch.bfloat16)
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[1, 6:] = 0
+    add2d = ((1.0 - mask.float()) * -10000.0).contiguous()
+    ds = _RecordingDropout() if p > 0 else None
+    h = x.reshape(B * S, H)
+    saved = []
+    for w in weights:
+        h, s = E.bert_layer_fwd(h, add2d, w, B, S, p, p, ds)
+        saved.append(s)
+    w_rand = torch.randn(B * S, H)
+    pack.prepare_grads()
+    d = w_rand.to(torch.bfloat16)
+    for w, s in zip(reversed(weights), reversed(saved)):
+        d = E.bert_layer_bwd(d, s, add2d, w, B, S)
+    # ---- oracle on the same (bf16-rounded) weights, inputs and masks ----
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    xo = x.float().clone().requires_grad_(True)
+    masks = None
+    if p > 0:
+        it = iter(ds.drawn)
+        masks = []
+        for _ in weights:      # draw order of bert_layer_fwd: attention probs, attention output, FFN output
+            a, n = next(it)
+            so, n1 = next(it)
+            fo, n2 = next(it)
+            masks.append({"attn": FK.unpack_keep_bits(a, n), "self_out": FK.unpack_keep_bits(so, n1).view(B, S, n1),
+                          "out": FK.unpack_keep_bits(fo, n2).view(B, S, n2)})
+    out = O.bert_encoder(xo, O.extended_attention_mask(mask), sd, "", 2, 2, masks, p, p)
+    (out.reshape(B * S, H) * w_rand.to(torch.bfloat16).float()).sum().backward()
+    assert rel(h.float(), out.reshape(B * S, H)) < 2e-2
+    assert rel(d.float(), xo.grad.reshape(B * S, H)) < 3e-2
+    named = dict(enc.named_parameters())
+    for k, v in sd.items():
+        if ".key.bias" in k:
+            continue            # analytically zero
+        assert rel(pack.grad_view(named[k]), v.grad) < 3e-2, k
+
+
+def test_vilbert_connection_layer_wiring_matches_oracle(fake):
+    from mmf_b200.modules import B200ViLBertEncoder
+    torch.manual_seed(1)
+    c = dict(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_hidden_layers=1,
+             v_hidden_size=128, v_num_attention_heads=2, v_intermediate_size=128, v_num_hidden_layers=1,
+             bi_hidden_size=128, bi_num_attention_heads=2, v_biattention_id=[0], t_biattention_id=[0])
+    cfg = types.SimpleNamespace(hidden_dropout_prob=0.0, v_hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                v_attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12, **c)
+    enc = B200ViLBertEncoder(cfg)
+    _bf16_round_(enc)
+    m = enc.c_layer[0]
+    used = E.ConnectionW.params(m)
+    pack = E.ParamPack(used, "cpu")
+    pack.refresh()
+    w = E.ConnectionW(pack, m)
+    B, R, T = 2, 5, 7
+    img = torch.randn(B * R, 128).to(torch.bfloat16)
+    txt = torch.randn(B * T, 64).to(torch.bfloat16)
+    imask = torch.ones(B, R, dtype=torch.long)
+    tmask = torch.ones(B, T, dtype=torch.long)
+    tmask[0, 4:] = 0
+    iadd = ((1.0 - imask.float()) * -10000.0).contiguous()
+    tadd = ((1.0 - tmask.float()) * -10000.0).contiguous()
+    o1, o2, saved = E.connection_fwd(img, txt, iadd, tadd, w, B, R, T, 0.0, 0.0, 0.0, 0.0, None)
+    wv, wt = torch.randn(B * R, 128), torch.randn(B * T, 64)
+    pack.prepare_grads()
+    dimg, dtxt = E.connection_bwd(wv.to(torch.bfloat16), wt.to(torch.bfloat16), saved, iadd, tadd, w, B, R, T)
+    sd = {"c." + k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    io = img.float().view(B, R, 128).clone().requires_grad_(True)
+    to = txt.float().view(B, T, 64).clone().requires_grad_(True)
+    ov, ot = O.connection_layer(io, O.extended_attention_mask(imask), to, O.extended_attention_mask(tmask), sd, "c", 2)
+    ((ov.reshape(B * R, 128) * wv.to(torch.bfloat16).float()).sum() + (ot.reshape(B * T, 64) * wt.to(torch.bfloat16).float()).sum()).backward()
+    assert rel(o1.float(), ov.reshape(B * R, 128)) < 2e-2 and rel(o2.float(), ot.reshape(B * T, 64)) < 2e-2
+    assert rel(dimg.float(), io.grad.reshape(B * R, 128)) < 3e-2 and rel(dtxt.float(), to.grad.reshape(B * T, 64)) < 3e-2
+    named = dict(m.named_parameters())
+    for k, prm in named.items():
+        g = sd["c." + k].grad
+        if g is None:
+            continue            # biOutput.q_dense1/2: unused in the reference too
+        if "key" in k and k.endswith("bias"):
+            continue
+        assert rel(pack.grad_view(prm), g) < 3e-2, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the drop-in modules end to end (autograd Function, parameter pack hand-over, ViLBERT schedule) over the test double,
+# against the reference's own outputs (tests/golden)
+# ---------------------------------------------------------------------------------------------------------------
+import os
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture()
+def cpu_modules(fake, monkeypatch):
+    import mmf_b200.modules as M
+    monkeypatch.setattr(M, "_require_cuda", lambda t, what: None)
+    yield M
+
+
+def _golden_bound(e, tol=4e-2):
+    # bf16 weights / activations against the reference's fp32 run on a 10-token fixture (see test_encoder_gpu.py)
+    return e < tol
+
+
+def test_bert_encoder_module_vs_reference_golden_cpu(cpu_modules):
+    g = torch.load(os.path.join(GOLD, "bert_encoder.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12)
+    enc = cpu_modules.B200BertEncoder(cfg)
+    enc.load_state_dict(g["state_dict"])
+    enc.eval()
+    x = g["x"].clone().requires_grad_(True)
+    add = O.extended_attention_mask(g["mask"])
+    out = enc(x, add)[0]
+    assert out.dtype == x.dtype and torch.isfinite(out).all()
+    assert _golden_bound(rel(out, g["out"]), 2e-2)
+    (out * g["w_rand"]).sum().backward()
+    assert _golden_bound(rel(x.grad, g["dx"]))
+    named = dict(enc.named_parameters())
+    for k, gv in g["grads"].items():
+        if ".key.bias" in k:
+            continue
+        assert _golden_bound(rel(named[k].grad, gv)), k
+    # gradients live in (and alias) the flat buffer
+    p0 = named["layer.0.attention.self.query.weight"]
+    assert p0.grad.data_ptr() == enc._runner.pack.grad_view(p0).data_ptr()
+
+
+def test_bert_encoder_applied_twice_in_one_graph_cpu(cpu_modules):
+    cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=1,
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12)
+    torch.manual_seed(3)
+    enc = cpu_modules.B200BertEncoder(cfg).eval()
+    x1, x2 = torch.randn(2, 6, 64), torch.randn(2, 6, 64)
+    w1, w2 = torch.randn(2, 6, 64), torch.randn(2, 6, 64)
+
+    def grads(fn):
+        enc.zero_grad(set_to_none=True)
+        fn().backward()
+        return {k: p.grad.detach().clone() for k, p in enc.named_parameters()}
+    both = grads(lambda: (enc(x1, None)[0] * w1).sum() + (enc(x2, None)[0] * w2).sum())
+    a = grads(lambda: (enc(x1, None)[0] * w1).sum())
+    b = grads(lambda: (enc(x2, None)[0] * w2).sum())
+    for k in both:
+        assert rel(both[k], a[k] + b[k]) < 2e-2, k
+
+
+def test_vilbert_encoder_module_vs_reference_golden_cpu(cpu_modules):
+    g = torch.load(os.path.join(GOLD, "vilbert_encoder.pt"), weights_only=False)
+    cfg = types.SimpleNamespace(hidden_dropout_prob=0.0, v_hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                v_attention_probs_dropout_prob=0.0, **dict(g["cfg"]))
+    enc = cpu_modules.B200ViLBertEncoder(cfg)
+    enc.load_state_dict(g["state_dict"])
+    enc.eval()
+    txt = g["txt"].clone().requires_grad_(True)
+    img = g["img"].clone().requires_grad_(True)
+    tadd, iadd = O.extended_attention_mask(g["tmask"]), O.extended_attention_mask(g["imask"])
+    tl, vl, _ = enc(txt, img, tadd, tadd, iadd, None, output_all_encoded_layers=False)
+    assert _golden_bound(rel(tl[-1], g["t_out"]), 2e-2) and _golden_bound(rel(vl[-1], g["v_out"]), 2e-2)
+    ((tl[-1] * g["wt"]).sum() + (vl[-1] * g["wv"]).sum()).backward()
+    assert _golden_bound(rel(txt.grad, g["dtxt"])) and _golden_bound(rel(img.grad, g["dimg"]))
+    for n, p in enc.named_parameters():
+        if n in g["unused"]:
+            assert p.grad is None, n
+        elif "key" in n and n.endswith("bias"):
+            continue
+        else:
+            assert _golden_bound(rel(p.grad, g["grads"][n]), 8e-2), n
+
+
+def test_train_mode_dropout_is_repeatable_under_manual_seed_cpu(cpu_modules):
+    cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2,
+                                hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12)
+    torch.manual_seed(5)
+    enc = cpu_modules.B200BertEncoder(cfg).train()
+    x = torch.randn(2, 8, 64)
+
+    def run():
+        torch.manual_seed(11)
+        cpu_modules._SEED_COUNTER[0] = 0
+        return enc(x, None)[0].detach().clone()
+    a, b = run(), run()
+    assert torch.equal(a, b)
+    enc.eval()
+    assert not torch.equal(enc(x, None)[0], a)      # dropout was really applied in train mode
