@@ -167,3 +167,42 @@ def dropout_bits(shape_rows, ncols, p, seed, offset, device):
 
 def cast_f32_bf16(src, dst):
     dst.copy_(src.to(BF))
+
+
+def embed_compose(M, H, srcs=(), tabs=(), device=None):
+    y = torch.zeros(M, H)
+    for t, rows in srcs:
+        r = rows.long()
+        ok = r >= 0
+        y[ok] += t.float()[r[ok]]
+    for t, idx in tabs:
+        i = idx.long()
+        ok = i >= 0
+        y[ok] += t.float()[i[ok]]
+    return y.to(BF)
+
+
+def embed_scatter(dy, dsrcs=(), dtabs=()):
+    for t, rows in dsrcs:
+        r = rows.long()
+        ok = r >= 0
+        t[r[ok]] = dy[ok]
+    for t, idx in dtabs:
+        i = idx.long()
+        ok = i >= 0
+        t.index_add_(0, i[ok], dy.float()[ok])
+
+
+def sort_indices(idx):
+    s, o = torch.sort(idx.to(torch.int64), stable=True)
+    return s.to(torch.int32).contiguous(), o.to(torch.int32).contiguous()
+
+
+def embed_scatter_sorted(dy, dtab, sorted_idx, order):
+    i = sorted_idx.long()
+    ok = i >= 0
+    dtab.index_add_(0, i[ok], dy.float()[order.long()[ok]])
+
+
+def relu_bwd(dy, y):
+    return torch.where(y > 0, dy, torch.zeros_like(dy))

@@ -252,3 +252,147 @@ def test_train_mode_dropout_is_repeatable_under_manual_seed_cpu(cpu_modules):
     assert torch.equal(a, b)
     enc.eval()
     assert not torch.equal(enc(x, None)[0], a)      # dropout was really applied in train mode
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# front-ends (embedding composers, MMBT token surgery, MMFT backend embeddings, encoder plugins) over the test double
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def cpu_frontends(cpu_modules, monkeypatch):
+    import mmf_b200.embeddings as EM
+    import mmf_b200.encoders as EN
+    import mmf_b200.mmbt as MB
+    import mmf_b200.mmft_backend as MF
+    import mmf_b200.ops as OPS
+    import mmf_b200.vilbert as VB
+    monkeypatch.setattr(OPS, "F", FK)
+    monkeypatch.setattr(EM, "F", FK)
+    for mod in (EM, EN, MB, MF, VB):
+        if hasattr(mod, "_require_cuda"):
+            monkeypatch.setattr(mod, "_require_cuda", lambda t, what: None)
+    yield types.SimpleNamespace(EM=EM, EN=EN, MB=MB, MF=MF, VB=VB)
+
+
+def test_visio_linguistic_embeddings_vs_reference_golden_cpu(cpu_frontends):
+    g = torch.load(os.path.join(GOLD, "embeddings.pt"), weights_only=False)
+    sd = g["vl_state_dict"]
+    cfg = types.SimpleNamespace(hidden_size=sd["word_embeddings.weight"].shape[1],
+                                vocab_size=sd["word_embeddings.weight"].shape[0],
+                                max_position_embeddings=sd["position_embeddings.weight"].shape[0],
+                                type_vocab_size=sd["token_type_embeddings.weight"].shape[0], hidden_dropout_prob=0.0,
+                                visual_embedding_dim=sd["projection.weight"].shape[1], layer_norm_eps=1e-12)
+    emb = cpu_frontends.EM.B200VisioLinguisticEmbeddings(cfg)
+    emb.load_state_dict({k: v for k, v in sd.items() if k in emb.state_dict()}, strict=False)
+    emb.eval()
+    out = emb(g["ids"], g["seg"], g["feats"], g["vtype"])
+    assert rel(out, g["out_plain"]) < 2e-2
+    out = emb(g["ids"], g["seg"], g["feats"], g["vtype"], g["alignment"])
+    assert rel(out, g["out_alignment"]) < 2e-2
+    out = emb(g["ids"], g["seg"])
+    assert rel(out, g["out_text"]) < 2e-2
+    # [PAD] row of the word table: read in the forward, no gradient (nn.Embedding(padding_idx=0))
+    ids = g["ids"].clone()
+    ids[:, -2:] = 0
+    emb.zero_grad(set_to_none=True)
+    emb(ids, g["seg"], g["feats"], g["vtype"]).float().square().sum().backward()
+    gw = emb.word_embeddings.weight.grad
+    assert torch.count_nonzero(gw[0]) == 0 and torch.count_nonzero(gw) > 0
+
+
+def test_mmbt_vs_reference_golden_cpu(cpu_frontends):
+    g = torch.load(os.path.join(GOLD, "mmbt.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                                layer_norm_eps=1e-12, hidden_act="gelu", initializer_range=0.02, vocab_size=50,
+                                max_position_embeddings=64, type_vocab_size=2, modal_hidden_size=c["modal_hidden"])
+    base = cpu_frontends.MB.B200MMBTBase(cfg)
+    base.mmbt.load_state_dict(g["state_dict"], strict=False)
+    base.eval()
+    sl = {"input_ids": g["ids"].clone(), "input_mask": g["mask"].clone(), "segment_ids": g["seg"],
+          "image_feature_0": g["feats"]}
+    seq, pooled, _ = base(sl)
+    assert torch.equal(sl["input_ids"], g["shifted_ids"]) and torch.equal(sl["input_mask"], g["shifted_mask"])
+    assert rel(seq, g["seq_out"]) < 2e-2 and rel(pooled, g["pooled"]) < 2e-2
+
+
+def test_encoder_plugins_vs_reference_golden_cpu(cpu_frontends):
+    g = torch.load(os.path.join(GOLD, "encoders.pt"), weights_only=False)
+    f = g["fc7"]
+    fc7 = cpu_frontends.EN.B200FinetuneFasterRcnnFpnFc7({"in_dim": 256, "out_dim": 128})
+    fc7.load_state_dict(f["state_dict"])
+    x = f["feat"].clone().requires_grad_(True)
+    y = fc7(x)
+    assert rel(y, f["out"]) < 1e-2
+    (y * f["w_rand"]).sum().backward()
+    assert rel(x.grad, f["dfeat"]) < 6e-2 and rel(fc7.lc.weight.grad, f["grads"]["lc.weight"]) < 6e-2
+    t = g["transformer"]
+    c = t["cfg"]
+    te = cpu_frontends.EN.B200TransformerEncoder(dict(
+        hidden_size=c["hidden"], num_hidden_layers=c["layers"], num_attention_heads=c["heads"],
+        intermediate_size=c["inter"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+        num_segments=c["num_segments"]))
+    te.load_state_dict(t["state_dict"])
+    te.eval()
+    pooled = te(t["ids"], t["mask"], t["seg"])
+    seq = te(t["ids"], t["mask"], t["seg"], return_sequence=True)
+    assert rel(seq, t["seq"]) < 2e-2 and rel(pooled, t["pooled"]) < 2e-2
+    ((seq * t["w_seq"]).sum() + (pooled * t["w_pooled"]).sum()).backward()       # two nodes on one pack, one pass
+    named = dict(te.named_parameters())
+    for k in ("module.embeddings.word_embeddings.weight", "module.embeddings.token_type_embeddings.weight",
+              "module.encoder.layer.0.intermediate.dense.weight", "module.encoder.layer.1.output.dense.weight",
+              "module.pooler.dense.weight"):
+        assert rel(named[k].grad, t["grads"][k]) < 6e-2, k
+    assert torch.count_nonzero(named["module.embeddings.word_embeddings.weight"].grad[0]) == 0
+
+
+def test_mmft_backend_and_vilbert_image_embeddings_vs_reference_golden_cpu(cpu_frontends):
+    from mmf_b200.registry import registry
+    g = torch.load(os.path.join(GOLD, "mmft_embeddings.pt"), weights_only=False)
+    tcfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=1,
+                                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12,
+                                 hidden_act="gelu", initializer_range=0.02, vocab_size=50, max_position_embeddings=32,
+                                 type_vocab_size=2, pad_token_id=0)
+    mods = [dict(type="text", key="text", position_dim=32, embedding_dim=64, segment_id=0),
+            dict(type="image", key="image", position_dim=16, embedding_dim=40, segment_id=1)]
+    backend = registry.get_transformer_backend_class("b200")(
+        dict(modalities=mods, transformer_config=tcfg, token_noise_mean=0.0, token_noise_std=0.01))
+    backend.embeddings.load_state_dict(g["state_dict"])
+    backend.eval()
+    emb = backend.generate_embeddings(g["tokens"], g["pos"], g["seg"], None)
+    assert rel(emb, g["out"]) < 2e-2
+    assert torch.equal(backend.generate_attention_mask(list(g["masks"])), g["attention_mask"])
+    seq, first = backend(g["tokens"], g["pos"], g["seg"], list(g["masks"]))
+    assert seq.shape == (2, 11, 64) and torch.isfinite(seq.float()).all()
+    ge = torch.load(os.path.join(GOLD, "embeddings.pt"), weights_only=False)
+    mod = cpu_frontends.VB.B200ImageFeatureEmbeddings(
+        types.SimpleNamespace(v_feature_size=40, v_hidden_size=96, hidden_dropout_prob=0.1))
+    mod.load_state_dict(ge["img_state_dict"])
+    mod.eval()
+    assert rel(mod(ge["feats"], ge["loc"]), ge["img_out"]) < 2e-2
+
+
+def test_monkey_patch_swap_on_hf_bert_encoder_cpu(cpu_modules):
+    """replace_with_b200() (the reference's replace_with_jit() boundary): a stock HuggingFace BertEncoder runs on the
+    engine, keeps its parameter names, and the original forward is restored by undo."""
+    from transformers import BertConfig
+    from transformers.models.bert.modeling_bert import BertEncoder
+    from mmf_b200.patch import replace_with_b200, undo_replace_with_b200
+    torch.manual_seed(0)
+    cfg = BertConfig(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2, vocab_size=50,
+                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    enc = BertEncoder(cfg).eval()
+    keys = set(enc.state_dict().keys())
+    x = torch.randn(2, 9, 64)
+    mask = torch.ones(2, 9, dtype=torch.long)
+    mask[0, 6:] = 0
+    add = O.extended_attention_mask(mask)
+    orig_forward = BertEncoder.forward
+    replace_with_b200()
+    try:
+        out = enc(x, add)[0]
+    finally:
+        undo_replace_with_b200()
+    assert BertEncoder.forward is orig_forward and set(enc.state_dict().keys()) == keys
+    sd = {k: v.detach().to(torch.bfloat16).float() for k, v in enc.state_dict().items()}
+    assert rel(out, O.bert_encoder(x.to(torch.bfloat16).float(), add, sd, "", 2, 1)) < 2e-2
