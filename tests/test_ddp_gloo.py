@@ -80,3 +80,72 @@ def test_bucket_allreduce_world2():
     result = mgr.dict()
     mp.spawn(_worker, args=(2, port, result), nprocs=2, join=True)
     assert result.get(0) and result.get(1)
+
+
+def _e2e_worker(rank, world, port, result):
+    """Whole data-parallel step on CPU: the real host code (encoder module, autograd Function, bucket hooks, end-of-backward
+    callback) over the kernel test double (tests/fake_kernels.py); both ranks must end with the average of the
+    single-process gradients of their two batches."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_kernels as FK
+        import mmf_b200.engine as E
+        import mmf_b200.modules as M
+        from mmf_b200.ddp import B200DataParallel
+        E.F = FK
+        M._require_cuda = lambda t, what: None
+        cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=3,
+                                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12)
+        torch.manual_seed(100 + rank)                     # different init per rank: the wrapper broadcasts rank 0's
+        enc = M.B200BertEncoder(cfg).eval()
+        ddp = B200DataParallel(enc, bucket_bytes=1, overlap=False)
+        g = torch.Generator().manual_seed(7)
+        xs = [torch.randn(2, 6, 64, generator=g) for _ in range(world)]
+        ws = [torch.randn(2, 6, 64, generator=g) for _ in range(world)]
+        (ddp(xs[rank], None)[0] * ws[rank]).sum().backward()
+        got = {k: p.grad.detach().clone() for k, p in enc.named_parameters()}
+        # single-process reference: mean over the two batches on an un-wrapped copy with the same (rank 0) weights
+        ref_enc = M.B200BertEncoder(cfg).eval()
+        ref_enc.load_state_dict(enc.state_dict())
+        acc = None
+        for r in range(world):
+            ref_enc.zero_grad(set_to_none=True)
+            (ref_enc(xs[r], None)[0] * ws[r]).sum().backward()
+            cur = {k: p.grad.detach().clone() for k, p in ref_enc.named_parameters()}
+            acc = cur if acc is None else {k: acc[k] + cur[k] for k in acc}
+        for k in got:
+            ref = acc[k] / world
+            err = (got[k] - ref).norm() / ref.norm().clamp_min(1e-3 * ref.numel() ** 0.5)
+            assert err < 1e-3, (k, float(err))
+        # second step under no_sync(): local gradients only, then reduce_now() gives the mean of the accumulated ones
+        enc.zero_grad(set_to_none=True)
+        with ddp.no_sync():
+            (ddp(xs[rank], None)[0] * ws[rank]).sum().backward()
+        local = enc.layer[0].output.dense.weight.grad.detach().clone()
+        ddp.reduce_now()
+        ref = acc["layer.0.output.dense.weight"] / world
+        assert (enc.layer[0].output.dense.weight.grad - ref).norm() / ref.norm() < 1e-3
+        assert (local - ref).norm() / ref.norm() > 1e-2           # before the reduction it really was rank-local
+        # the encoder applied twice in one graph (two autograd nodes on one pack): the second node re-enters the pack,
+        # the wrapper re-sends the regions, and the result is still the mean over ranks of the summed gradients
+        enc.zero_grad(set_to_none=True)
+        o = 1 - rank
+        ((ddp(xs[rank], None)[0] * ws[rank]).sum() + (enc(xs[o], None)[0] * ws[o]).sum()).backward()
+        k = "layer.1.intermediate.dense.weight"
+        ref = acc[k]                                       # every rank saw both batches -> mean == sum of the two
+        assert (enc.layer[1].intermediate.dense.weight.grad - ref).norm() / ref.norm() < 1e-3
+        result[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_step_end_to_end_world2():
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_e2e_worker, args=(2, port, result), nprocs=2, join=True)
+    assert result.get(0) and result.get(1)
