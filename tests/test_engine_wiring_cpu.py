@@ -396,3 +396,31 @@ def test_monkey_patch_swap_on_hf_bert_encoder_cpu(cpu_modules):
     assert BertEncoder.forward is orig_forward and set(enc.state_dict().keys()) == keys
     sd = {k: v.detach().to(torch.bfloat16).float() for k, v in enc.state_dict().items()}
     assert rel(out, O.bert_encoder(x.to(torch.bfloat16).float(), add, sd, "", 2, 1)) < 2e-2
+
+
+def test_visual_bert_trunk_vs_oracle_cpu(cpu_frontends):
+    """SampleList -> masks (integer, exact) -> embeddings -> encoder -> pooler, the bench's model at toy size"""
+    from mmf_b200.visual_bert import B200VisualBERT
+    cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2,
+                                vocab_size=50, max_position_embeddings=64, type_vocab_size=2, visual_embedding_dim=40,
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12,
+                                hidden_act="gelu", initializer_range=0.02)
+    torch.manual_seed(2)
+    model = B200VisualBERT(cfg).eval()
+    _bf16_round_(model)
+    B, T, R = 3, 9, 5
+    ids = torch.randint(1, 50, (B, T))
+    imask = torch.ones(B, T, dtype=torch.long)
+    imask[0, 6:] = 0
+    seg = torch.zeros(B, T, dtype=torch.long)
+    feats = torch.randn(B, R, 40).abs().to(torch.bfloat16).float()
+    maxf = torch.tensor([5, 3, 4])
+    out = model({"input_ids": ids, "input_mask": imask, "segment_ids": seg, "image_feature_0": feats,
+                 "image_info_0": {"max_features": maxf}})
+    image_mask, vtype, att = O.visual_bert_masks(imask, maxf, R)
+    assert torch.equal(out["image_mask"], image_mask) and torch.equal(out["attention_mask"], att)
+    sd = {k: v.detach() for k, v in model.bert.state_dict().items()}
+    emb = O.visio_linguistic_embeddings(ids, seg, feats, vtype, sd, "embeddings")
+    seq = O.bert_encoder(emb, O.extended_attention_mask(att), sd, "encoder", 2, 1)
+    assert rel(out["sequence_output"], seq) < 2e-2
+    assert rel(out["pooled_output"], O.bert_pooler(seq, sd, "pooler")) < 2e-2
