@@ -17,6 +17,10 @@ _LAZY = {
     "B200MMBTModel": ("mmbt", "B200MMBTModel"),
     "B200ViLBERTBase": ("vilbert", "B200ViLBERTBase"),
     "B200TransformerBackend": ("mmft_backend", "B200TransformerBackend"),
+    "B200TransformerEncoder": ("encoders", "B200TransformerEncoder"),
+    "B200FinetuneFasterRcnnFpnFc7": ("encoders", "B200FinetuneFasterRcnnFpnFc7"),
+    "B200IdentityEncoder": ("encoders", "B200IdentityEncoder"),
+    "build_encoder": ("encoders", "build_encoder"),
     "B200DataParallel": ("ddp", "B200DataParallel"),
     "replace_with_b200": ("patch", "replace_with_b200"),
     "undo_replace_with_b200": ("patch", "undo_replace_with_b200"),
