@@ -1324,8 +1324,8 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
   p.scale2 = LOG2E / sqrtf(static_cast<float>(D));
   if (D == 64 && a.Skv <= 256) {
-    static const bool v2 = [] { const char* e = getenv("MMFB_ATTN_FWD"); return e != nullptr && e[0] == '2'; }();
-    if (v2) {
+    const char* v2_env = getenv("MMFB_ATTN_FWD");      // read per call: a test process can run both kernels
+    if (v2_env != nullptr && v2_env[0] == '2') {
       const int smem2 = 2 * (16384 + 32768 + 32768) + (512 + 1024 + 1024) * 4 + 128 + 1024;
       static bool attr_set = false;
       if (!attr_set) {

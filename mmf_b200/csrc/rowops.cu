@@ -667,7 +667,9 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   if (!a.dx || !a.y || !a.mean || !a.rstd || !a.gamma) return set_error(MMFB_ERR_ARG, "layernorm_bwd: null pointer");
   if (a.drop_mask && !a.dz) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dropout mask given without dz");
   const int nv_ = (a.H + 255) / 256;
-  static const bool lean = [] { const char* e = getenv("MMFB_LN_BWD"); return e != nullptr && e[0] == 'l'; }();
+  // read per call (not cached) so that one test process can run both variants back to back
+  const char* lean_env = getenv("MMFB_LN_BWD");
+  const bool lean = lean_env != nullptr && lean_env[0] == 'l';
   if (lean && nv_ <= 4) {
     int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
     const int cap = num_sms() * 2;      // two resident blocks per SM, rows strided over them

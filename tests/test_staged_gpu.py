@@ -29,3 +29,69 @@ def test_async_dropout_state_draws_the_same_bits():
     with pytest.raises(RuntimeError):
         a.prefetch(sites, torch.device("cuda"))
         a.bits((1,), 32, 0.1, "cuda")                   # asked out of order
+
+
+def test_lean_layernorm_backward_matches_the_default_pair():
+    from mmf_b200 import functional as F
+    torch.manual_seed(0)
+    M, H = 1000, 768
+    dx = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    dx2 = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    y = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    g = (1.0 + 0.1 * torch.randn(H, device="cuda")).to(torch.bfloat16)
+    b = torch.zeros(H, device="cuda", dtype=torch.bfloat16)
+    _, mean, rstd = F.layernorm_fwd(y, g, b)
+    bits = F.dropout_bits((M,), H, 0.1, 3, 0, "cuda")
+
+    def run(variant, with_dx2, with_drop):
+        if variant:
+            os.environ["MMFB_LN_BWD"] = variant
+        else:
+            os.environ.pop("MMFB_LN_BWD", None)
+        dg, db, dbias = (torch.zeros(H, device="cuda") for _ in range(3))
+        dy, dz = F.layernorm_bwd(dx, y, mean, rstd, g, dg, db, dbias=dbias, dx2=dx2 if with_dx2 else None,
+                                 drop_mask=bits if with_drop else None, drop_scale=1.0 / 0.9)
+        torch.cuda.synchronize()
+        return dy.float(), dz.float(), dg, db, dbias
+    try:
+        for with_dx2 in (False, True):
+            for with_drop in (False, True):
+                ref = run(None, with_dx2, with_drop)
+                got = run("lean", with_dx2, with_drop)
+                assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])          # row math is identical
+                for r, t in zip(ref[2:], got[2:]):                                         # sums: different order
+                    assert (r - t).abs().max() <= 1e-3 * r.abs().max().clamp_min(1.0)
+    finally:
+        os.environ.pop("MMFB_LN_BWD", None)
+
+
+@pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (128, 256, False), (100, 36, True), (256, 17, False)])
+def test_pipelined_attention_forward_matches_the_default_kernel(Sq, Skv, drop):
+    from mmf_b200 import functional as F
+    torch.manual_seed(Sq + Skv)
+    B, heads, d = 5, 3, 64
+    W = heads * d
+    q = torch.randn(B * Sq, W, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    mask = torch.zeros(B, Skv, device="cuda")
+    mask[1, Skv // 2:] = -10000.0
+    mask[2, :] = -10000.0                                   # fully masked sample: uniform softmax
+    bits = F.dropout_bits((B, heads, Sq), Skv, 0.1, 5, 0, "cuda") if drop else None
+
+    def run(variant):
+        if variant:
+            os.environ["MMFB_ATTN_FWD"] = variant
+        else:
+            os.environ.pop("MMFB_ATTN_FWD", None)
+        ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, Sq, Skv, mask, bits, 1.0 / 0.9 if drop else 1.0, save_fp32=True)
+        torch.cuda.synchronize()
+        return ctx.float(), lse2, c32
+    try:
+        ref, got = run(None), run("2")
+    finally:
+        os.environ.pop("MMFB_ATTN_FWD", None)
+    assert torch.isfinite(got[0]).all()
+    assert (ref[1] - got[1]).abs().max() < 1e-3             # row statistics (log2 domain)
+    assert (ref[2] - got[2]).abs().max() <= 2e-2 * ref[2].abs().max()      # same P (bf16) x V, different summation order
+    assert (ref[0] - got[0]).abs().max() <= 2e-2 * ref[0].abs().max()
