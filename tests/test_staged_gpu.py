@@ -58,7 +58,8 @@ def test_lean_layernorm_backward_matches_the_default_pair():
             for with_drop in (False, True):
                 ref = run(None, with_dx2, with_drop)
                 got = run("lean", with_dx2, with_drop)
-                assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])          # row math is identical
+                for r, t in zip(ref[:2], got[:2]):      # same row arithmetic; FMA contraction may flip a last bf16 bit
+                    assert (r - t).abs().max() <= 1e-2 * r.abs().max() and (r != t).float().mean() < 0.01
                 for r, t in zip(ref[2:], got[2:]):                                         # sums: different order
                     assert (r - t).abs().max() <= 1e-3 * r.abs().max().clamp_min(1.0)
     finally:
