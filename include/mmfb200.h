@@ -160,6 +160,36 @@ int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_strea
 /* fp32 -> bf16 cast of a flat (parameter) buffer */
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream);
 
+/* Fused AdamW step over a FLAT fp32 parameter / gradient buffer (the engine's ParamPack), optionally refreshing the
+ * bf16 compute copy in the same pass.  SURVEY.md 8(f) item 2 - staged: parity tests exist, not yet run on the GPU.
+ * Replaces the per-tensor loop of the reference's optimizer "adam_w" (mmf/modules/optimizers.py:8-17):
+ *   mode 0: transformers AdamW arithmetic as restated in the reference (optimizers.py:60-84):
+ *           m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= step_size * m / (sqrt(v) + eps);  p -= lr * wd * p
+ *           with step_size = lr * sqrt(1-b2^t)/(1-b1^t) (or lr when correct_bias is off), computed by the host
+ *   mode 1: torch.optim.AdamW arithmetic (the reference's fallback when transformers has no AdamW):
+ *           p *= 1 - lr wd;  m += (g-m)(1-b1);  v = b2 v + (1-b2) g^2;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
+ *           with step_size = lr/(1-b1^t), bc2_sqrt = sqrt(1-b2^t)
+ * `group` (nullable) gives the hyper-parameter group of every 8-element block (parameters are padded to multiples of
+ * 8 in the flat buffer); grad_scale multiplies the gradient first (1/loss_scale, clipping coefficient). */
+#define MMFB_ADAMW_MAX_GROUPS 8
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* param_bf16;          /* nullable */
+  const uint8_t* group;      /* nullable: all blocks use group 0 */
+  int64_t n;                 /* elements, multiple of 8 */
+  int n_groups;
+  float lr[MMFB_ADAMW_MAX_GROUPS];
+  float weight_decay[MMFB_ADAMW_MAX_GROUPS];
+  float step_size[MMFB_ADAMW_MAX_GROUPS];
+  float bc2_sqrt[MMFB_ADAMW_MAX_GROUPS];
+  float beta1, beta2, eps, grad_scale;
+  int mode;
+} mmfb_adamw_args;
+int mmfb_adamw(const mmfb_adamw_args* args, mmfb_stream stream);
+
 /* library / diagnostics */
 const char* mmfb_last_error(void);
 int mmfb_version(void);

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import lib
-from .lib import LIB, AttnArgs, ComposeArgs, GemmArgs, LnArgs, ScatterArgs, _ptr, _stream_ptr, check
+from .lib import LIB, AdamWArgs, AttnArgs, ComposeArgs, GemmArgs, LnArgs, ScatterArgs, _ptr, _stream_ptr, check
 
 
 def _req(t, dtype, name):
@@ -225,6 +225,33 @@ def relu_bwd(dy, y):
     dz = torch.empty_like(dy)
     check(LIB.mmfb_relu_bwd(dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), _stream_ptr()))
     return dz
+
+
+def adamw(param, grad, exp_avg, exp_avg_sq, groups, *, beta1, beta2, eps, mode, grad_scale=1.0, group_of_block=None,
+          param_bf16=None):
+    """One fused AdamW step over flat fp32 buffers (staged, include/mmfb200.h: mmfb_adamw).
+    groups: list (<= 8) of dicts {lr, weight_decay, step_size, bc2_sqrt}; group_of_block: uint8 [n/8] or None."""
+    for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, n)
+        if not t.is_contiguous() or t.numel() != param.numel():
+            raise ValueError("adamw: %s must be contiguous and as large as param" % n)
+    a = AdamWArgs()
+    a.param, a.grad, a.exp_avg, a.exp_avg_sq = param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr()
+    if param_bf16 is not None:
+        _req(param_bf16, torch.bfloat16, "param_bf16")
+        a.param_bf16 = param_bf16.data_ptr()
+    if group_of_block is not None:
+        _req(group_of_block, torch.uint8, "group_of_block")
+        if group_of_block.numel() != param.numel() // 8:
+            raise ValueError("adamw: group_of_block needs one entry per 8 elements")
+        a.group = group_of_block.data_ptr()
+    a.n, a.n_groups = param.numel(), len(groups)
+    if not 1 <= len(groups) <= 8:
+        raise ValueError("adamw: between 1 and 8 hyper-parameter groups per launch")
+    for i, g in enumerate(groups):
+        a.lr[i], a.weight_decay[i], a.step_size[i], a.bc2_sqrt[i] = g["lr"], g["weight_decay"], g["step_size"], g["bc2_sqrt"]
+    a.beta1, a.beta2, a.eps, a.grad_scale, a.mode = float(beta1), float(beta2), float(eps), float(grad_scale), int(mode)
+    check(LIB.mmfb_adamw(ctypes.byref(a), _stream_ptr()))
 
 
 def cast_f32_bf16(src, dst):

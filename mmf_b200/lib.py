@@ -84,6 +84,18 @@ class ComposeArgs(ctypes.Structure):
     ]
 
 
+class AdamWArgs(ctypes.Structure):
+    _fields_ = [
+        ("param", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p),
+        ("exp_avg_sq", ctypes.c_void_p), ("param_bf16", ctypes.c_void_p), ("group", ctypes.c_void_p),
+        ("n", ctypes.c_int64), ("n_groups", ctypes.c_int),
+        ("lr", ctypes.c_float * 8), ("weight_decay", ctypes.c_float * 8), ("step_size", ctypes.c_float * 8),
+        ("bc2_sqrt", ctypes.c_float * 8),
+        ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float), ("grad_scale", ctypes.c_float),
+        ("mode", ctypes.c_int),
+    ]
+
+
 class ScatterArgs(ctypes.Structure):
     _fields_ = [
         ("dsrc", ctypes.c_void_p * 2), ("ldsrc", ctypes.c_int64 * 2), ("src_row", ctypes.c_void_p * 2),

@@ -426,3 +426,31 @@ def make_encoder_weights(num_layers, hidden, inter, seed=0, prefix="layer"):
     for i in range(num_layers):
         init_bert_layer_weights(sd, "%s.%d" % (prefix, i), hidden, inter, gen)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------
+# optimizer "adam_w" 
+# ----------------------------------------------------------------------------------------------
+def adamw_step_transformers(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay, correct_bias=True):
+    """One step of the transformers AdamW arithmetic as it stands in the reference tree
+    (mmf/modules/optimizers.py:60-84); `step` is the 1-based step count.  In place on p, m, v."""
+    m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    denom = v.sqrt().add_(eps)
+    step_size = lr
+    if correct_bias:
+        step_size = step_size * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    p.addcdiv_(m, denom, value=-step_size)
+    if weight_decay > 0.0:
+        p.add_(p, alpha=-lr * weight_decay)
+
+
+def adamw_step_torch(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay):
+    """torch.optim.AdamW (single-tensor path), what `adam_w` resolves to when transformers ships no AdamW
+    (mmf/modules/optimizers.py:8-14).  In place on p, m, v."""
+    p.mul_(1.0 - lr * weight_decay)
+    m.lerp_(g, 1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))

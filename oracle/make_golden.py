@@ -289,6 +289,31 @@ def golden_encoders():
     })
 
 
+def golden_adamw():
+    """optimizer `adam_w`: 5 steps on three small parameters, two hyper-parameter groups (decay / no decay), with the
+    reference's transformers arithmetic (AdamWSkipParamsWithZeroGrad.step, optimizers.py:22-86) and with what `adam_w`
+    itself resolves to here (torch.optim.AdamW, optimizers.py:8-14)."""
+    opt = R.optimizers()
+    g = torch.Generator().manual_seed(71)
+    init = [torch.randn(16, 24, generator=g), torch.randn(24, generator=g), 1.0 + 0.1 * torch.randn(24, generator=g)]
+    grads = [[torch.randn(t.shape, generator=g) * 0.1 for t in init] for _ in range(5)]
+    hp = dict(lr=5e-3, betas=(0.9, 0.98), eps=1e-6)
+
+    def run(cls):
+        ps = [torch.nn.Parameter(t.clone()) for t in init]
+        o = cls([{"params": [ps[0]], "weight_decay": 0.01}, {"params": ps[1:], "weight_decay": 0.0}], **hp)
+        traj = []
+        for gs in grads:
+            for p_, g_ in zip(ps, gs):
+                p_.grad = g_.clone()
+            o.step()
+            traj.append([p_.detach().clone() for p_ in ps])
+        return traj
+    _save("adamw", {"init": init, "grads": grads, "hp": hp, "weight_decay": [0.01, 0.0, 0.0],
+                    "transformers": run(opt.AdamWSkipParamsWithZeroGrad), "torch": run(opt.AdamW),
+                    "adam_w_is": opt.AdamW.__module__})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -298,6 +323,7 @@ def main():
     golden_mmbt()
     golden_mmft_embeddings()
     golden_encoders()
+    golden_adamw()
 
 
 if __name__ == "__main__":

@@ -136,3 +136,9 @@ def encoders():
     hf_layers()
     embeddings()
     return load("mmf/modules/encoders.py", "mmf.modules.encoders")
+
+
+def optimizers():
+    """mmf/modules/optimizers.py: `adam_w` (transformers AdamW, or torch.optim.AdamW when transformers has none - the case
+    here) and AdamWSkipParamsWithZeroGrad, whose step() carries the transformers arithmetic inside the reference tree."""
+    return load("mmf/modules/optimizers.py", "mmf.modules.optimizers")

@@ -206,3 +206,25 @@ def embed_scatter_sorted(dy, dtab, sorted_idx, order):
 
 def relu_bwd(dy, y):
     return torch.where(y > 0, dy, torch.zeros_like(dy))
+
+
+def adamw(param, grad, exp_avg, exp_avg_sq, groups, *, beta1, beta2, eps, mode, grad_scale=1.0, group_of_block=None,
+          param_bf16=None):
+    """contract of mmfb_adamw: one pass over flat fp32 buffers, hyper-parameters looked up per 8-element block"""
+    assert param.numel() % 8 == 0
+    gid = group_of_block.long().repeat_interleave(8) if group_of_block is not None else torch.zeros(param.numel(), dtype=torch.long)
+    tab = lambda k: torch.tensor([g[k] for g in groups], dtype=torch.float32)[gid]
+    lr, wd, step, bc2s = tab("lr"), tab("weight_decay"), tab("step_size"), tab("bc2_sqrt")
+    g = grad * grad_scale
+    if mode == 0:
+        exp_avg.mul_(beta1).add_(g, alpha=1.0 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+        param.sub_(step * (exp_avg / (exp_avg_sq.sqrt() + eps)))
+        param.sub_(torch.where(wd > 0, lr * wd * param, torch.zeros_like(param)))
+    else:
+        param.mul_(1.0 - lr * wd)
+        exp_avg.lerp_(g, 1.0 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+        param.sub_(step * (exp_avg / (exp_avg_sq.sqrt() / bc2s + eps)))
+    if param_bf16 is not None:
+        param_bf16.copy_(param.to(BF))
