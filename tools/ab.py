@@ -7,6 +7,9 @@ On the GPU box:   python tools/ab.py run x2 [--tests] [--steps 12]   (one gpurun
     1. (--tests) the whole `-m gpu` suite with MMFB_LIB pointing at the variant: parity first
     2. bench.py with the product library, then with the variant, back to back on the same box / clocks
     3. one line per arm + the ratio; the two bench JSON lines are kept in gpurun_out/ab_<name>_{base,variant}.json
+                  python tools/ab.py sweep x2 lnlean:MMFB_LN_BWD=lean rng:MMFB_DROPOUT_ASYNC=1 all:MMFB_LN_BWD=lean,MMFB_DROPOUT_ASYNC=1
+                  (the product library once, then every NAME[:ENV=VAL,...] in turn; a variant library libmmfb200_NAME.so
+                  is used when it exists; one table at the end, JSON lines in gpurun_out/ab_sweep_*.json)
 MMFB_LIB only selects which build of the SAME C ABI is loaded; there is no fallback involved.
 """
 import json
@@ -35,7 +38,32 @@ def bench(env, steps, warmup, out):
     return json.loads(lines[-1])
 
 
+def sweep(specs, steps):
+    env_b = {k: v for k, v in os.environ.items() if k != "MMFB_LIB"}
+    rows = [("base", bench(env_b, steps, 4, "ab_sweep_base.json"))]
+    for spec in specs:
+        name, _, envs = spec.partition(":")
+        env = dict(env_b)
+        for kv in filter(None, envs.split(",")):
+            k, v = kv.split("=", 1)
+            env[k] = v
+        if os.path.exists(lib_path(name)):
+            env["MMFB_LIB"] = lib_path(name)
+        try:
+            rows.append((spec, bench(env, steps, 4, "ab_sweep_%s.json" % name)))
+        except SystemExit as e:
+            print("%-40s FAILED (%s)" % (spec, e))
+    base = rows[0][1]["value"]
+    for tag, d in rows:
+        print("%-40s %8.1f samples/s  %7.3f ms/step  x%.4f  sm_mhz %s" % (
+            tag, d["value"], d["ms_per_step"], d["value"] / base, (d.get("clocks") or {}).get("sm_mhz")))
+
+
 def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "sweep":
+        specs = [a for a in sys.argv[2:] if not a.startswith("--") and not a.isdigit()]
+        steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 12
+        return sweep(specs, steps)
     if len(sys.argv) < 3 or sys.argv[1] not in ("build", "run"):
         raise SystemExit(__doc__)
     mode, name = sys.argv[1], sys.argv[2]
