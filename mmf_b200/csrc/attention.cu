@@ -986,7 +986,10 @@ struct AttnBwdFusedDev {
   bf16* dv; int64_t ld_dv;
 };
 
-template <bool DROP>
+// OVL (staged, MMFB_ATTN_BWD_OVERLAP=1): the score MMAs of pair k+1 are issued BEFORE the accumulations of pair k, and the
+// compute threads wait for those accumulations only right before their first shared-memory store - the first chunk's
+// arithmetic of pair k+1 then overlaps the 24 accumulation MMAs of pair k instead of idling behind them.
+template <bool DROP, bool OVL = false>
 __global__ void __launch_bounds__(288, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1059,22 +1062,40 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t idesc_q = umma_idesc_bf16(128, D, false, true);   // A K-major,  B MN-major
       const uint32_t idesc_t = umma_idesc_bf16(128, D, true, true);    // A MN-major, B MN-major
       mbar_wait(r_full, 0);
+      auto issue_scores = [&](int i, int j) {      // S = Q_i K_j^T, dP = dO_i V_j^T
+        const uint32_t aQ_ = smem_u32(sQ + i * TILE), adO_ = smem_u32(sdO + i * TILE);
+        const uint32_t aK_ = smem_u32(sK + j * TILE), aV_ = smem_u32(sV + j * TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + COL_S, umma_desc_sw128(aQ_ + kk * 32, 16, 1024), umma_desc_sw128(aK_ + kk * 32, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + COL_DP, umma_desc_sw128(adO_ + kk * 32, 16, 1024), umma_desc_sw128(aV_ + kk * 32, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(s_ready);
+      };
       int pair = 0;
+      if (OVL) {
+        tc_fence_after();
+        issue_scores(0, 0);
+      }
       for (int j = 0; j < nj; ++j) {
         for (int i = 0; i < ni; ++i, ++pair) {
           tc_fence_after();
           const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
-          const uint32_t aK = smem_u32(sK + j * TILE), aV = smem_u32(sV + j * TILE);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_base + COL_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
-                      idesc_s, kk > 0 ? 1u : 0u);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_base + COL_DP, umma_desc_sw128(adO + kk * 32, 16, 1024), umma_desc_sw128(aV + kk * 32, 16, 1024),
-                      idesc_s, kk > 0 ? 1u : 0u);
-          umma_commit(s_ready);
+          const uint32_t aK = smem_u32(sK + j * TILE);
+          if (!OVL) issue_scores(i, j);
           mbar_wait(p_ready, pair & 1);
+          if (OVL) {
+            // S and dP of this pair have been read: the next pair's scores go first, its arithmetic starts while the
+            // accumulations below are still running
+            const int i2 = (i + 1 < ni) ? i + 1 : 0, j2 = (i + 1 < ni) ? j : j + 1;
+            if (j2 < nj) {
+              tc_fence_after();
+              issue_scores(i2, j2);
+            }
+          }
           // dK_j / dV_j of the previous key block must have been read out before the first pair of this block overwrites them
           if (i == 0 && j > 0) mbar_wait(kv_read, (j - 1) & 1);
           tc_fence_after();
@@ -1104,7 +1125,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int i = 0; i < ni; ++i, ++pair) {
         const int q = i * 128 + row;
         const float l2 = sLse[q], dl = sDel[q];
-        if (pair > 0) mbar_wait(acc_done, (pair - 1) & 1);   // P'/dS' buffers are free again
+        if (!OVL && pair > 0) mbar_wait(acc_done, (pair - 1) & 1);   // P'/dS' buffers are free again
         mbar_wait(s_ready, pair & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -1168,6 +1189,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #endif
           uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
           uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
+          // OVL: the accumulations of the previous pair still read P'/dS' while the arithmetic above ran
+          if (OVL && c == half && pair > 0) mbar_wait(acc_done, (pair - 1) & 1);
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
@@ -1417,7 +1440,19 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       fset = true;
     }
     dim3 grid(a.heads, a.B);
-    if (f.dmask != nullptr) attn_bwd_fused_kernel<true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+    const char* ovl_env = getenv("MMFB_ATTN_BWD_OVERLAP");      // staged variant, read per call
+    if (ovl_env != nullptr && ovl_env[0] == '1') {
+      static bool ovl_attr = false;
+      if (!ovl_attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(attn_bwd_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(fused, overlap) smem attr: %s", cudaGetErrorString(e));
+        ovl_attr = true;
+      }
+      if (f.dmask != nullptr) attn_bwd_fused_kernel<true, true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+      else attn_bwd_fused_kernel<false, true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+    } else if (f.dmask != nullptr) attn_bwd_fused_kernel<true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
     else attn_bwd_fused_kernel<false><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
     count_launch();
     cudaError_t e = cudaGetLastError();

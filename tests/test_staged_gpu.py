@@ -136,3 +136,35 @@ def test_adamw_kernel_matches_the_oracle(mode):
         idx = sel < 2
         assert (p.cpu()[idx] - ref_p[idx]).abs().max() <= 2e-6 * ref_p[idx].abs().max()
         assert torch.equal(p.cpu()[sel == 2], ref_p[sel == 2])          # frozen blocks are bit-identical
+
+
+@pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (256, 130, False), (100, 256, True)])
+def test_overlapped_fused_attention_backward_matches_the_default(Sq, Skv, drop):
+    from mmf_b200 import functional as F
+    torch.manual_seed(Sq * 3 + Skv)
+    B, heads, d = 4, 3, 64
+    W = heads * d
+    q = torch.randn(B * Sq, W, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    dctx = torch.randn(B * Sq, W, device="cuda").to(torch.bfloat16)
+    mask = torch.zeros(B, Skv, device="cuda")
+    mask[1, Skv // 3:] = -10000.0
+    bits = F.dropout_bits((B, heads, Sq), Skv, 0.1, 9, 0, "cuda") if drop else None
+    scale = 1.0 / 0.9 if drop else 1.0
+    ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, Sq, Skv, mask, bits, scale, save_fp32=True)
+
+    def run(flag):
+        if flag:
+            os.environ["MMFB_ATTN_BWD_OVERLAP"] = "1"
+        else:
+            os.environ.pop("MMFB_ATTN_BWD_OVERLAP", None)
+        out = F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask, bits, scale, ctx32=c32)
+        torch.cuda.synchronize()
+        return [t.clone() for t in out]
+    try:
+        ref, got = run(False), run(True)
+    finally:
+        os.environ.pop("MMFB_ATTN_BWD_OVERLAP", None)
+    for r, t in zip(ref, got):
+        assert torch.equal(r, t)        # the same MMAs in the same accumulation order: only the issue order differs

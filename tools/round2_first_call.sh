@@ -10,7 +10,8 @@ MMFB_STAGED_TESTS=1 timeout 300 python -m pytest tests/test_staged_gpu.py -m gpu
 MMFB_LIB=$PWD/mmf_b200/csrc/libmmfb200_x2.so timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 MMFB_LN_BWD=lean timeout 300 python -m pytest tests/test_rowops_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_ATTN_FWD=2 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
+MMFB_ATTN_BWD_OVERLAP=1 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_DROPOUT_ASYNC=1 MMFB_SIDE_REDUCE=1 timeout 300 python -m pytest tests/test_encoder_gpu.py tests/test_visual_bert_gpu.py -m gpu -q -x 2>&1 | tail -5
 timeout 600 python tools/ab.py sweep x2 lnlean:MMFB_LN_BWD=lean rng:MMFB_DROPOUT_ASYNC=1 side:MMFB_SIDE_REDUCE=1 \
-    attn2:MMFB_ATTN_FWD=2 --steps 12
+    attn2:MMFB_ATTN_FWD=2 bwdovl:MMFB_ATTN_BWD_OVERLAP=1 --steps 12
 timeout 200 python tools/bench_vilbert.py --steps 5 --warmup 3
