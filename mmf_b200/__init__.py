@@ -17,6 +17,7 @@ _LAZY = {
     "B200MMBTModel": ("mmbt", "B200MMBTModel"),
     "B200ViLBERTBase": ("vilbert", "B200ViLBERTBase"),
     "B200TransformerBackend": ("mmft_backend", "B200TransformerBackend"),
+    "B200UNITERModelBase": ("uniter", "B200UNITERModelBase"),
     "B200TransformerEncoder": ("encoders", "B200TransformerEncoder"),
     "B200FinetuneFasterRcnnFpnFc7": ("encoders", "B200FinetuneFasterRcnnFpnFc7"),
     "B200IdentityEncoder": ("encoders", "B200IdentityEncoder"),

@@ -429,6 +429,37 @@ def make_encoder_weights(num_layers, hidden, inter, seed=0, prefix="layer"):
 
 
 # ----------------------------------------------------------------------------------------------
+# UNITER (BASELINE.json configs[4] class)
+# ----------------------------------------------------------------------------------------------
+def uniter_image_embeddings(img_feat, img_pos_feat, type_embeddings, sd, prefix, img_masks=None, eps=LN_EPS):
+    """UNITERImageEmbeddings.forward, mmf/models/uniter.py:69-88 (dropout p = 0)."""
+    if img_masks is not None:
+        table = sd[prefix + ".mask_embedding.weight"].clone()
+        table[0] = 0.0                                   # padding_idx row is forced to zero on every call (:77)
+        img_feat = img_feat + table[img_masks.long()]
+    im = layer_norm(linear(img_feat, sd, prefix + ".img_linear"), sd, prefix + ".img_layer_norm", eps)
+    pos = layer_norm(linear(img_pos_feat, sd, prefix + ".pos_linear"), sd, prefix + ".pos_layer_norm", eps)
+    return layer_norm(im + pos + type_embeddings, sd, prefix + ".final_layer_norm", eps)
+
+
+def uniter_forward(input_ids, position_ids, img_feat, img_pos_feat, attention_mask, sd, num_layers, heads, img_masks=None,
+                   txt_type_ids=None, img_type_ids=None, input_modality="image-text"):
+    """UNITERModelBase.forward, mmf/models/uniter.py:197-243 -> (final_layer, hidden_layers)"""
+    add = extended_attention_mask(attention_mask)
+    parts = []
+    if input_modality != "image":
+        parts.append(bert_embeddings(input_ids, txt_type_ids, sd, "text_embeddings", position_ids))
+    if input_modality != "text":
+        if img_type_ids is None:
+            img_type_ids = torch.ones_like(img_feat[:, :, 0].long())
+        tt = sd["text_embeddings.token_type_embeddings.weight"][img_type_ids]
+        parts.append(uniter_image_embeddings(img_feat, img_pos_feat, tt, sd, "img_embeddings", img_masks))
+    emb = torch.cat(parts, dim=1)
+    out, hiddens = bert_encoder(emb, add, sd, "encoder", num_layers, heads, output_hidden_states=True)
+    return out, hiddens
+
+
+# ----------------------------------------------------------------------------------------------
 # optimizer "adam_w" (SURVEY.md 8f item 2)
 # ----------------------------------------------------------------------------------------------
 def adamw_step_transformers(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay, correct_bias=True):

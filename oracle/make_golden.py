@@ -289,6 +289,51 @@ def golden_encoders():
     })
 
 
+def golden_uniter():
+    """UNITERModelBase.forward (uniter.py:197-243) with UNITERImageEmbeddings (:43-88).  The constructor pulls
+    bert-base-uncased from the hub, so the object is assembled around the reference's own forward / embedding code with
+    explicit-config sub-modules; the encoder is the reference's BertEncoderJit (what replace_with_jit() installs)."""
+    from transformers import BertConfig
+    from transformers.models.bert.modeling_bert import BertEmbeddings, BertPooler
+    un = R.uniter()
+    hl = R.hf_layers()
+    cfg = BertConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2, vocab_size=50,
+                     max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = un.UNITERModelBase.__new__(un.UNITERModelBase)
+    torch.nn.Module.__init__(m)
+    m.text_embeddings = BertEmbeddings(cfg)
+    m.img_embeddings = un.UNITERImageEmbeddings(img_dim=40, hidden_size=128, hidden_dropout_prob=0.0)
+    m.encoder = hl.BertEncoderJit(cfg)
+    m.pooler = BertPooler(cfg)
+    _perturb(m, 81)
+    m.eval()
+    g = torch.Generator().manual_seed(82)
+    B, T, Rr = 3, 6, 5
+    ids = torch.randint(0, 50, (B, T), generator=g)
+    pos_ids = torch.arange(T).unsqueeze(0).expand(B, T).contiguous()
+    feat = torch.randn(B, Rr, 40, generator=g, requires_grad=True)
+    pos = torch.rand(B, Rr, 7, generator=g)
+    att = torch.ones(B, T + Rr, dtype=torch.long)
+    att[1, 4:T] = 0
+    att[2, T + 3:] = 0
+    img_masks = torch.zeros(B, Rr, dtype=torch.long)
+    img_masks[0, 1] = 1
+    out = m(ids, pos_ids, feat, pos, att)
+    w = torch.randn(out.final_layer.shape, generator=g)
+    (out.final_layer * w).sum().backward()
+    names = [n for n, _ in m.named_parameters()]
+    masked = m(ids, pos_ids, feat.detach(), pos, att, img_masks=img_masks).final_layer.detach()
+    img_only = m(ids, pos_ids, feat.detach(), pos, att[:, T:], input_modality="image").final_layer.detach()
+    _save("uniter", {
+        "cfg": {"hidden": 128, "heads": 2, "inter": 256, "layers": 2, "vocab": 50, "max_pos": 32, "img_dim": 40},
+        "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+        "ids": ids, "pos_ids": pos_ids, "feat": feat.detach(), "pos": pos, "att": att, "img_masks": img_masks,
+        "final": out.final_layer.detach(), "n_hidden": len(out.hidden_layers),
+        "hidden_1": out.hidden_layers[1].detach(), "w_rand": w, "dfeat": feat.grad.detach(), "grads": _grads(m, names),
+        "final_masked": masked, "final_image_only": img_only,
+    })
+
+
 def golden_adamw():
     """optimizer `adam_w`: 5 steps on three small parameters, two hyper-parameter groups (decay / no decay), with the
     reference's transformers arithmetic (AdamWSkipParamsWithZeroGrad.step, optimizers.py:22-86) and with what `adam_w`
@@ -324,6 +369,7 @@ def main():
     golden_mmft_embeddings()
     golden_encoders()
     golden_adamw()
+    golden_uniter()
 
 
 if __name__ == "__main__":

@@ -142,3 +142,8 @@ def optimizers():
     """mmf/modules/optimizers.py: `adam_w` (transformers AdamW, or torch.optim.AdamW when transformers has none - the case
     here) and AdamWSkipParamsWithZeroGrad, whose step() carries the transformers arithmetic inside the reference tree."""
     return load("mmf/modules/optimizers.py", "mmf.modules.optimizers")
+
+
+def uniter():
+    hf_layers()
+    return load("mmf/models/uniter.py", "mmf.models.uniter")

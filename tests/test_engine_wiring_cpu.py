@@ -424,3 +424,36 @@ def test_visual_bert_trunk_vs_oracle_cpu(cpu_frontends):
     seq = O.bert_encoder(emb, O.extended_attention_mask(att), sd, "encoder", 2, 1)
     assert rel(out["sequence_output"], seq) < 2e-2
     assert rel(out["pooled_output"], O.bert_pooler(seq, sd, "pooler")) < 2e-2
+
+
+def test_uniter_model_base_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
+    import mmf_b200.uniter as UN
+    monkeypatch.setattr(UN, "_require_cuda", lambda t, what: None)
+    g = torch.load(os.path.join(GOLD, "uniter.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                type_vocab_size=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12, initializer_range=0.02)
+    m = UN.B200UNITERModelBase(cfg, img_dim=c["img_dim"])
+    ref_keys = {k for k in g["state_dict"] if not k.endswith("position_ids") and not k.endswith("token_type_ids")}
+    assert set(m.state_dict().keys()) == ref_keys                   # HF's index buffers aside, the reference's names
+    m.load_state_dict({k: v for k, v in g["state_dict"].items() if k in ref_keys})
+    m.eval()
+    feat = g["feat"].clone().requires_grad_(True)
+    out = m(g["ids"], g["pos_ids"], feat, g["pos"], g["att"])
+    assert len(out.hidden_layers) == g["n_hidden"]
+    assert rel(out.final_layer, g["final"]) < 2e-2 and rel(out.hidden_layers[1], g["hidden_1"]) < 2e-2
+    (out.final_layer * g["w_rand"]).sum().backward()
+    assert rel(feat.grad, g["dfeat"]) < 4e-2
+    named = dict(m.named_parameters())
+    for k in ("img_embeddings.img_linear.weight", "img_embeddings.pos_linear.weight", "img_embeddings.final_layer_norm.weight",
+              "img_embeddings.img_layer_norm.bias", "text_embeddings.token_type_embeddings.weight",
+              "encoder.layer.1.intermediate.dense.weight"):
+        assert rel(named[k].grad, g["grads"][k]) < 6e-2, k
+    with torch.no_grad():
+        masked = m(g["ids"], g["pos_ids"], g["feat"], g["pos"], g["att"], img_masks=g["img_masks"]).final_layer
+        assert rel(masked, g["final_masked"]) < 2e-2
+        T = g["ids"].shape[1]
+        img_only = m(g["ids"], g["pos_ids"], g["feat"], g["pos"], g["att"][:, T:], input_modality="image").final_layer
+        assert rel(img_only, g["final_image_only"]) < 2e-2

@@ -168,3 +168,25 @@ def test_overlapped_fused_attention_backward_matches_the_default(Sq, Skv, drop):
         os.environ.pop("MMFB_ATTN_BWD_OVERLAP", None)
     for r, t in zip(ref, got):
         assert torch.equal(r, t)        # the same MMAs in the same accumulation order: only the issue order differs
+
+
+def test_uniter_model_base_vs_reference_golden():
+    """SURVEY.md 8f item 3 (written after the round's GPU budget was spent; CPU-verified over the kernel test double)"""
+    import types
+    from mmf_b200.uniter import B200UNITERModelBase
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "uniter.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                type_vocab_size=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12, initializer_range=0.02)
+    m = B200UNITERModelBase(cfg, img_dim=c["img_dim"])
+    m.load_state_dict({k: v for k, v in g["state_dict"].items() if k in m.state_dict()})
+    m = m.cuda().eval()
+    cu = lambda k: g[k].cuda()
+    feat = cu("feat").requires_grad_(True)
+    out = m(cu("ids"), cu("pos_ids"), feat, cu("pos"), cu("att"))
+    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
+    assert rel(out.final_layer, g["final"]) < 1e-2 and rel(out.hidden_layers[1], g["hidden_1"]) < 1e-2
+    (out.final_layer * cu("w_rand")).sum().backward()
+    assert rel(feat.grad, g["dfeat"]) < 3e-2
