@@ -18,6 +18,7 @@ _LAZY = {
     "B200ViLBERTBase": ("vilbert", "B200ViLBERTBase"),
     "B200TransformerBackend": ("mmft_backend", "B200TransformerBackend"),
     "B200UNITERModelBase": ("uniter", "B200UNITERModelBase"),
+    "B200LXMERTEncoder": ("lxmert", "B200LXMERTEncoder"),
     "B200TransformerEncoder": ("encoders", "B200TransformerEncoder"),
     "B200FinetuneFasterRcnnFpnFc7": ("encoders", "B200FinetuneFasterRcnnFpnFc7"),
     "B200IdentityEncoder": ("encoders", "B200IdentityEncoder"),

@@ -460,6 +460,49 @@ def uniter_forward(input_ids, position_ids, img_feat, img_pos_feat, attention_ma
 
 
 # ----------------------------------------------------------------------------------------------
+# LXMERT encoder (BASELINE.json configs[4] class)
+# ----------------------------------------------------------------------------------------------
+def visual_feat_encoder(feats, boxes, sd, prefix):
+    """VisualFeatEncoder.forward, mmf/models/lxmert.py:211-223 (dropout p = 0)."""
+    x = layer_norm(linear(feats, sd, prefix + ".visn_fc"), sd, prefix + ".visn_layer_norm")
+    if boxes is None:
+        return x
+    y = layer_norm(linear(boxes, sd, prefix + ".box_fc"), sd, prefix + ".box_layer_norm")
+    return (x + y) / 2
+
+
+def lxmert_xlayer(lang, lang_mask, visn, visn_mask, sd, prefix, heads):
+    """LXMERTXLayer.forward, mmf/models/lxmert.py:244-283: ONE cross-attention block (BertCrossattLayer :68-82) used in
+    both directions from the layer inputs, then per-stream self-attention (BertAttention) and FFN."""
+    ca = prefix + ".visual_attention"
+
+    def cross(x, ctx, ctx_mask):
+        out, _ = bert_self_attention(x, None, sd, ca + ".att", heads, kv=ctx, kv_mask=ctx_mask)
+        return bert_self_output(out, x, sd, ca + ".output")
+    la, va = cross(lang, visn, visn_mask), cross(visn, lang, lang_mask)
+    outs = []
+    for x, mask, name in ((la, lang_mask, "lang"), (va, visn_mask, "visn")):
+        ctx, _ = bert_self_attention(x, mask, sd, "%s.%s_self_att.self" % (prefix, name), heads)
+        att = bert_self_output(ctx, x, sd, "%s.%s_self_att.output" % (prefix, name))
+        inter = bert_intermediate(att, sd, "%s.%s_inter" % (prefix, name))
+        outs.append(bert_self_output(inter, att, sd, "%s.%s_output" % (prefix, name)))
+    return outs[0], outs[1]
+
+
+def lxmert_encoder(lang, lang_mask, feats, boxes, visn_mask, sd, prefix, l_layers, x_layers, r_layers, heads):
+    """LXMERTEncoder.forward, mmf/models/lxmert.py:309-336; masks are the additive [B,1,1,S] tensors."""
+    pre = prefix + "." if prefix else ""
+    visn = visual_feat_encoder(feats, boxes, sd, pre + "visn_fc")
+    for i in range(l_layers):
+        lang, _ = bert_layer(lang, lang_mask, sd, "%slayer.%d" % (pre, i), heads)
+    for i in range(r_layers):
+        visn, _ = bert_layer(visn, visn_mask, sd, "%sr_layers.%d" % (pre, i), heads)
+    for i in range(x_layers):
+        lang, visn = lxmert_xlayer(lang, lang_mask, visn, visn_mask, sd, "%sx_layers.%d" % (pre, i), heads)
+    return lang, visn
+
+
+# ----------------------------------------------------------------------------------------------
 # optimizer "adam_w" (SURVEY.md 8f item 2)
 # ----------------------------------------------------------------------------------------------
 def adamw_step_transformers(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay, correct_bias=True):

@@ -334,6 +334,46 @@ def golden_uniter():
     })
 
 
+def golden_lxmert():
+    """LXMERTEncoder.forward (lxmert.py:309-336) = VisualFeatEncoder + language / relational BERT layers + cross-modality
+    layers with the shared cross-attention block, under the reference's replace_with_jit() (lxmert.py relies on
+    BertSelfAttention(encoder_hidden_states=...), which only the reference's JIT forwards provide on transformers 5)."""
+    from transformers import BertConfig
+    hl = R.hf_layers()
+    lx = R.lxmert()
+    cfg = BertConfig(hidden_size=64, num_attention_heads=1, intermediate_size=128, vocab_size=50,
+                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg.visual_feat_dim, cfg.visual_pos_dim, cfg.l_layers, cfg.x_layers, cfg.r_layers = 40, 4, 2, 2, 1
+    hl.replace_with_jit()
+    try:
+        enc = lx.LXMERTEncoder(cfg).eval()
+        _perturb(enc, 91)
+        g = torch.Generator().manual_seed(92)
+        B, T, Rr = 3, 7, 5
+        lang = torch.randn(B, T, 64, generator=g, requires_grad=True)
+        feats = torch.randn(B, Rr, 40, generator=g, requires_grad=True)
+        boxes = torch.rand(B, Rr, 4, generator=g)
+        lmask = torch.ones(B, T, dtype=torch.long)
+        lmask[1, 4:] = 0
+        vmask = torch.ones(B, Rr, dtype=torch.long)
+        vmask[2, 3:] = 0
+        ladd = (1.0 - lmask[:, None, None, :].float()) * -10000.0
+        vadd = (1.0 - vmask[:, None, None, :].float()) * -10000.0
+        lo, vo = enc(lang, ladd, (feats, boxes), vadd)
+        wl, wv = torch.randn(lo.shape, generator=g), torch.randn(vo.shape, generator=g)
+        ((lo * wl).sum() + (vo * wv).sum()).backward()
+        names = [n for n, _ in enc.named_parameters()]
+        _save("lxmert", {
+            "cfg": {"hidden": 64, "heads": 1, "inter": 128, "feat_dim": 40, "pos_dim": 4, "l": 2, "x": 2, "r": 1},
+            "state_dict": {k: v.detach().clone() for k, v in enc.state_dict().items()},
+            "lang": lang.detach(), "feats": feats.detach(), "boxes": boxes, "lmask": lmask, "vmask": vmask,
+            "lang_out": lo.detach(), "visn_out": vo.detach(), "wl": wl, "wv": wv, "dlang": lang.grad.detach(),
+            "dfeats": feats.grad.detach(), "grads": _grads(enc, names),
+        })
+    finally:
+        hl.undo_replace_with_jit()
+
+
 def golden_adamw():
     """optimizer `adam_w`: 5 steps on three small parameters, two hyper-parameter groups (decay / no decay), with the
     reference's transformers arithmetic (AdamWSkipParamsWithZeroGrad.step, optimizers.py:22-86) and with what `adam_w`
@@ -370,6 +410,7 @@ def main():
     golden_encoders()
     golden_adamw()
     golden_uniter()
+    golden_lxmert()
 
 
 if __name__ == "__main__":

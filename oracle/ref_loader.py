@@ -147,3 +147,10 @@ def optimizers():
 def uniter():
     hf_layers()
     return load("mmf/models/uniter.py", "mmf.models.uniter")
+
+
+def lxmert():
+    """mmf/models/lxmert.py; its BertSelfAttention(encoder_hidden_states=...) call needs the reference's JIT layer
+    implementations installed (hf_layers().replace_with_jit(), as the reference's own constructors do)."""
+    hf_layers()
+    return load("mmf/models/lxmert.py", "mmf.models.lxmert")

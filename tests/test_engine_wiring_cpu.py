@@ -457,3 +457,29 @@ def test_uniter_model_base_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
         T = g["ids"].shape[1]
         img_only = m(g["ids"], g["pos_ids"], g["feat"], g["pos"], g["att"][:, T:], input_modality="image").final_layer
         assert rel(img_only, g["final_image_only"]) < 2e-2
+
+
+def test_lxmert_encoder_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
+    """language / relational layers + cross-modality layers whose ONE cross-attention block serves both directions:
+    its weight gradients are the sum of the two uses (engine.xlayer_bwd accumulates both into the same regions)."""
+    import mmf_b200.lxmert as LX
+    monkeypatch.setattr(LX, "_require_cuda", lambda t, what: None)
+    g = torch.load(os.path.join(GOLD, "lxmert.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, visual_feat_dim=c["feat_dim"],
+                                visual_pos_dim=c["pos_dim"], l_layers=c["l"], x_layers=c["x"], r_layers=c["r"])
+    enc = LX.B200LXMERTEncoder(cfg)
+    assert set(enc.state_dict().keys()) == set(g["state_dict"].keys())
+    enc.load_state_dict(g["state_dict"])
+    enc.eval()
+    lang = g["lang"].clone().requires_grad_(True)
+    feats = g["feats"].clone().requires_grad_(True)
+    lo, vo = enc(lang, O.extended_attention_mask(g["lmask"]), (feats, g["boxes"]), O.extended_attention_mask(g["vmask"]))
+    assert rel(lo, g["lang_out"]) < 2e-2 and rel(vo, g["visn_out"]) < 2e-2
+    ((lo * g["wl"]).sum() + (vo * g["wv"]).sum()).backward()
+    assert rel(lang.grad, g["dlang"]) < 4e-2 and rel(feats.grad, g["dfeats"]) < 4e-2
+    for n, p in enc.named_parameters():
+        if "key" in n and n.endswith("bias"):
+            continue
+        assert rel(p.grad, g["grads"][n]) < 8e-2, n

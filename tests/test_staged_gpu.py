@@ -190,3 +190,28 @@ def test_uniter_model_base_vs_reference_golden():
     assert rel(out.final_layer, g["final"]) < 1e-2 and rel(out.hidden_layers[1], g["hidden_1"]) < 1e-2
     (out.final_layer * cu("w_rand")).sum().backward()
     assert rel(feat.grad, g["dfeat"]) < 3e-2
+
+
+def test_lxmert_encoder_vs_reference_golden():
+    """cross-modality layers with the shared cross-attention block (CPU-verified over the test double)"""
+    import types
+    from mmf_b200.lxmert import B200LXMERTEncoder
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "lxmert.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, visual_feat_dim=c["feat_dim"],
+                                visual_pos_dim=c["pos_dim"], l_layers=c["l"], x_layers=c["x"], r_layers=c["r"])
+    enc = B200LXMERTEncoder(cfg)
+    enc.load_state_dict(g["state_dict"])
+    enc = enc.cuda().eval()
+    lang = g["lang"].cuda().requires_grad_(True)
+    feats = g["feats"].cuda().requires_grad_(True)
+    ladd = ((1.0 - g["lmask"][:, None, None, :].float()) * -10000.0).cuda()
+    vadd = ((1.0 - g["vmask"][:, None, None, :].float()) * -10000.0).cuda()
+    lo, vo = enc(lang, ladd, (feats, g["boxes"].cuda()), vadd)
+    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
+    assert rel(lo, g["lang_out"]) < 1e-2 and rel(vo, g["visn_out"]) < 1e-2
+    ((lo * g["wl"].cuda()).sum() + (vo * g["wv"].cuda()).sum()).backward()
+    assert rel(lang.grad, g["dlang"]) < 3e-2 and rel(feats.grad, g["dfeats"]) < 3e-2
+    k = "x_layers.0.visual_attention.att.query.weight"          # shared block: gradient = sum of both directions
+    assert rel(dict(enc.named_parameters())[k].grad, g["grads"][k]) < 5e-2
