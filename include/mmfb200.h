@@ -157,6 +157,11 @@ int mmfb_embed_scatter_sorted(const void* dy, int64_t lddy, const int32_t* order
 /* dz = dy where y > 0 else 0 (backward of the ReLU epilogue); contiguous bf16 buffers of n elements */
 int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_stream stream);
 
+/* du = dh * GELU'(u) (erf GELU, the arithmetic of the MMFB_EPI_GELU_BWD epilogue) for a GELU that is NOT followed by a GEMM:
+ * BertPredictionHeadTransform (dense -> gelu -> LayerNorm), HF modeling_bert via mmf/models/visual_bert.py:205-214.
+ * Contiguous bf16 buffers of n elements. */
+int mmfb_gelu_bwd(const void* dh, const void* u, void* du, int64_t n, mmfb_stream stream);
+
 /* fp32 -> bf16 cast of a flat (parameter) buffer */
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream);
 

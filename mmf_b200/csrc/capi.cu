@@ -177,6 +177,11 @@ int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_strea
   MMFB_REQUIRE_DEVICE();
   return relu_bwd(dy, y, dz, n, reinterpret_cast<cudaStream_t>(stream));
 }
+int mmfb_gelu_bwd(const void* dh, const void* u, void* du, int64_t n, mmfb_stream stream) {
+  if (!dh || !u || !du) return set_error(MMFB_ERR_ARG, "mmfb_gelu_bwd: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return gelu_bwd(dh, u, du, n, reinterpret_cast<cudaStream_t>(stream));
+}
 int mmfb_adamw(const mmfb_adamw_args* args, mmfb_stream stream) {
   if (!args) return set_error(MMFB_ERR_ARG, "mmfb_adamw: null args");
   MMFB_REQUIRE_DEVICE();

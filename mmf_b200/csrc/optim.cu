@@ -92,4 +92,36 @@ int adamw(const mmfb_adamw_args& a, cudaStream_t s) {
   return MMFB_OK;
 }
 
+// du = dh * GELU'(u), 16-byte vectors (staged with the MLM head)
+__global__ void gelu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ u, bf16* __restrict__ du, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 a = *reinterpret_cast<const uint4*>(dh + i);
+    const uint4 b = *reinterpret_cast<const uint4*>(u + i);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = unpack_bf16x2(aw[k]), x = unpack_bf16x2(bw[k]);
+      ow[k] = pack_bf16x2(d.x * gelu_erf_grad(x.x), d.y * gelu_erf_grad(x.y));
+    }
+    *reinterpret_cast<uint4*>(du + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  } else {
+    for (int64_t j = i; j < n; ++j)
+      du[j] = __float2bfloat16_rn(__bfloat162float(dh[j]) * gelu_erf_grad(__bfloat162float(u[j])));
+  }
+}
+
+int gelu_bwd(const void* dh, const void* u, void* du, int64_t n, cudaStream_t s) {
+  if (n <= 0) return set_error(MMFB_ERR_ARG, "gelu_bwd: empty");
+  if ((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(du)) & 15)
+    return set_error(MMFB_ERR_ARG, "gelu_bwd: buffers must be 16-byte aligned");
+  const int64_t thr = (n + 7) / 8;
+  gelu_bwd_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)dh, (const bf16*)u, (bf16*)du, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "gelu_bwd launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return MMFB_OK;
+}
+
 }  // namespace mmfb

@@ -227,6 +227,16 @@ def relu_bwd(dy, y):
     return dz
 
 
+def gelu_bwd(dh, u):
+    """du = dh * GELU'(u) (bf16, contiguous) - for a GELU that is followed by a LayerNorm instead of a GEMM."""
+    _req(dh, torch.bfloat16, "dh"); _req(u, torch.bfloat16, "u")
+    if not (dh.is_contiguous() and u.is_contiguous()) or dh.numel() != u.numel():
+        raise ValueError("gelu_bwd: contiguous, equally sized buffers required")
+    du = torch.empty_like(dh)
+    check(LIB.mmfb_gelu_bwd(dh.data_ptr(), u.data_ptr(), du.data_ptr(), dh.numel(), _stream_ptr()))
+    return du
+
+
 def adamw(param, grad, exp_avg, exp_avg_sq, groups, *, beta1, beta2, eps, mode, grad_scale=1.0, group_of_block=None,
           param_bf16=None):
     """One fused AdamW step over flat fp32 buffers (staged, include/mmfb200.h: mmfb_adamw).

@@ -86,6 +86,41 @@ def linear_relu(x2d, weight, bias):
     return _LinearReLU.apply(x2d, weight, bias)
 
 
+class _LinearGELU(torch.autograd.Function):
+    """h = gelu(x W^T + b): GEMM with the bias + GELU epilogue (it also writes the pre-activation u, saved for the
+    backward); backward: du = dh * GELU'(u) (row kernel), then the Linear backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xb, wb, bb = _bf16(x), _bf16(weight), _bf16(bias)
+        u, h = F.gemm(xb, wb, epi=lib.EPI_BIAS_GELU, bias=bb)
+        ctx.save_for_backward(xb, wb, u)
+        ctx.dtypes = (x.dtype, weight.dtype, bias.dtype)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        xb, wb, u = ctx.saved_tensors
+        du = F.gelu_bwd(dh.to(torch.bfloat16).contiguous(), u)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = F.gemm(du, wb, b_mn=True, epi=lib.EPI_BIAS).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(wb.shape, dtype=torch.float32, device=wb.device)
+            F.gemm(du, xb, a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=dw,
+                   splits=best_splits(wb.shape[0], wb.shape[1], xb.shape[0]))
+            dw = dw.to(ctx.dtypes[1])
+        if ctx.needs_input_grad[2]:
+            db = torch.zeros(wb.shape[0], dtype=torch.float32, device=wb.device)
+            F.colsum(du, db)
+            db = db.to(ctx.dtypes[2])
+        return dx, dw, db
+
+
+def linear_gelu(x2d, weight, bias):
+    return _LinearGELU.apply(x2d, weight, bias)
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):

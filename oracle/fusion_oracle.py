@@ -503,6 +503,25 @@ def lxmert_encoder(lang, lang_mask, feats, boxes, visn_mask, sd, prefix, l_layer
 
 
 # ----------------------------------------------------------------------------------------------
+# masked-LM pre-training head
+# ----------------------------------------------------------------------------------------------
+def bert_pretraining_heads(sequence_output, pooled_output, sd, prefix):
+    """HF BertPreTrainingHeads (transformers, pinned <= 4.10), the reference's `self.cls`
+    (mmf/models/visual_bert.py:205-214): transform = LayerNorm(gelu(dense(h))), decoder = h W^T + bias (W tied to the
+    word embeddings), seq_relationship = Linear(pooled).  -> (prediction_scores, seq_relationship_score)"""
+    p = prefix + ".predictions"
+    h = layer_norm(gelu_erf(linear(sequence_output, sd, p + ".transform.dense")), sd, p + ".transform.LayerNorm")
+    scores = h @ sd[p + ".decoder.weight"].t() + sd[p + ".bias"]
+    return scores, linear(pooled_output, sd, prefix + ".seq_relationship")
+
+
+def masked_lm_loss(prediction_scores, labels, ignore_index=-1):
+    """CrossEntropyLoss(ignore_index=-1) over all positions, mmf/models/visual_bert.py:215, 269-277"""
+    V = prediction_scores.shape[-1]
+    return F.cross_entropy(prediction_scores.reshape(-1, V), labels.reshape(-1), ignore_index=ignore_index)
+
+
+# ----------------------------------------------------------------------------------------------
 # optimizer "adam_w" (SURVEY.md 8f item 2)
 # ----------------------------------------------------------------------------------------------
 def adamw_step_transformers(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay, correct_bias=True):

@@ -374,6 +374,43 @@ def golden_lxmert():
         hl.undo_replace_with_jit()
 
 
+def golden_mlm_head():
+    """`self.cls` of VisualBERTForPretraining (visual_bert.py:205-214) = HF BertPreTrainingHeads with the decoder tied to
+    the word embeddings, and the masked-LM loss (:269-277).  Third-party arithmetic (transformers): the installed
+    module is run as is; keys are stored with the reference pin's names (`predictions.bias` is the decoder bias)."""
+    from transformers import BertConfig
+    from transformers.models.bert.modeling_bert import BertPreTrainingHeads
+    cfg = BertConfig(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=1, vocab_size=203)
+    heads = BertPreTrainingHeads(cfg)
+    emb = torch.nn.Embedding(203, 64)
+    heads.predictions.decoder.weight = emb.weight
+    _perturb(heads, 95)
+    heads.eval()
+    g = torch.Generator().manual_seed(96)
+    B, S = 3, 9
+    seq = torch.randn(B, S, 64, generator=g, requires_grad=True)
+    pooled = torch.randn(B, 64, generator=g)
+    labels = torch.full((B, S), -1, dtype=torch.long)
+    labels[0, 2], labels[0, 5], labels[1, 1], labels[2, 7] = 17, 202, 0, 99
+    scores, rel_score = heads(seq, pooled)
+    loss = torch.nn.CrossEntropyLoss(ignore_index=-1)(scores.view(-1, 203), labels.view(-1))
+    loss.backward()
+    sd = {"cls.predictions.transform.dense.weight": heads.predictions.transform.dense.weight,
+          "cls.predictions.transform.dense.bias": heads.predictions.transform.dense.bias,
+          "cls.predictions.transform.LayerNorm.weight": heads.predictions.transform.LayerNorm.weight,
+          "cls.predictions.transform.LayerNorm.bias": heads.predictions.transform.LayerNorm.bias,
+          "cls.predictions.decoder.weight": heads.predictions.decoder.weight,
+          "cls.predictions.bias": heads.predictions.decoder.bias,
+          "cls.seq_relationship.weight": heads.seq_relationship.weight,
+          "cls.seq_relationship.bias": heads.seq_relationship.bias}
+    _save("mlm_head", {
+        "cfg": {"hidden": 64, "vocab": 203}, "state_dict": {k: v.detach().clone() for k, v in sd.items()},
+        "seq": seq.detach(), "pooled": pooled, "labels": labels, "scores": scores.detach(), "rel": rel_score.detach(),
+        "loss": loss.detach(), "dseq": seq.grad.detach(),
+        "grads": {k: v.grad.detach().clone() for k, v in sd.items() if v.grad is not None},
+    })
+
+
 def golden_adamw():
     """optimizer `adam_w`: 5 steps on three small parameters, two hyper-parameter groups (decay / no decay), with the
     reference's transformers arithmetic (AdamWSkipParamsWithZeroGrad.step, optimizers.py:22-86) and with what `adam_w`
@@ -411,6 +448,7 @@ def main():
     golden_adamw()
     golden_uniter()
     golden_lxmert()
+    golden_mlm_head()
 
 
 if __name__ == "__main__":

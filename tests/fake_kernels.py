@@ -228,3 +228,7 @@ def adamw(param, grad, exp_avg, exp_avg_sq, groups, *, beta1, beta2, eps, mode, 
         param.sub_(step * (exp_avg / (exp_avg_sq.sqrt() / bc2s + eps)))
     if param_bf16 is not None:
         param_bf16.copy_(param.to(BF))
+
+
+def gelu_bwd(dh, u):
+    return (dh.float() * _gelu_grad(u.float())).to(BF)

@@ -483,3 +483,39 @@ def test_lxmert_encoder_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
         if "key" in n and n.endswith("bias"):
             continue
         assert rel(p.grad, g["grads"][n]) < 8e-2, n
+
+
+def test_masked_lm_head_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
+    """vocabulary 203 (not a multiple of 8): padded compute copy of the tied decoder weight, logits = column slice;
+    loss over all positions == loss over the labelled rows only"""
+    import mmf_b200.heads as HD
+    monkeypatch.setattr(HD, "_require_cuda", lambda t, what: None)
+    g = torch.load(os.path.join(GOLD, "mlm_head.pt"), weights_only=False)
+    cfg = types.SimpleNamespace(hidden_size=g["cfg"]["hidden"], vocab_size=g["cfg"]["vocab"], layer_norm_eps=1e-12,
+                                initializer_range=0.02)
+    emb = torch.nn.Embedding(cfg.vocab_size, cfg.hidden_size)
+    cls = HD.B200BertPreTrainingHeads(cfg, emb.weight)
+    assert cls.predictions.decoder.weight is emb.weight and cls.predictions.decoder.bias is cls.predictions.bias
+    keys = set(cls.state_dict().keys())
+    assert {"predictions.bias", "predictions.decoder.bias", "predictions.decoder.weight",
+            "predictions.transform.dense.weight", "predictions.transform.LayerNorm.bias", "seq_relationship.weight"} <= keys
+    sd = {k[len("cls."):]: v for k, v in g["state_dict"].items()}
+    sd["predictions.decoder.bias"] = sd["predictions.bias"]
+    cls.load_state_dict(sd)
+    cls.eval()
+    seq = g["seq"].clone().requires_grad_(True)
+    scores, rel_score = cls(seq, g["pooled"])
+    assert scores.shape == g["scores"].shape and rel(scores, g["scores"]) < 2e-2 and rel(rel_score, g["rel"]) < 1e-5
+    loss, logits = HD.masked_lm_loss(cls, seq, g["labels"])
+    assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
+    loss.backward()
+    assert rel(seq.grad, g["dseq"]) < 5e-2
+    named = dict(cls.named_parameters())
+    for k in ("predictions.transform.dense.weight", "predictions.transform.LayerNorm.weight", "predictions.decoder.weight",
+              "predictions.bias"):
+        assert rel(named[k].grad, g["grads"]["cls." + k]) < 6e-2, k
+    assert emb.weight.grad is named["predictions.decoder.weight"].grad        # the tie: one parameter, one gradient
+    full = loss.item()
+    cls.zero_grad(set_to_none=True)
+    loss_m, logits_m = HD.masked_lm_loss(cls, seq.detach(), g["labels"], positions="masked")
+    assert logits_m.shape == (4, cfg.vocab_size) and abs(loss_m.item() - full) < 1e-3 * abs(full)

@@ -215,3 +215,34 @@ def test_lxmert_encoder_vs_reference_golden():
     assert rel(lang.grad, g["dlang"]) < 3e-2 and rel(feats.grad, g["dfeats"]) < 3e-2
     k = "x_layers.0.visual_attention.att.query.weight"          # shared block: gradient = sum of both directions
     assert rel(dict(enc.named_parameters())[k].grad, g["grads"][k]) < 5e-2
+
+
+def test_gelu_bwd_kernel_and_masked_lm_head():
+    """mmfb_gelu_bwd against the fp32 formula, then the head + loss against the HF golden"""
+    import math
+    import types
+    from mmf_b200 import functional as F
+    from mmf_b200.heads import B200BertPreTrainingHeads, masked_lm_loss
+    torch.manual_seed(0)
+    u = (torch.randn(1000, 72, device="cuda") * 2).to(torch.bfloat16)
+    dh = torch.randn(1000, 72, device="cuda").to(torch.bfloat16)
+    du = F.gelu_bwd(dh, u)
+    uf = u.float()
+    ref = dh.float() * (0.5 * (1 + torch.erf(uf / math.sqrt(2))) + uf * torch.exp(-0.5 * uf * uf) / math.sqrt(2 * math.pi))
+    assert ((du.float() - ref).norm() / ref.norm()).item() < 5e-3
+    tail = F.gelu_bwd(dh.reshape(-1)[:13].contiguous(), u.reshape(-1)[:13].contiguous())      # scalar tail path
+    assert ((tail.float() - ref.reshape(-1)[:13]).abs().max() < 2e-2)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mlm_head.pt"), weights_only=False)
+    cfg = types.SimpleNamespace(hidden_size=g["cfg"]["hidden"], vocab_size=g["cfg"]["vocab"], layer_norm_eps=1e-12,
+                                initializer_range=0.02)
+    cls = B200BertPreTrainingHeads(cfg)
+    sd = {k[len("cls."):]: v for k, v in g["state_dict"].items()}
+    sd["predictions.decoder.bias"] = sd["predictions.bias"]
+    cls.load_state_dict(sd)
+    cls = cls.cuda().eval()
+    seq = g["seq"].cuda().requires_grad_(True)
+    loss, logits = masked_lm_loss(cls, seq, g["labels"].cuda())
+    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
+    assert rel(logits, g["scores"]) < 1e-2 and abs(loss.item() - g["loss"].item()) < 1e-2 * abs(g["loss"].item())
+    loss.backward()
+    assert rel(seq.grad, g["dseq"]) < 3e-2
