@@ -13,6 +13,9 @@ _LAZY = {
     "B200VisioLinguisticEmbeddings": ("embeddings", "B200VisioLinguisticEmbeddings"),
     "B200VisualBERT": ("visual_bert", "B200VisualBERT"),
     "B200VisualBERTBase": ("visual_bert", "B200VisualBERTBase"),
+    "B200VisualBERTForPretraining": ("visual_bert", "B200VisualBERTForPretraining"),
+    "B200BertPreTrainingHeads": ("heads", "B200BertPreTrainingHeads"),
+    "B200AdamW": ("optim", "B200AdamW"),
     "B200MMBTBase": ("mmbt", "B200MMBTBase"),
     "B200MMBTModel": ("mmbt", "B200MMBTModel"),
     "B200ViLBERTBase": ("vilbert", "B200ViLBERTBase"),

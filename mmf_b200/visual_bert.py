@@ -89,3 +89,37 @@ class B200VisualBERT(nn.Module):
         seq, pooled, _ = self.bert(input_ids, attention_mask, segment_ids, feats, visual_embeddings_type)
         return {"sequence_output": seq, "pooled_output": pooled, "attention_mask": attention_mask,
                 "image_mask": image_mask}
+
+
+class B200VisualBERTForPretraining(nn.Module):
+    """VisualBERTForPretraining (visual_bert.py:160-279) on the engine: `bert` trunk + `cls` heads with the decoder tied to
+    the word embeddings (:219-228) + CrossEntropyLoss(ignore_index=-1).  STAGED with mmf_b200.heads.
+    forward returns the reference's output dict: `logits`, `masked_lm_loss`, `loss` (when labels are given), plus
+    `sequence_output` / `pooled_output` when `output_hidden_states` is set."""
+
+    def __init__(self, config, mlm_positions="all"):
+        super().__init__()
+        from .heads import B200BertPreTrainingHeads
+        self.config = config
+        self.output_hidden_states = bool(getattr(config, "output_hidden_states", False))
+        if getattr(config, "output_attentions", False):
+            raise NotImplementedError("attention probabilities are never materialised on the B200 path")
+        self.bert = B200VisualBERTBase(config)
+        self.vocab_size = config.vocab_size
+        self.cls = B200BertPreTrainingHeads(config, self.bert.embeddings.word_embeddings.weight)
+        self.mlm_positions = mlm_positions
+
+    def forward(self, input_ids, input_mask, attention_mask=None, token_type_ids=None, visual_embeddings=None,
+                visual_embeddings_type=None, image_text_alignment=None, masked_lm_labels=None):
+        from .heads import masked_lm_loss
+        sequence_output, pooled_output, _ = self.bert(input_ids, attention_mask, token_type_ids, visual_embeddings,
+                                                      visual_embeddings_type, image_text_alignment)
+        out = {}
+        if self.output_hidden_states:
+            out["sequence_output"], out["pooled_output"] = sequence_output, pooled_output
+        if masked_lm_labels is not None:
+            loss, logits = masked_lm_loss(self.cls, sequence_output, masked_lm_labels, positions=self.mlm_positions)
+            out["logits"] = logits
+            out["masked_lm_loss"] = loss
+            out["loss"] = loss
+        return out

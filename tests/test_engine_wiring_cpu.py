@@ -519,3 +519,42 @@ def test_masked_lm_head_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
     cls.zero_grad(set_to_none=True)
     loss_m, logits_m = HD.masked_lm_loss(cls, seq.detach(), g["labels"], positions="masked")
     assert logits_m.shape == (4, cfg.vocab_size) and abs(loss_m.item() - full) < 1e-3 * abs(full)
+
+
+def test_visual_bert_for_pretraining_vs_oracle_cpu(cpu_frontends, monkeypatch):
+    """visual_bert/pretrain (BASELINE.json configs[1]) end to end: trunk + tied MLM head + loss and its gradients"""
+    import mmf_b200.heads as HD
+    from mmf_b200.visual_bert import B200VisualBERTForPretraining
+    monkeypatch.setattr(HD, "_require_cuda", lambda t, what: None)
+    cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2,
+                                vocab_size=51, max_position_embeddings=64, type_vocab_size=2, visual_embedding_dim=40,
+                                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12,
+                                hidden_act="gelu", initializer_range=0.02)
+    torch.manual_seed(4)
+    model = B200VisualBERTForPretraining(cfg).eval()
+    _bf16_round_(model)
+    B, T, R = 2, 8, 4
+    ids = torch.randint(1, 51, (B, T))
+    seg = torch.zeros(B, T, dtype=torch.long)
+    feats = torch.randn(B, R, 40).abs().to(torch.bfloat16).float()
+    vtype = torch.zeros(B, R, dtype=torch.long)
+    att = torch.ones(B, T + R, dtype=torch.long)
+    att[1, 6:T] = 0
+    labels = torch.full((B, T + R), -1, dtype=torch.long)
+    labels[0, 1], labels[0, 4], labels[1, 2] = 7, 50, 19
+    out = model(ids, None, att, seg, feats, vtype, masked_lm_labels=labels)
+    assert out["logits"].shape == (B, T + R, 51) and out["loss"] is out["masked_lm_loss"]
+    out["loss"].backward()
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    sd["cls.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]        # the tie
+    emb = O.visio_linguistic_embeddings(ids, seg, feats, vtype, sd, "bert.embeddings")
+    seq = O.bert_encoder(emb, O.extended_attention_mask(att), sd, "bert.encoder", 2, 1)
+    scores, _ = O.bert_pretraining_heads(seq, O.bert_pooler(seq, sd, "bert.pooler"), sd, "cls")
+    loss = O.masked_lm_loss(scores, labels)
+    loss.backward()
+    assert abs(out["loss"].item() - loss.item()) < 2e-2 * abs(loss.item())
+    assert rel(out["logits"], scores) < 2e-2
+    named = dict(model.named_parameters())
+    for k in ("bert.embeddings.word_embeddings.weight", "bert.encoder.layer.1.output.dense.weight",
+              "cls.predictions.transform.dense.weight", "bert.embeddings.projection.weight"):
+        assert rel(named[k].grad, sd[k].grad) < 8e-2, k
