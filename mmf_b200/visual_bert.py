@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from .embeddings import B200VisioLinguisticEmbeddings
-from .modules import B200BertEncoder, _init_bert_weights
+from .modules import B200BertEncoder, B200BertLayer, EncoderRunner, _init_bert_weights, run_bert_encoder
 
 
 class BertPooler(nn.Module):
@@ -41,9 +41,17 @@ class B200VisualBERTBase(nn.Module):
         self.encoder = B200BertEncoder(config)
         self.pooler = BertPooler(config.hidden_size)
         _init_bert_weights(self.pooler, float(getattr(config, "initializer_range", 0.02)))
-        self.bypass_transformer = getattr(config, "bypass_transformer", False)
+        self.bypass_transformer = bool(getattr(config, "bypass_transformer", False))
         if self.bypass_transformer:
-            raise NotImplementedError("bypass_transformer is not implemented on the B200 path")
+            # visual_bert.py:66-67, 118-143: the encoder sees the text only; ONE extra BERT layer fuses
+            # [text output ; visual embeddings].  The layer is a parameter holder driven by its own runner
+            # (`_runner` on the module is also how mmf_b200.ddp finds the pack).
+            self.additional_layer = B200BertLayer(
+                config.hidden_size, config.num_attention_heads, config.intermediate_size,
+                float(config.attention_probs_dropout_prob), float(config.hidden_dropout_prob),
+                float(getattr(config, "layer_norm_eps", 1e-12)))
+            _init_bert_weights(self.additional_layer, float(getattr(config, "initializer_range", 0.02)))
+            self.additional_layer._runner = EncoderRunner([self.additional_layer])
 
     def forward(self, input_ids, attention_mask=None, token_type_ids=None, visual_embeddings=None,
                 visual_embeddings_type=None, image_text_alignment=None):
@@ -58,7 +66,14 @@ class B200VisualBERTBase(nn.Module):
         emb = self.embeddings(input_ids, token_type_ids, visual_embeddings=visual_embeddings,
                               visual_embeddings_type=visual_embeddings_type,
                               image_text_alignment=image_text_alignment)
-        seq = self.encoder(emb, ext)[0].to(next(self.pooler.parameters()).dtype)
+        dt = next(self.pooler.parameters()).dtype
+        if self.bypass_transformer and visual_embeddings is not None:
+            T = input_ids.size(1)
+            text_out = self.encoder(emb[:, :T], ext[:, :, :T, :T])[0]        # [B,1,1,S] sliced -> [B,1,1,T]
+            new_input = torch.cat((text_out.to(emb.dtype), emb[:, T:]), dim=1)
+            seq = run_bert_encoder(self.additional_layer._runner, new_input, ext, self.training)[0].to(dt)
+            return seq, self.pooler(seq), []
+        seq = self.encoder(emb, ext)[0].to(dt)
         return seq, self.pooler(seq), []
 
 

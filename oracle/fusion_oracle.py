@@ -272,6 +272,22 @@ def embedding(table, ids, padding_idx=None):
     return torch.where((ids == padding_idx).unsqueeze(-1), out.detach(), out)
 
 
+def visual_bert_base(input_ids, attention_mask, token_type_ids, visual_embeddings, visual_embeddings_type, sd, num_layers,
+                     heads, bypass_transformer=False, image_text_alignment=None):
+    """VisualBERTBase.forward, mmf/models/visual_bert.py:74-157 -> (sequence_output, pooled_output).
+    bypass_transformer (:118-143): encoder over the text part only, then `additional_layer` over [text ; visual]."""
+    add = extended_attention_mask(attention_mask)
+    emb = visio_linguistic_embeddings(input_ids, token_type_ids, visual_embeddings, visual_embeddings_type, sd, "embeddings",
+                                      image_text_alignment)
+    if bypass_transformer and visual_embeddings is not None:
+        T = input_ids.shape[1]
+        text = bert_encoder(emb[:, :T], add[:, :, :T, :T], sd, "encoder", num_layers, heads)
+        seq, _ = bert_layer(torch.cat((text, emb[:, T:]), dim=1), add, sd, "additional_layer", heads)
+    else:
+        seq = bert_encoder(emb, add, sd, "encoder", num_layers, heads)
+    return seq, bert_pooler(seq, sd, "pooler")
+
+
 def bert_embeddings(input_ids, token_type_ids, sd, prefix, position_ids=None, keep=None, p=0.0, padding_idx=0):
     """BertEmbeddingsJit.forward, mmf/modules/hf_layers.py:107-135."""
     B, T = input_ids.shape

@@ -411,6 +411,44 @@ def golden_mlm_head():
     })
 
 
+def golden_visual_bert_bypass():
+    """VisualBERTBase.forward with bypass_transformer=True (visual_bert.py:118-143): the encoder sees the text only, one
+    `additional_layer` fuses [text output; visual embeddings].  Also the plain path of the same class for reference."""
+    from transformers import BertConfig
+    vb = R.visual_bert()
+    orig = vb.VisualBERTBase.init_weights
+    vb.VisualBERTBase.init_weights = lambda self: None            # see ref_loader.visual_bert()
+    try:
+        cfg = BertConfig(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2, vocab_size=51,
+                         max_position_embeddings=64, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        m = vb.VisualBERTBase(cfg, visual_embedding_dim=40, bypass_transformer=True).eval()
+    finally:
+        vb.VisualBERTBase.init_weights = orig
+    _perturb(m, 97)
+    g = torch.Generator().manual_seed(98)
+    B, T, Rr = 3, 8, 4
+    ids = torch.randint(1, 51, (B, T), generator=g)
+    seg = torch.zeros(B, T, dtype=torch.long)
+    feats = torch.randn(B, Rr, 40, generator=g, requires_grad=True)
+    vtype = torch.zeros(B, Rr, dtype=torch.long)
+    att = torch.ones(B, T + Rr, dtype=torch.long)
+    att[1, 5:T] = 0
+    att[2, T + 2:] = 0
+    seq, pooled, _ = m(ids, att, seg, feats, vtype)
+    w = torch.randn(seq.shape, generator=g)
+    (seq * w).sum().backward()
+    names = [n for n, _ in m.named_parameters()]
+    m.bypass_transformer = False
+    plain_seq, plain_pooled, _ = m(ids, att, seg, feats.detach(), vtype)
+    _save("visual_bert_bypass", {
+        "cfg": {"hidden": 64, "heads": 1, "inter": 128, "layers": 2, "vocab": 51, "max_pos": 64, "vdim": 40},
+        "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+        "ids": ids, "seg": seg, "feats": feats.detach(), "vtype": vtype, "att": att, "seq": seq.detach(),
+        "pooled": pooled.detach(), "w_rand": w, "dfeats": feats.grad.detach(), "grads": _grads(m, names),
+        "plain_seq": plain_seq.detach(), "plain_pooled": plain_pooled.detach(),
+    })
+
+
 def golden_adamw():
     """optimizer `adam_w`: 5 steps on three small parameters, two hyper-parameter groups (decay / no decay), with the
     reference's transformers arithmetic (AdamWSkipParamsWithZeroGrad.step, optimizers.py:22-86) and with what `adam_w`
@@ -449,6 +487,7 @@ def main():
     golden_uniter()
     golden_lxmert()
     golden_mlm_head()
+    golden_visual_bert_bypass()
 
 
 if __name__ == "__main__":

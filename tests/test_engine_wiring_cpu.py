@@ -558,3 +558,33 @@ def test_visual_bert_for_pretraining_vs_oracle_cpu(cpu_frontends, monkeypatch):
     for k in ("bert.embeddings.word_embeddings.weight", "bert.encoder.layer.1.output.dense.weight",
               "cls.predictions.transform.dense.weight", "bert.embeddings.projection.weight"):
         assert rel(named[k].grad, sd[k].grad) < 8e-2, k
+
+
+def test_visual_bert_bypass_transformer_vs_reference_golden_cpu(cpu_frontends):
+    from mmf_b200.visual_bert import B200VisualBERTBase
+    g = torch.load(os.path.join(GOLD, "visual_bert_bypass.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                type_vocab_size=2, visual_embedding_dim=c["vdim"], hidden_dropout_prob=0.0,
+                                attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12, hidden_act="gelu",
+                                initializer_range=0.02, bypass_transformer=True)
+    m = B200VisualBERTBase(cfg)
+    ref_keys = {k for k in g["state_dict"] if not k.endswith("position_ids") and not k.endswith("token_type_ids")}
+    assert set(m.state_dict().keys()) == ref_keys
+    m.load_state_dict({k: v for k, v in g["state_dict"].items() if k in ref_keys})
+    m.eval()
+    feats = g["feats"].clone().requires_grad_(True)
+    seq, pooled, _ = m(g["ids"], g["att"], g["seg"], feats, g["vtype"])
+    assert rel(seq, g["seq"]) < 2e-2 and rel(pooled, g["pooled"]) < 2e-2
+    (seq * g["w_rand"]).sum().backward()
+    assert rel(feats.grad, g["dfeats"]) < 4e-2
+    named = dict(m.named_parameters())
+    for k in ("additional_layer.attention.self.query.weight", "additional_layer.output.dense.weight",
+              "encoder.layer.1.intermediate.dense.weight", "embeddings.projection.weight",
+              "embeddings.word_embeddings.weight"):
+        assert rel(named[k].grad, g["grads"][k]) < 6e-2, k
+    m.bypass_transformer = False
+    with torch.no_grad():
+        ps, pp, _ = m(g["ids"], g["att"], g["seg"], g["feats"], g["vtype"])
+    assert rel(ps, g["plain_seq"]) < 2e-2 and rel(pp, g["plain_pooled"]) < 2e-2

@@ -246,3 +246,24 @@ def test_gelu_bwd_kernel_and_masked_lm_head():
     assert rel(logits, g["scores"]) < 1e-2 and abs(loss.item() - g["loss"].item()) < 1e-2 * abs(g["loss"].item())
     loss.backward()
     assert rel(seq.grad, g["dseq"]) < 3e-2
+
+
+def test_visual_bert_bypass_transformer_vs_reference_golden():
+    import types
+    from mmf_b200.visual_bert import B200VisualBERTBase
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "visual_bert_bypass.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                type_vocab_size=2, visual_embedding_dim=c["vdim"], hidden_dropout_prob=0.0,
+                                attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12, hidden_act="gelu",
+                                initializer_range=0.02, bypass_transformer=True)
+    m = B200VisualBERTBase(cfg)
+    m.load_state_dict({k: v for k, v in g["state_dict"].items() if k in m.state_dict()})
+    m = m.cuda().eval()
+    feats = g["feats"].cuda().requires_grad_(True)
+    seq, pooled, _ = m(g["ids"].cuda(), g["att"].cuda(), g["seg"].cuda(), feats, g["vtype"].cuda())
+    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
+    assert rel(seq, g["seq"]) < 1e-2 and rel(pooled, g["pooled"]) < 1e-2
+    (seq * g["w_rand"].cuda()).sum().backward()
+    assert rel(feats.grad, g["dfeats"]) < 3e-2
