@@ -56,6 +56,18 @@ class B200BertTextEmbeddings(_BertEmbeddingsHolder):
         return y.view(B, T, H)
 
 
+class _FirstTokenPooler(nn.Module):
+    """relu(dense(h[:, 0])) - consumer of the trunk output, plain torch"""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.dense = nn.Linear(in_features, out_features)
+        self.activation = nn.ReLU()
+
+    def forward(self, hidden_states):
+        return self.activation(self.dense(hidden_states[:, 0]))
+
+
 class B200ViLBERTBase(nn.Module):
     """ViLBERTBase.forward (vilbert.py:936-1051) up to the encoder outputs; poolers / heads are torch consumers."""
 
@@ -65,12 +77,17 @@ class B200ViLBERTBase(nn.Module):
         self.embeddings = B200BertTextEmbeddings(config)
         self.v_embeddings = B200ImageFeatureEmbeddings(config)
         self.encoder = B200ViLBertEncoder(config)
-        _init_bert_weights(self.embeddings, float(getattr(config, "initializer_range", 0.02)))
-        _init_bert_weights(self.v_embeddings, float(getattr(config, "initializer_range", 0.02)))
+        self.t_pooler = _FirstTokenPooler(config.hidden_size, config.bi_hidden_size)        # BertTextPooler  vilbert.py:798-811
+        self.v_pooler = _FirstTokenPooler(config.v_hidden_size, config.bi_hidden_size)      # BertImagePooler vilbert.py:814-827
+        for m in (self.embeddings, self.v_embeddings, self.t_pooler, self.v_pooler):
+            _init_bert_weights(m, float(getattr(config, "initializer_range", 0.02)))
 
     def forward(self, input_txt, image_feature, image_location, token_type_ids=None, attention_mask=None,
                 image_attention_mask=None, co_attention_mask=None, task_ids=None, output_all_encoded_layers=False,
-                output_all_attention_masks=False):
+                output_all_attention_masks=False, reference_outputs=False):
+        """-> (sequence_output_t, sequence_output_v, attention maps) by default; with reference_outputs=True the
+        reference's 7-tuple (vilbert.py:1035-1051): (sequence_output_t, sequence_output_v, pooled_output_t,
+        pooled_output_v, all_attention_mask, encoded_layers_t, encoded_layers_v) with the poolers applied."""
         if attention_mask is None:
             attention_mask = torch.ones_like(input_txt)
         if token_type_ids is None:
@@ -85,4 +102,8 @@ class B200ViLBERTBase(nn.Module):
         t_layers, v_layers, attn = self.encoder(emb, v_emb, ext_t, ext_t, ext_v, co_attention_mask,
                                                 output_all_encoded_layers=output_all_encoded_layers,
                                                 output_all_attention_masks=output_all_attention_masks)
-        return t_layers[-1].to(dt), v_layers[-1].to(dt), attn
+        seq_t, seq_v = t_layers[-1].to(dt), v_layers[-1].to(dt)
+        if reference_outputs:
+            return (seq_t, seq_v, self.t_pooler(seq_t), self.v_pooler(seq_v), attn if output_all_attention_masks else None,
+                    t_layers if output_all_encoded_layers else None, v_layers if output_all_encoded_layers else None)
+        return seq_t, seq_v, attn

@@ -588,3 +588,37 @@ def test_visual_bert_bypass_transformer_vs_reference_golden_cpu(cpu_frontends):
     with torch.no_grad():
         ps, pp, _ = m(g["ids"], g["att"], g["seg"], g["feats"], g["vtype"])
     assert rel(ps, g["plain_seq"]) < 2e-2 and rel(pp, g["plain_pooled"]) < 2e-2
+
+
+def test_vilbert_base_front_to_back_vs_oracle_cpu(cpu_frontends):
+    """ids / region features / locations -> text + image embeddings -> two-stream encoder -> poolers"""
+    c = dict(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2, vocab_size=50,
+             max_position_embeddings=32, type_vocab_size=2, v_feature_size=40, v_hidden_size=128, v_num_attention_heads=2,
+             v_intermediate_size=128, v_num_hidden_layers=1, bi_hidden_size=128, bi_num_attention_heads=2,
+             v_biattention_id=[0], t_biattention_id=[1])
+    cfg = types.SimpleNamespace(hidden_dropout_prob=0.0, v_hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                v_attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12, initializer_range=0.02, **c)
+    torch.manual_seed(6)
+    m = cpu_frontends.VB.B200ViLBERTBase(cfg).eval()
+    _bf16_round_(m)
+    B, T, R = 2, 7, 5
+    ids = torch.randint(1, 50, (B, T))
+    feats = torch.randn(B, R, 40).to(torch.bfloat16).float()
+    loc = torch.rand(B, R, 5).to(torch.bfloat16).float()
+    tmask = torch.ones(B, T, dtype=torch.long)
+    tmask[0, 5:] = 0
+    imask = torch.ones(B, R, dtype=torch.long)
+    imask[1, 3:] = 0
+    out = m(ids, feats, loc, attention_mask=tmask, image_attention_mask=imask, reference_outputs=True)
+    assert len(out) == 7 and out[4] is None and out[5] is None
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    temb = O.bert_embeddings(ids, torch.zeros_like(ids), sd, "embeddings")
+    vemb = O.image_feature_embeddings(feats, loc, sd, "v_embeddings")
+    t_out, v_out = O.vilbert_encoder(temb, vemb, O.extended_attention_mask(tmask), O.extended_attention_mask(imask),
+                                     {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, "", c)
+    assert rel(out[0], t_out) < 2e-2 and rel(out[1], v_out) < 2e-2
+    pt = torch.relu(t_out[:, 0] @ sd["t_pooler.dense.weight"].t() + sd["t_pooler.dense.bias"])
+    pv = torch.relu(v_out[:, 0] @ sd["v_pooler.dense.weight"].t() + sd["v_pooler.dense.bias"])
+    assert rel(out[2], pt) < 3e-2 and rel(out[3], pv) < 3e-2
+    seq_t, seq_v, _ = m(ids, feats, loc, attention_mask=tmask, image_attention_mask=imask)      # default: trunk outputs only
+    assert torch.equal(seq_t, out[0]) and torch.equal(seq_v, out[1])
