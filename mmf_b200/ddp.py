@@ -64,6 +64,13 @@ class B200DataParallel(nn.Module):
             self._queue_finalize()
             pack = runner.pack
             st = self._state.setdefault(id(runner), {"hi": None})
+            if st.get("deferred") or self._must_defer(pack):
+                # some parameter's .grad is (or will be) a tensor of its own - a weight tied to a torch-side head whose
+                # gradient autograd installed first, or a bf16 pack whose .grad are cast copies: the flat slices are not
+                # what the optimizer reads, and autograd may still be reading them on the main stream.  Reduce this
+                # pack after the backward instead (_finalize).
+                st["deferred"] = True
+                return
             if pack.on_reentry is None:
                 pack.on_reentry = lambda: self._reenter(runner)
             if st["hi"] is None:
@@ -74,6 +81,17 @@ class B200DataParallel(nn.Module):
                 self._all_reduce(pack.grad[lo:st["hi"]])
                 st["hi"] = lo
         return hook
+
+    @staticmethod
+    def _aliases(pack, i):
+        g = pack.params[i].grad
+        return g is not None and g.dtype == torch.float32 and g.data_ptr() == pack._gptrs[i]
+
+    @classmethod
+    def _must_defer(cls, pack):
+        if pack.dtype != torch.float32:
+            return True
+        return any(p.grad is not None and not cls._aliases(pack, i) for i, p in enumerate(pack.params))
 
     def _reenter(self, runner):
         """The runner backs a second autograd node of the SAME backward pass (module applied twice in the graph): its
@@ -144,7 +162,11 @@ class B200DataParallel(nn.Module):
         if self._sync and self.world > 1:
             for r in _runners(self.module):
                 st = self._state.get(id(r))
-                if st is not None and st["hi"] not in (None, 0):
+                if st is not None and st.get("deferred"):
+                    if r.pack.dtype == torch.float32:
+                        self._all_reduce(r.pack.grad)          # the aliased parameters of the pack; the others go below
+                    st["deferred"] = False
+                elif st is not None and st["hi"] not in (None, 0):
                     self._all_reduce(r.pack.grad[0:st["hi"]])
                 if st is not None:
                     st["hi"] = None
@@ -154,10 +176,12 @@ class B200DataParallel(nn.Module):
                 self._pending = []
 
     def _reduce_loose_params(self):
+        # a packed parameter counts as reduced only if its .grad IS its slice of the flat buffer; anything else (tied to a
+        # torch-side head, bf16 cast copies, a grad installed by another node) is reduced here like an unpacked one
         packed = set()
         for r in _runners(self.module):
             if r.pack is not None:
-                packed.update(id(p) for p in r.pack.params)
+                packed.update(id(p) for i, p in enumerate(r.pack.params) if self._aliases(r.pack, i))
         loose = [p for p in self.module.parameters() if id(p) not in packed and p.grad is not None]
         if not loose:
             return
@@ -184,7 +208,7 @@ class B200DataParallel(nn.Module):
         if self.world == 1:
             return
         for r in _runners(self.module):
-            if r.pack is not None:
+            if r.pack is not None and r.pack.dtype == torch.float32:
                 self._avg(r.pack.grad)
         self._reduce_loose_params()
 

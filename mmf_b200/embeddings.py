@@ -24,6 +24,7 @@ class _EmbedRunner:
         self.tables, self.others = list(tables), list(others)
         self.pack = None
         self.grad_ready_hook = None
+        self.eps = F.LN_EPS       # set by the owning module from its LayerNorm holder
 
     def ensure(self, device):
         if self.pack is not None and self.pack.intact() and self.pack.device == device:
@@ -69,7 +70,7 @@ class _VLEmbedFn(torch.autograd.Function):
         bits, scale = (None, 1.0)
         if training and p_drop > 0.0:
             bits, scale = _fresh_dropout_state().bits((M,), H, p_drop, pk.device), 1.0 / (1.0 - p_drop)
-        x, mean, rstd = F.layernorm_fwd(y, ln_g.w, ln_b.w, drop_mask=bits, drop_scale=scale)
+        x, mean, rstd = F.layernorm_fwd(y, ln_g.w, ln_b.w, runner.eps, drop_mask=bits, drop_scale=scale)
         ctx.runner, ctx.idx, ctx.dims = runner, idx, dims
         ctx.saved = (fb, y, mean, rstd, bits, scale)
         ctx.feats_dtype = feats.dtype if feats is not None else None
@@ -136,6 +137,7 @@ class B200VisioLinguisticEmbeddings(nn.Module):
             [self.word_embeddings.weight, self.position_embeddings.weight, self.token_type_embeddings.weight,
              self.token_type_embeddings_visual.weight, self.position_embeddings_visual.weight],
             [self.projection.weight, self.projection.bias, self.LayerNorm.weight, self.LayerNorm.bias])
+        self._runner.eps = float(self.LayerNorm.eps)
 
     def initialize_visual_from_pretrained(self):
         """embeddings.py:320-327"""

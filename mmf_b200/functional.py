@@ -23,6 +23,12 @@ def _req(t, dtype, name):
         raise ValueError("%s must be contiguous in its last dimension" % name)
 
 
+def _idx_len(idx, M, name):
+    """the kernels read one index per output row and never check: a short index buffer is an out-of-bounds device read"""
+    if idx.numel() != M or not idx.is_contiguous():
+        raise ValueError("%s must be a contiguous vector of %d indices (one per row), got shape %s" % (name, M, tuple(idx.shape)))
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=lib.EPI_BIAS, bias=None, aux=None, drop_mask=None,
          drop_scale=1.0, out=None, out2=None, splits=1, block_n=0, cluster=0):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T) on the tcgen05 GEMM.
@@ -280,10 +286,12 @@ def embed_compose(M, H, srcs=(), tabs=(), device=None):
     keep = []
     for k, (t, rows) in enumerate(srcs):
         _req(t, torch.bfloat16, "src%d" % k); _req(rows, torch.int32, "src_row%d" % k)
+        _idx_len(rows, M, "src_row%d" % k)
         a.src[k], a.ldsrc[k], a.src_row[k] = t.data_ptr(), t.stride(0), rows.data_ptr()
         device = t.device
     for k, (t, idx) in enumerate(tabs):
         _req(t, torch.bfloat16, "tab%d" % k); _req(idx, torch.int32, "tab_idx%d" % k)
+        _idx_len(idx, M, "tab_idx%d" % k)
         if t.shape[1] != H or not t.is_contiguous():
             raise ValueError("embedding table %d must be contiguous [V, %d]" % (k, H))
         a.tab[k], a.tab_idx[k] = t.data_ptr(), idx.data_ptr()
@@ -302,9 +310,11 @@ def embed_scatter(dy, dsrcs=(), dtabs=()):
     a = ScatterArgs()
     for k, (t, rows) in enumerate(dsrcs):
         _req(t, torch.bfloat16, "dsrc%d" % k)
+        _idx_len(rows, M, "src_row%d" % k)
         a.dsrc[k], a.ldsrc[k], a.src_row[k] = t.data_ptr(), t.stride(0), rows.data_ptr()
     for k, (t, idx) in enumerate(dtabs):
         _req(t, torch.float32, "dtab%d" % k)
+        _idx_len(idx, M, "tab_idx%d" % k)
         a.dtab[k], a.tab_idx[k] = t.data_ptr(), idx.data_ptr()
     a.dy, a.lddy, a.M, a.H = dy.data_ptr(), dy.stride(0), M, H
     check(LIB.mmfb_embed_scatter(ctypes.byref(a), _stream_ptr()))
@@ -321,6 +331,7 @@ def embed_scatter_sorted(dy, dtab, sorted_idx, order):
     _req(dy, torch.bfloat16, "dy"); _req(dtab, torch.float32, "dtab")
     _req(sorted_idx, torch.int32, "sorted_idx"); _req(order, torch.int32, "order")
     M, H = dy.shape
+    _idx_len(sorted_idx, M, "sorted_idx"); _idx_len(order, M, "order")
     check(LIB.mmfb_embed_scatter_sorted(dy.data_ptr(), dy.stride(0), order.data_ptr(), sorted_idx.data_ptr(),
                                         dtab.data_ptr(), M, H, _stream_ptr()))
 

@@ -81,6 +81,10 @@ def masked_lm_loss(cls, sequence_output, masked_lm_labels, ignore_index=-1, posi
     H = sequence_output.shape[-1]
     if positions == "masked":
         idx = torch.nonzero(labels != ignore_index, as_tuple=False).squeeze(1)
+        if idx.numel() == 0:
+            # no labelled position in the batch: the reference's mean over zero targets is NaN and training goes on; the
+            # GEMM rejects an empty problem, so hand back a zero loss that still connects to the graph
+            return sequence_output.sum() * 0.0, sequence_output.new_zeros(0, cls.predictions.decoder.weight.shape[0])
         logits = cls.predictions(sequence_output.reshape(-1, H).index_select(0, idx))
         loss = nn.functional.cross_entropy(logits.float(), labels.index_select(0, idx), ignore_index=ignore_index)
         return loss, logits

@@ -29,6 +29,24 @@ def _require_cuda(t, what):
         raise RuntimeError("libmmfb200 needs an sm_100 (B200) device: " + lib.last_error())
 
 
+def _check_erf_gelu(layer):
+    """The FFN epilogue IS the exact erf GELU of the reference configs (ACT2FN["gelu"]); an attached HuggingFace layer
+    with any other activation (gelu_new, relu, swish ...) must not be rerouted silently."""
+    fn = getattr(getattr(layer, "intermediate", None), "intermediate_act_fn", None)
+    if fn is None:
+        return
+    name = getattr(fn, "__name__", None) or type(fn).__name__
+    if name.lower() in ("gelu", "geluactivation"):
+        return
+    probe = torch.tensor([-1.5, -0.3, 0.7, 2.0])
+    try:
+        ok = torch.allclose(fn(probe), torch.nn.functional.gelu(probe), atol=1e-6)
+    except Exception:
+        ok = False
+    if not ok:
+        raise NotImplementedError("the B200 fusion block implements the erf GELU only; this encoder uses %s" % name)
+
+
 _SEED_COUNTER = [0]
 
 
@@ -73,6 +91,7 @@ class EncoderRunner:
             return
         params = []
         for m in self.layers:
+            _check_erf_gelu(m)
             params += E.BertLayerW.params(m)
         for p in params:
             _require_cuda(p, "encoder parameter")

@@ -44,9 +44,13 @@ class B200BertTextEmbeddings(_BertEmbeddingsHolder):
         B, T = input_ids.shape
         dev = input_ids.device
         if position_ids is None:
-            position_ids = torch.arange(T, device=dev).unsqueeze(0).expand(B, T)
+            position_ids = torch.arange(T, device=dev).unsqueeze(0)
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
+        # HF BertEmbeddings broadcasts [1, T] ids over the batch (UNITER passes arange(T).unsqueeze(0), uniter.py:732-737):
+        # the composer wants one index per output row
+        position_ids = position_ids.expand(B, T)
+        token_type_ids = token_type_ids.expand(B, T)
         H = self.LayerNorm.weight.shape[0]
         y = ops.compose_ln(B * T, H, [], [(self.word_embeddings.weight, ops.i32(input_ids), self.word_embeddings.padding_idx),
                                           (self.position_embeddings.weight, ops.i32(position_ids)),
@@ -88,6 +92,13 @@ class B200ViLBERTBase(nn.Module):
         """-> (sequence_output_t, sequence_output_v, attention maps) by default; with reference_outputs=True the
         reference's 7-tuple (vilbert.py:1035-1051): (sequence_output_t, sequence_output_v, pooled_output_t,
         pooled_output_v, all_attention_mask, encoded_layers_t, encoded_layers_v) with the poolers applied."""
+        if getattr(self.config, "task_specific_tokens", False) or task_ids is not None:
+            # the reference prepends a mask column and adds a task embedding (vilbert.py:966-969): not built here
+            raise NotImplementedError("ViLBERT task_specific_tokens / task_ids are not implemented on the B200 path")
+        if output_all_encoded_layers and reference_outputs:
+            # the reference's sequence_output_t/v would then be the state after the LAST CO-ATTENTION block, not the final
+            # state (vilbert.py:1030-1033 with the encoder's per-block lists): refuse instead of silently differing
+            raise NotImplementedError("output_all_encoded_layers=True with reference_outputs is not implemented")
         if attention_mask is None:
             attention_mask = torch.ones_like(input_txt)
         if token_type_ids is None:

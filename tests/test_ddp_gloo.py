@@ -149,3 +149,77 @@ def test_data_parallel_step_end_to_end_world2():
     result = mgr.dict()
     mp.spawn(_e2e_worker, args=(2, port, result), nprocs=2, join=True)
     assert result.get(0) and result.get(1)
+
+
+def _tied_bf16_worker(rank, world, port, result):
+    """ADVICE r1 (ddp.py:157): a packed parameter whose .grad is NOT its slice of the flat buffer must still be averaged.
+    (a) a weight of the pack is also used by a torch-side head (the tied MLM decoder case): autograd installs the
+    head's gradient first and adds the flat view into that separate tensor; (b) a bf16 pack hands autograd cast copies."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_kernels as FK
+        import mmf_b200.engine as E
+        import mmf_b200.modules as M
+        from mmf_b200.ddp import B200DataParallel
+        E.F = FK
+        M._require_cuda = lambda t, what: None
+        cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2,
+                                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12)
+        g = torch.Generator().manual_seed(11)
+        xs = [torch.randn(2, 5, 64, generator=g) for _ in range(world)]
+        ws = [torch.randn(2, 5, 64, generator=g) for _ in range(world)]
+        zs = [torch.randn(3, 128, generator=g) for _ in range(world)]
+
+        def loss_of(enc, r):
+            tied = enc.layer[0].output.dense.weight                     # [64, 128], lives in the encoder's pack
+            head = torch.nn.functional.linear(zs[r], tied).square().sum()
+            return (enc(xs[r], None)[0] * ws[r]).sum() + head
+
+        for dtype, tol in ((torch.float32, 1e-3), (torch.bfloat16, 3e-2)):
+            torch.manual_seed(200 + rank)
+            enc = M.B200BertEncoder(cfg).eval().to(dtype)
+            ddp = B200DataParallel(enc, bucket_bytes=1, overlap=False)
+            zs_ = zs
+            if dtype == torch.bfloat16:
+                zs_ = [z.to(dtype) for z in zs]
+
+            def loss_dd(r):
+                tied = enc.layer[0].output.dense.weight
+                head = torch.nn.functional.linear(zs_[r], tied).float().square().sum()
+                return (ddp(xs[r].to(dtype), None)[0].float() * ws[r]).sum() + head
+            loss_dd(rank).backward()
+            got = {k: p.grad.detach().float().clone() for k, p in enc.named_parameters()}
+            ref_enc = M.B200BertEncoder(cfg).eval().to(dtype)
+            ref_enc.load_state_dict(enc.state_dict())
+            acc = None
+            for r in range(world):
+                ref_enc.zero_grad(set_to_none=True)
+                tied = ref_enc.layer[0].output.dense.weight
+                head = torch.nn.functional.linear(zs_[r], tied).float().square().sum()
+                ((ref_enc(xs[r].to(dtype), None)[0].float() * ws[r]).sum() + head).backward()
+                cur = {k: p.grad.detach().float().clone() for k, p in ref_enc.named_parameters()}
+                acc = cur if acc is None else {k: acc[k] + cur[k] for k in acc}
+            for k in got:
+                ref = acc[k] / world
+                err = (got[k] - ref).norm() / ref.norm().clamp_min(1e-3 * ref.numel() ** 0.5)
+                assert err < tol, (str(dtype), k, float(err))
+            # every rank holds the same gradients afterwards
+            flat = torch.cat([v.reshape(-1) for v in got.values()])
+            both = [torch.zeros_like(flat) for _ in range(world)]
+            dist.all_gather(both, flat)
+            assert torch.equal(both[0], both[1]), str(dtype)
+        result[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_tied_and_bf16_pack_world2():
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_tied_bf16_worker, args=(2, port, result), nprocs=2, join=True)
+    assert result.get(0) and result.get(1)

@@ -457,6 +457,10 @@ def test_uniter_model_base_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
         T = g["ids"].shape[1]
         img_only = m(g["ids"], g["pos_ids"], g["feat"], g["pos"], g["att"][:, T:], input_modality="image").final_layer
         assert rel(img_only, g["final_image_only"]) < 2e-2
+        # the reference passes position ids as [1, T] (uniter.py:732-737) and HF broadcasts them over the batch
+        assert g["ids"].shape[0] > 1 and torch.equal(g["pos_ids"], g["pos_ids"][:1].expand_as(g["pos_ids"]))
+        bc = m(g["ids"], g["pos_ids"][:1], g["feat"], g["pos"], g["att"]).final_layer
+        assert torch.equal(bc, m(g["ids"], g["pos_ids"], g["feat"], g["pos"], g["att"]).final_layer)
 
 
 def test_lxmert_encoder_vs_reference_golden_cpu(cpu_frontends, monkeypatch):

@@ -190,6 +190,9 @@ def test_uniter_model_base_vs_reference_golden():
     assert rel(out.final_layer, g["final"]) < 1e-2 and rel(out.hidden_layers[1], g["hidden_1"]) < 1e-2
     (out.final_layer * cu("w_rand")).sum().backward()
     assert rel(feat.grad, g["dfeat"]) < 3e-2
+    with torch.no_grad():      # [1, T] position ids broadcast over the batch like HF BertEmbeddings (uniter.py:732-737)
+        bc = m(cu("ids"), cu("pos_ids")[:1], cu("feat"), cu("pos"), cu("att")).final_layer
+        assert torch.equal(bc, m(cu("ids"), cu("pos_ids"), cu("feat"), cu("pos"), cu("att")).final_layer)
 
 
 def test_lxmert_encoder_vs_reference_golden():
