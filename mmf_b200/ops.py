@@ -205,3 +205,20 @@ def compose_ln(M, H, srcs, tabs, ln_weight, ln_bias, eps=1e-12, p=0.0, training=
 
 def i32(t):
     return t.reshape(-1).to(torch.int32).contiguous()
+
+
+def linear_any(x2d, weight, bias=None):
+    """`linear` for arbitrary out/in feature counts: the GEMM wants N and K in multiples of 8 (16-byte TMA row pitch), so a
+    classifier with 2 labels or a 5-column location input gets zero-padded operands and a sliced result; autograd's
+    pad / slice backward routes the gradients.  No-op wrapper when the sizes already fit."""
+    N, K = weight.shape
+    pn, pk = (-N) % 8, (-K) % 8
+    if pk:
+        x2d = torch.nn.functional.pad(x2d, (0, pk))
+        weight = torch.nn.functional.pad(weight, (0, pk))
+    if pn:
+        weight = torch.nn.functional.pad(weight, (0, 0, 0, pn))
+        if bias is not None:
+            bias = torch.nn.functional.pad(bias, (0, pn))
+    y = linear(x2d, weight, bias)
+    return y[:, :N] if pn else y

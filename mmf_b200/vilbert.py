@@ -61,7 +61,7 @@ class B200BertTextEmbeddings(_BertEmbeddingsHolder):
 
 
 class _FirstTokenPooler(nn.Module):
-    """relu(dense(h[:, 0])) - consumer of the trunk output, plain torch"""
+    """relu(dense(h[:, 0])): GEMM with the ReLU epilogue on the first-token rows"""
 
     def __init__(self, in_features, out_features):
         super().__init__()
@@ -69,7 +69,7 @@ class _FirstTokenPooler(nn.Module):
         self.activation = nn.ReLU()
 
     def forward(self, hidden_states):
-        return self.activation(self.dense(hidden_states[:, 0]))
+        return ops.linear_relu(hidden_states[:, 0], self.dense.weight, self.dense.bias).to(self.dense.weight.dtype)
 
 
 class B200ViLBERTBase(nn.Module):

@@ -15,7 +15,8 @@ from .modules import B200BertEncoder, B200BertLayer, EncoderRunner, _init_bert_w
 
 
 class BertPooler(nn.Module):
-    """HF BertPooler: tanh(dense(h[:, 0])) - consumer of the trunk output, plain torch (visual_bert.py:146)."""
+    """HF BertPooler: tanh(dense(h[:, 0])) (visual_bert.py:146): the [B, H] x [H, H]^T product on the tcgen05 GEMM, tanh as
+    a torch elementwise op on the [B, H] result."""
 
     def __init__(self, hidden):
         super().__init__()
@@ -23,7 +24,9 @@ class BertPooler(nn.Module):
         self.activation = nn.Tanh()
 
     def forward(self, hidden_states):
-        return self.activation(self.dense(hidden_states[:, 0]))
+        from . import ops
+        first = hidden_states[:, 0]
+        return self.activation(ops.linear_any(first, self.dense.weight, self.dense.bias).to(self.dense.weight.dtype))
 
 
 def image_mask_from_dims(max_features, num_regions):

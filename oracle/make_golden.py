@@ -474,6 +474,136 @@ def golden_adamw():
                     "adam_w_is": opt.AdamW.__module__})
 
 
+class _OmegaConfShim:
+    """the two OmegaConf calls the reference's model classes make on this path (visual_bert.py:171-173, vilbert.py:1061-1063)"""
+
+    @staticmethod
+    def to_container(cfg, resolve=True):
+        return dict(cfg)
+
+
+def _new_base_model(cls, cfg):
+    """BaseModel is lightning-backed in the reference (not importable here): build the registered model class around a
+    plain nn.Module base - its build() / forward() are the reference's own."""
+    m = cls.__new__(cls)
+    torch.nn.Module.__init__(m)
+    m.config = cfg
+    return m
+
+
+def _ref_model_modules():
+    R._install()
+    R.load("mmf/utils/transform.py", "mmf.utils.transform")
+    R.load("mmf/utils/torchscript.py", "mmf.utils.torchscript")
+    vb, vil = R.visual_bert(), R.vilbert()
+    for mod in (vb, vil):
+        mod.OmegaConf = _OmegaConfShim
+        mod.get_mmf_cache_dir = lambda: "/tmp"
+    vb.VisualBERTBase.init_weights = lambda self: None          # see ref_loader.visual_bert()
+    vil.ViLBERTBase.init_weights = lambda self: None
+    vil.ViLBERTBase.from_pretrained = classmethod(lambda cls, name, config=None, cache_dir=None, **kw: cls(config, **kw))
+    return vb, vil
+
+
+def golden_models():
+    """The reference's REGISTERED MODEL classes end to end: VisualBERT / ViLBERT `forward(sample_list)` -> scores / losses
+    (visual_bert.py:407-601, vilbert.py:1336-1472), classification and pretraining heads, plus the integer tensors the
+    SampleList plumbing derives (image_mask, attention_mask, padded labels)."""
+    vb, vil = _ref_model_modules()
+    g = torch.Generator().manual_seed(123)
+    out = {}
+    # ---------------- VisualBERT ----------------
+    base = dict(bert_model_name=None, visual_embedding_dim=40, special_visual_initialize=True, embedding_strategy="plain",
+                bypass_transformer=False, output_attentions=False, output_hidden_states=False, random_initialize=True,
+                freeze_base=False, finetune_lr_multiplier=1, pooler_strategy="default", zerobias=False, num_labels=3,
+                hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=2, vocab_size=51,
+                max_position_embeddings=64, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    B, T, Rr = 4, 8, 5
+    ids = torch.randint(1, 51, (B, T), generator=g)
+    mask = torch.ones(B, T, dtype=torch.long)
+    mask[1, 6:] = 0
+    mask[3, 4:] = 0
+    seg = torch.zeros(B, T, dtype=torch.long)
+    feats = torch.randn(B, Rr, 40, generator=g).abs()
+    maxf = torch.tensor([5, 2, 3, 4])
+    labels = torch.full((B, T), -1)
+    labels[0, 2], labels[1, 4], labels[2, 1], labels[2, 6] = 7, 11, 3, 40
+    targets = torch.tensor([0, 2, 1, 1])
+
+    def sample_list():
+        return _Cfg(input_ids=ids.clone(), input_mask=mask.clone(), segment_ids=seg.clone(), image_feature_0=feats.clone(),
+                    image_info_0=_Cfg(max_features=maxf.clone()), lm_label_ids=labels.clone(), targets=targets.clone(),
+                    dataset_name="golden", dataset_type="train")
+
+    for head, strategy in (("classification", "default"), ("classification", "vqa"), ("pretraining", "default")):
+        cfg = _Cfg(dict(base, training_head_type=head, pooler_strategy=strategy))
+        m = _new_base_model(vb.VisualBERT, cfg)
+        m.training_head_type = head
+        m.build()
+        m.eval()
+        _perturb(m, 500 + len(out))
+        if head == "pretraining":
+            # tie_weights() (visual_bert.py:227-235): transformers 5 no longer has _tie_or_clone_weights; its non-torchscript
+            # branch is exactly this parameter sharing
+            m.model.cls.predictions.decoder.weight = m.model.bert.embeddings.word_embeddings.weight
+        sl = sample_list()
+        o = m.forward(sl)
+        if head == "classification":
+            loss = torch.nn.functional.cross_entropy(o["scores"], targets)
+        else:
+            loss = o["losses"]["golden/train/masked_lm_loss"]
+        loss.backward()
+        names = [n for n, p_ in m.named_parameters() if p_.grad is not None]
+        key = "visual_bert_%s_%s" % (head, strategy)
+        out[key] = {
+            "config": dict(cfg), "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+            "image_mask": sl["image_mask"], "attention_mask": sl["attention_mask"],
+            "masked_lm_labels": sl["masked_lm_labels"] if head == "pretraining" else None,
+            "scores": o["scores"].detach() if "scores" in o else None,
+            "logits": o["logits"].detach() if "logits" in o else None, "loss": loss.detach(),
+            "loss_keys": sorted(o.get("losses", {}).keys()), "grads": _grads(m, names)}
+    out["visual_bert_inputs"] = {"ids": ids, "mask": mask, "seg": seg, "feats": feats, "max_features": maxf,
+                                 "lm_label_ids": labels, "targets": targets}
+    # ---------------- ViLBERT ----------------
+    vcfg = dict(bert_model_name=None, num_labels=3, random_initialize=True, hidden_size=64, num_attention_heads=1,
+                intermediate_size=128, num_hidden_layers=2, vocab_size=51, max_position_embeddings=64, type_vocab_size=2,
+                hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, hidden_act="gelu", v_feature_size=40,
+                v_target_size=17, v_hidden_size=64, v_num_hidden_layers=2, v_num_attention_heads=1, v_intermediate_size=96,
+                bi_hidden_size=64, bi_num_attention_heads=1, bi_intermediate_size=64, bi_attention_type=1,
+                v_attention_probs_dropout_prob=0.0, v_hidden_act="gelu", v_hidden_dropout_prob=0.0, v_initializer_range=0.02,
+                v_biattention_id=[0, 1], t_biattention_id=[0, 1], pooling_method="mul", fusion_method="mul", fast_mode=False,
+                with_coattention=True, dynamic_attention=False, in_batch_pairs=False, task_specific_tokens=False,
+                fixed_v_layer=0, fixed_t_layer=0, visualization=False, visual_target=0, objective=0, num_negative=128,
+                model="bert", layer_norm_eps=1e-12, initializer_range=0.02, output_attentions=False,
+                output_hidden_states=False, freeze_base=False)
+    bbox = torch.rand(B, Rr, 5, generator=g)
+    cls_prob = torch.softmax(torch.randn(B, Rr, 17, generator=g), dim=-1)
+    image_labels = torch.tensor([[1, 0, 0, 1, 0], [0, 1, 0, 0, 0], [0, 0, 0, 0, 1], [1, 1, 0, 0, 0]])
+    for head in ("classification", "pretraining"):
+        cfg = _Cfg(dict(vcfg, training_head_type=head))
+        m = _new_base_model(vil.ViLBERT, cfg)
+        m.build()
+        m.eval()
+        _perturb(m, 600 + len(out))
+        sl = sample_list()
+        sl["image_info_0"] = _Cfg(max_features=maxf.clone(), bbox=bbox.clone(), cls_prob=cls_prob.numpy().copy())
+        sl["image_labels"] = image_labels.clone()
+        o = m.forward(sl)
+        if head == "classification":
+            loss = torch.nn.functional.cross_entropy(o["scores"], targets)
+        else:
+            loss = sum(v.sum() for v in o["losses"].values())
+        loss.backward()
+        names = [n for n, p_ in m.named_parameters() if p_.grad is not None]
+        out["vilbert_" + head] = {
+            "config": dict(cfg), "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+            "scores": o["scores"].detach() if "scores" in o else None,
+            "losses": {k: v.detach() for k, v in o.get("losses", {}).items()}, "loss": loss.detach(),
+            "grads": _grads(m, names), "unused": sorted(n for n, p_ in m.named_parameters() if p_.grad is None)}
+    out["vilbert_inputs"] = {"bbox": bbox, "cls_prob": cls_prob, "image_labels": image_labels}
+    _save("models", out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -488,6 +618,7 @@ def main():
     golden_lxmert()
     golden_mlm_head()
     golden_visual_bert_bypass()
+    golden_models()
 
 
 if __name__ == "__main__":
