@@ -31,6 +31,12 @@ _LAZY = {
     "undo_replace_with_b200": ("patch", "undo_replace_with_b200"),
     "attach_encoder": ("patch", "attach_encoder"),
     "SampleList": ("sample", "SampleList"),
+    "VisualBERT": ("models", "VisualBERT"),
+    "ViLBERT": ("models", "ViLBERT"),
+    "MMBT": ("models", "MMBT"),
+    "MMFTransformer": ("mmft", "MMFTransformer"),
+    "build_model": ("models", "build_model"),
+    "load_model_config": ("models", "load_model_config"),
 }
 
 

@@ -179,8 +179,10 @@ def test_mmbt_registered_model_classification_runs_and_matches_oracle(cpu_models
 def test_restated_defaults_equal_the_reference_yaml(cpu_models):
     """MODEL_DEFAULTS is a restatement: pin it to the YAML files it cites, read with the module's own YAML loader"""
     MD = cpu_models
+    import mmf_b200.mmft  # noqa: F401  (adds the mmf_transformer defaults)
     for name, rel_path in (("visual_bert", "configs/models/visual_bert/defaults.yaml"),
-                           ("vilbert", "configs/models/vilbert/defaults.yaml"), ("mmbt", "configs/models/mmbt/defaults.yaml")):
+                           ("vilbert", "configs/models/vilbert/defaults.yaml"), ("mmbt", "configs/models/mmbt/defaults.yaml"),
+                           ("mmf_transformer", "configs/models/mmf_transformer/defaults.yaml")):
         doc = MD.read_yaml_with_includes(os.path.join(REF, rel_path), REF)
         block = MD._resolve_interpolations(doc["model_config"][name], doc)
         assert dict(MD.ConfigNode(MD.MODEL_DEFAULTS[name])) == dict(MD.ConfigNode(block)), name

@@ -1,17 +1,20 @@
 #!/bin/bash
-# First GPU call of the next round (one gpurun, ~6 GPU-minutes): parity of every staged variant, then one sweep that
-# times the product library once and each variant against it on the same box.  Build the x2 library BEFORE gpurun:
-#     python tools/ab.py build x2 -DMMFB_F32X2=1
-#     gpurun --timeout 900 -- 'bash tools/round2_first_call.sh > gpurun_out/round2_first_call.log 2>&1'
+# First GPU call of round 2 (one gpurun): the WHOLE -m gpu suite with the staged tests enabled (no -x: every failure is
+# listed), parity of every staged kernel variant, then one sweep that times the product library once and each variant
+# against it on the same box, then the ViLBERT throughput script.
+#     python tools/ab.py build x2 -DMMFB_F32X2=1        (here, before the call)
+#     tools/gpurun_retry.sh 1500 'bash tools/round2_first_call.sh > gpurun_out/round2_first_call.log 2>&1'
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-MMFB_STAGED_TESTS=1 timeout 300 python -m pytest tests/test_staged_gpu.py -m gpu -q 2>&1 | tail -15
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
+MMFB_STAGED_TESTS=1 timeout 600 python -m pytest tests -m gpu -q -rfEs 2>&1 | tail -60
 MMFB_LIB=$PWD/mmf_b200/csrc/libmmfb200_x2.so timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 MMFB_LN_BWD=lean timeout 300 python -m pytest tests/test_rowops_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_ATTN_FWD=2 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_ATTN_BWD_OVERLAP=1 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_DROPOUT_ASYNC=1 MMFB_SIDE_REDUCE=1 timeout 300 python -m pytest tests/test_encoder_gpu.py tests/test_visual_bert_gpu.py -m gpu -q -x 2>&1 | tail -5
-timeout 600 python tools/ab.py sweep x2 lnlean:MMFB_LN_BWD=lean rng:MMFB_DROPOUT_ASYNC=1 side:MMFB_SIDE_REDUCE=1 \
-    attn2:MMFB_ATTN_FWD=2 bwdovl:MMFB_ATTN_BWD_OVERLAP=1 --steps 12
+timeout 900 python tools/ab.py sweep x2 lnlean:MMFB_LN_BWD=lean rng:MMFB_DROPOUT_ASYNC=1 side:MMFB_SIDE_REDUCE=1 \
+    attn2:MMFB_ATTN_FWD=2 bwdovl:MMFB_ATTN_BWD_OVERLAP=1 \
+    all:MMFB_LN_BWD=lean,MMFB_DROPOUT_ASYNC=1,MMFB_SIDE_REDUCE=1,MMFB_ATTN_FWD=2,MMFB_ATTN_BWD_OVERLAP=1 --steps 12
 timeout 200 python tools/bench_vilbert.py --steps 5 --warmup 3
