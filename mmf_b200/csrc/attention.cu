@@ -1270,6 +1270,285 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// fused backward, 16 compute warps (d = 64, Sq, Skv <= 256)
+//
+// Same data flow, TMEM map and MMAs as attn_bwd_fused_kernel, re-balanced after its ncu capture (IPC ~0.3 per scheduler
+// with 2 compute warps each, every pair a serial chain  scores -> exp/dS arithmetic -> 24 accumulation MMAs):
+//   * FOUR threads per query row (warp w: TMEM lane quarter w & 3, 32-column chunk w >> 2 of the 128-wide key block):
+//     4 warps per scheduler hide the MUFU / TMEM-load latencies; a thread handles its chunk as two 16-column halves so the
+//     kernel fits the 120 registers that 544 threads leave.
+//   * overlapped issue order: S/dP of pair k+1 are issued as soon as pair k's have been read, BEFORE the accumulations of
+//     pair k; the compute threads wait for those accumulations only right before they overwrite P'/dS'.
+//   * the operand tiles arrive on four barriers in order of first use (K_0,V_0 | Q_0,dO_0 | Q_1,dO_1 | K_1,V_1): the first
+//     pair starts after 64 KB instead of 128 KB; the dropout word of a chunk is fetched before the score barrier.
+// Accumulation order is that of attn_bwd_fused_kernel, so the results are bit-identical to it.
+// ----------------------------------------------------------------------------------------------
+template <bool DROP>
+__global__ void __launch_bounds__(544, 1)
+attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        AttnBwdFusedDev p) {
+  constexpr int D = 64;
+  constexpr int TILE = 16384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sQ = smem;                 // [2][128 x 128B]
+  uint8_t* sdO = sQ + 2 * TILE;
+  uint8_t* sK = sdO + 2 * TILE;
+  uint8_t* sV = sK + 2 * TILE;
+  uint8_t* sP = sV + 2 * TILE;        // [128 q x 128 kv] bf16 = 2 chunks of [128 x 128B]
+  uint8_t* sDS = sP + 2 * TILE;
+  float* sLse = reinterpret_cast<float*>(sDS + 2 * TILE);
+  float* sDel = sLse + 256;
+  float* sMsk = sDel + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMsk + 256);
+  uint64_t* q_full = bars;            // [2]  Q_i + dO_i
+  uint64_t* kv_full = bars + 2;       // [2]  K_j + V_j
+  uint64_t* s_ready = bars + 4;
+  uint64_t* p_ready = bars + 5;
+  uint64_t* acc_done = bars + 6;
+  uint64_t* kv_read = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ni = (p.Sq + 127) / 128, nj = (p.Skv + 127) / 128;
+  const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+
+  if (warp == 16) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+      mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, 512);
+      mbar_init(acc_done, 1);
+      mbar_init(kv_read, 512);
+      fence_barrier_init();
+      // operand tiles in order of first use; nothing here depends on the barrier below
+      auto load_kv = [&](int j) {
+        mbar_expect_tx(&kv_full[j], 2 * TILE);
+        tma_load_3d(sK + j * TILE, &tmK, &kv_full[j], h * D, j * 128, b);
+        tma_load_3d(sV + j * TILE, &tmV, &kv_full[j], h * D, j * 128, b);
+      };
+      auto load_q = [&](int i) {
+        mbar_expect_tx(&q_full[i], 2 * TILE);
+        tma_load_3d(sQ + i * TILE, &tmQ, &q_full[i], h * D, i * 128, b);
+        tma_load_3d(sdO + i * TILE, &tmdO, &q_full[i], h * D, i * 128, b);
+      };
+      load_kv(0);
+      for (int i = 0; i < ni; ++i) load_q(i);
+      for (int j = 1; j < nj; ++j) load_kv(j);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else {
+    if (threadIdx.x < 256) {
+      const int i = threadIdx.x;
+      const bool qv = i < p.Sq, kv = i < p.Skv;
+      sLse[i] = qv ? p.lse2[bh * p.Sq + i] : INFINITY;
+      sDel[i] = qv ? p.delta[bh * p.Sq + i] : 0.0f;
+      sMsk[i] = kv ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      const uint32_t idesc_q = umma_idesc_bf16(128, D, false, true);   // A K-major,  B MN-major
+      const uint32_t idesc_t = umma_idesc_bf16(128, D, true, true);    // A MN-major, B MN-major
+      auto issue_scores = [&](int i, int j) {      // S = Q_i K_j^T, dP = dO_i V_j^T
+        mbar_wait(&q_full[i], 0);
+        mbar_wait(&kv_full[j], 0);
+        tc_fence_after();
+        const uint32_t aQ_ = smem_u32(sQ + i * TILE), adO_ = smem_u32(sdO + i * TILE);
+        const uint32_t aK_ = smem_u32(sK + j * TILE), aV_ = smem_u32(sV + j * TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + COL_S, umma_desc_sw128(aQ_ + kk * 32, 16, 1024), umma_desc_sw128(aK_ + kk * 32, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + COL_DP, umma_desc_sw128(adO_ + kk * 32, 16, 1024), umma_desc_sw128(aV_ + kk * 32, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(s_ready);
+      };
+      int pair = 0;
+      issue_scores(0, 0);
+      for (int j = 0; j < nj; ++j) {
+        for (int i = 0; i < ni; ++i, ++pair) {
+          const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
+          const uint32_t aK = smem_u32(sK + j * TILE);
+          mbar_wait(p_ready, pair & 1);            // S/dP of this pair have been read, P'/dS' are in shared memory
+          const int i2 = (i + 1 < ni) ? i + 1 : 0, j2 = (i + 1 < ni) ? j : j + 1;
+          if (j2 < nj) issue_scores(i2, j2);
+          // dK_j / dV_j of the previous key block must have been read out before the first pair of this block overwrites them
+          if (i == 0 && j > 0) mbar_wait(kv_read, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {   // K dimension = the 128 keys of block j
+            const uint32_t aoff = (kk >> 2) * TILE + (kk & 3) * 32;
+            umma_bf16(tmem_base + COL_DQ + i * D, umma_desc_sw128(smem_u32(sDS) + aoff, 16, 1024),
+                      umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {   // K dimension = the 128 queries of block i; A = transposed views
+            umma_bf16(tmem_base + COL_DK, umma_desc_sw128(smem_u32(sDS) + kk * 2048, TILE, 1024),
+                      umma_desc_sw128(aQ + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + COL_DV, umma_desc_sw128(smem_u32(sP) + kk * 2048, TILE, 1024),
+                      umma_desc_sw128(adO + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(acc_done);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3, c = warp >> 2;          // c: this thread's 32-column chunk of the key block
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    int pair = 0;
+    for (int j = 0; j < nj; ++j) {
+      for (int i = 0; i < ni; ++i, ++pair) {
+        const int q = i * 128 + row;
+        const float l2 = sLse[q], dl = sDel[q];
+        uint32_t bits = 0xFFFFFFFFu;
+        if (DROP && q < p.Sq) {
+          const int w = j * 4 + c;
+          if (w < p.W) bits = __ldg(p.dmask + (bh * p.Sq + q) * p.W + w);
+        }
+        const float4* m4 = reinterpret_cast<const float4*>(sMsk + j * 128 + c * 32);
+        uint32_t wds[16], wp[16];                           // packed bf16 pairs of dS' and P' for this thread's 32 columns
+        mbar_wait(s_ready, pair & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t rs[16], rd[16];
+          tmem_ld16(trow + COL_S + c * 32 + hh * 16, rs);
+          tmem_ld16(trow + COL_DP + c * 32 + hh * 16, rd);
+          tmem_ld_wait();
+#if MMFB_F32X2
+          const uint64_t sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-l2, -l2), ndl2 = pk2(-dl, -dl);
+#endif
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 m = m4[hh * 4 + q4];
+            const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+              const int jx = q4 * 4 + k;                    // column inside the 16-column half
+              const int bx = hh * 16 + jx;                  // bit index inside the 32-column chunk
+              float ds0, ds1, pv0, pv1;
+#if MMFB_F32X2
+              float a0, a1;
+              upk2(add2(fma2(pk2(__uint_as_float(rs[jx]), __uint_as_float(rs[jx + 1])), sc2, pk2(mm[k], mm[k + 1])), nl2), a0, a1);
+              const uint64_t pr = pk2(ex2_approx(a0), ex2_approx(a1));
+              const uint64_t dp = pk2(__uint_as_float(rd[jx]), __uint_as_float(rd[jx + 1]));
+              if (DROP) {
+                const uint64_t kf = pk2(((bits >> bx) & 1u) ? p.dscale : 0.0f, ((bits >> (bx + 1)) & 1u) ? p.dscale : 0.0f);
+                upk2(mul2(pr, fma2(dp, kf, ndl2)), ds0, ds1);
+                upk2(mul2(pr, kf), pv0, pv1);
+              } else {
+                upk2(mul2(pr, add2(dp, ndl2)), ds0, ds1);
+                upk2(pr, pv0, pv1);
+              }
+#else
+              const float pr0 = ex2_approx(fmaf(__uint_as_float(rs[jx]), p.scale2, mm[k]) - l2);
+              const float pr1 = ex2_approx(fmaf(__uint_as_float(rs[jx + 1]), p.scale2, mm[k + 1]) - l2);
+              float dp0 = __uint_as_float(rd[jx]), dp1 = __uint_as_float(rd[jx + 1]);
+              pv0 = pr0; pv1 = pr1;
+              if (DROP) {
+                const bool k0 = (bits >> bx) & 1u, k1 = (bits >> (bx + 1)) & 1u;
+                dp0 = k0 ? dp0 * p.dscale : 0.0f;  pv0 = k0 ? pr0 * p.dscale : 0.0f;
+                dp1 = k1 ? dp1 * p.dscale : 0.0f;  pv1 = k1 ? pr1 * p.dscale : 0.0f;
+              }
+              ds0 = pr0 * (dp0 - dl);
+              ds1 = pr1 * (dp1 - dl);
+#endif
+              wds[hh * 8 + (jx >> 1)] = pack_bf16x2(ds0, ds1);
+              wp[hh * 8 + (jx >> 1)] = pack_bf16x2(pv0, pv1);
+            }
+          }
+        }
+        // the accumulations of the previous pair still read P'/dS' while the arithmetic above ran
+        if (pair > 0) mbar_wait(acc_done, (pair - 1) & 1);
+        uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
+        uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
+          *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(wds[qd * 4], wds[qd * 4 + 1], wds[qd * 4 + 2], wds[qd * 4 + 3]);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(wp[qd * 4], wp[qd * 4 + 1], wp[qd * 4 + 2], wp[qd * 4 + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+      // ---- dK_j, dV_j are complete: rows = keys of block j; this thread stores 16 of the 64 columns of each ----
+      mbar_wait(acc_done, (pair - 1) & 1);
+      tc_fence_after();
+      {
+        const int kvr = j * 128 + row;
+        uint32_t rk[16], rv[16];
+        tmem_ld16(trow + COL_DK + c * 16, rk);
+        tmem_ld16(trow + COL_DV + c * 16, rv);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(kv_read);
+        if (kvr < p.Skv) {
+          uint4* dk4 = reinterpret_cast<uint4*>(p.dk + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dk + h * D + c * 16);
+          uint4* dv4 = reinterpret_cast<uint4*>(p.dv + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dv + h * D + c * 16);
+#pragma unroll
+          for (int qd = 0; qd < 2; ++qd) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(rk[qd * 8 + 0]) * p.scale, __uint_as_float(rk[qd * 8 + 1]) * p.scale);
+            o.y = pack_bf16x2(__uint_as_float(rk[qd * 8 + 2]) * p.scale, __uint_as_float(rk[qd * 8 + 3]) * p.scale);
+            o.z = pack_bf16x2(__uint_as_float(rk[qd * 8 + 4]) * p.scale, __uint_as_float(rk[qd * 8 + 5]) * p.scale);
+            o.w = pack_bf16x2(__uint_as_float(rk[qd * 8 + 6]) * p.scale, __uint_as_float(rk[qd * 8 + 7]) * p.scale);
+            dk4[qd] = o;
+            o.x = pack_bf16x2(__uint_as_float(rv[qd * 8 + 0]), __uint_as_float(rv[qd * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(rv[qd * 8 + 2]), __uint_as_float(rv[qd * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(rv[qd * 8 + 4]), __uint_as_float(rv[qd * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(rv[qd * 8 + 6]), __uint_as_float(rv[qd * 8 + 7]));
+            dv4[qd] = o;
+          }
+        }
+      }
+    }
+    // ---- dQ_i: rows = queries (all accumulations are complete: acc_done of the last pair was waited for above) ----
+    for (int i = 0; i < ni; ++i) {
+      const int q = i * 128 + row;
+      uint32_t rq[16];
+      tmem_ld16(trow + COL_DQ + i * D + c * 16, rq);
+      tmem_ld_wait();
+      if (q < p.Sq) {
+        uint4* dq4 = reinterpret_cast<uint4*>(p.dq + (static_cast<int64_t>(b) * p.Sq + q) * p.ld_dq + h * D + c * 16);
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(rq[qd * 8 + 0]) * p.scale, __uint_as_float(rq[qd * 8 + 1]) * p.scale);
+          o.y = pack_bf16x2(__uint_as_float(rq[qd * 8 + 2]) * p.scale, __uint_as_float(rq[qd * 8 + 3]) * p.scale);
+          o.z = pack_bf16x2(__uint_as_float(rq[qd * 8 + 4]) * p.scale, __uint_as_float(rq[qd * 8 + 5]) * p.scale);
+          o.w = pack_bf16x2(__uint_as_float(rq[qd * 8 + 6]) * p.scale, __uint_as_float(rq[qd * 8 + 7]) * p.scale);
+          dq4[qd] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d].  One warp per token row, 16-byte vector loads; a head of D
 // elements is owned by D/8 consecutive lanes and reduced with shuffles (coalesced 512 B / 1 KB per warp access).
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
@@ -1440,6 +1719,22 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       fset = true;
     }
     dim3 grid(a.heads, a.B);
+    const char* w16_env = getenv("MMFB_ATTN_BWD");              // staged variant "16" (16 compute warps), read per call
+    if (w16_env != nullptr && w16_env[0] == '1' && w16_env[1] == '6') {
+      static bool w16_attr = false;
+      if (!w16_attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_fused16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(fused16) smem attr: %s", cudaGetErrorString(e));
+        w16_attr = true;
+      }
+      if (f.dmask != nullptr) attn_bwd_fused16_kernel<true><<<grid, 544, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+      else attn_bwd_fused16_kernel<false><<<grid, 544, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+      count_launch();
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd_fused16 launch: %s", cudaGetErrorString(e));
+      return MMFB_OK;
+    }
     const char* ovl_env = getenv("MMFB_ATTN_BWD_OVERLAP");      // staged variant, read per call
     if (ovl_env != nullptr && ovl_env[0] == '1') {
       static bool ovl_attr = false;

@@ -270,3 +270,40 @@ def test_visual_bert_bypass_transformer_vs_reference_golden():
     assert rel(seq, g["seq"]) < 1e-2 and rel(pooled, g["pooled"]) < 1e-2
     (seq * g["w_rand"].cuda()).sum().backward()
     assert rel(feats.grad, g["dfeats"]) < 3e-2
+
+
+@pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (256, 130, False), (100, 256, True), (36, 36, True), (128, 128, False)])
+def test_16_warp_fused_attention_backward_matches_the_default(Sq, Skv, drop):
+    """MMFB_ATTN_BWD=16: four threads per query row, overlapped issue order, tiles on four barriers - same MMAs in the same
+    accumulation order and the same per-element arithmetic as the default fused kernel"""
+    from mmf_b200 import functional as F
+    torch.manual_seed(Sq * 5 + Skv)
+    B, heads, d = 4, 3, 64
+    W = heads * d
+    q = torch.randn(B * Sq, W, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    dctx = torch.randn(B * Sq, W, device="cuda").to(torch.bfloat16)
+    mask = torch.zeros(B, Skv, device="cuda")
+    mask[1, Skv // 3:] = -10000.0
+    mask[2, :] = -10000.0
+    bits = F.dropout_bits((B, heads, Sq), Skv, 0.1, 9, 0, "cuda") if drop else None
+    scale = 1.0 / 0.9 if drop else 1.0
+    ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, Sq, Skv, mask, bits, scale, save_fp32=True)
+
+    def run(flag):
+        if flag:
+            os.environ["MMFB_ATTN_BWD"] = "16"
+        else:
+            os.environ.pop("MMFB_ATTN_BWD", None)
+        out = F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask, bits, scale, ctx32=c32)
+        torch.cuda.synchronize()
+        return [t.clone() for t in out]
+    try:
+        ref, got = run(False), run(True)
+    finally:
+        os.environ.pop("MMFB_ATTN_BWD", None)
+    for name, r, t in zip(("dq", "dk", "dv"), ref, got):
+        r, t = r.float(), t.float()
+        assert (r - t).abs().max() <= 1e-2 * r.abs().max(), name
+        assert (r != t).float().mean() < 0.01, (name, (r != t).float().mean().item())
