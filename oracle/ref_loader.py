@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE - loads the reference's own hot-path source files, unmodified, by path.
+"""TEST / BASELINE INFRASTRUCTURE - loads the reference's own hot-path source files, unmodified, by path.
 
-Only usable where /root/reference exists (the build container); never imported by the product, by
-`-m gpu` tests, smoke() or bench.py.  Its single consumer is oracle/make_golden.py, which turns
-the reference's outputs into the fixtures under tests/golden/.
+Roots, in order: $MMF_REFERENCE_ROOT, /root/reference (the build container), oracle/_ref (the files staged by
+oracle/build_ref.py, which travel to the GPU box).  Never imported by the product or by the `-m gpu` tests.  Consumers:
+oracle/make_golden.py (fixtures under tests/golden/) and the CPU arms of bench.py (`--impl reference`, `cpu_baseline`),
+which time the reference's own implementation on the host cores.
 
 Why a loader: `import mmf` fails here (omegaconf / pytorch_lightning / iopath ... are not installed
 and transformers is 5.5, outside the reference's <=4.10.1 pin - SURVEY.md 8c), but the hot-path
@@ -19,7 +20,16 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MMF_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    env = os.environ.get("MMF_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/mmf"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REF_ROOT = _default_root()
 
 # NB: `transformers3` is deliberately NOT stubbed: the reference's `try: from transformers3 ...` must fail
 # so that it falls back to the real (aliased) transformers.modeling_bert.
@@ -82,8 +92,9 @@ def _install():
     global _installed
     if _installed:
         return
-    if not os.path.isdir(REF_ROOT):
-        raise RuntimeError("reference tree %s not present: the loader only works in the build container" % REF_ROOT)
+    if not os.path.isdir(os.path.join(REF_ROOT, "mmf")):
+        raise RuntimeError("reference files not present under %s (run `python -m oracle.build_ref` where /root/reference "
+                           "exists; oracle/_ref then travels with the snapshot)" % REF_ROOT)
     import transformers.models.bert.modeling_bert as mb
     sys.modules.setdefault("transformers.modeling_bert", mb)
     sys.meta_path.insert(0, _StubFinder())

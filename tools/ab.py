@@ -26,7 +26,7 @@ def lib_path(name):
 
 def bench(env, steps, warmup, out):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(steps), "--warmup", str(warmup),
-           "--no-cpu-baseline"]
+           "--no-cpu-baseline", "--no-parity"]
     r = subprocess.run(cmd, env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if r.returncode != 0 or not lines:
