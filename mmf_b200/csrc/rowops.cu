@@ -308,6 +308,139 @@ ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
   }
 }
 
+// Single-pass LayerNorm backward, tile variant (staged: MMFB_LN_BWD=tile).  A row is spread over WPR warps (each lane
+// owns ONE 8-column slab for all rows it visits), so the three column-sum sets cost 24 registers per thread instead of
+// 24 x (H / 256), gamma is loop-invariant, and a group of WPR warps processes RB rows per step: 2 x RB 16-byte loads in
+// flight per lane and one named barrier per RB rows (row statistics of the WPR warps exchanged through shared memory,
+// double-buffered by step parity).  dx, y, keep-bits are read once, dy / dz written once: traffic = the algorithmic bytes.
+template <int WPR, int G, bool HAS_DX2>
+__global__ void __launch_bounds__(WPR * G * 32, 1)
+ln_bwd_tile_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
+                   const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
+                   bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  constexpr int RB = 4;
+  __shared__ float sStat[2][G][WPR][RB][2];
+  __shared__ float sRed[G][WPR * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = warp / WPR, wig = warp % WPR;
+  const int col = (wig * 32 + lane) * 8;
+  const bool cok = col < H;
+  float g[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) g[e] = 0.0f;
+  if (cok) ld8(gamma + col, g);
+  float ag[8], ab[8], az[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { ag[e] = 0.0f; ab[e] = 0.0f; az[e] = 0.0f; }
+  const float invH = 1.0f / static_cast<float>(H);
+  const int64_t n_steps = (static_cast<int64_t>(M) + RB - 1) / RB;
+  int par = 0;
+  const int64_t g_first = static_cast<int64_t>(blockIdx.x) * G + grp, g_stride = static_cast<int64_t>(gridDim.x) * G;
+  for (int64_t st = g_first; st < n_steps; st += g_stride, par ^= 1) {
+    const int64_t row0 = st * RB;
+    uint4 dw[RB], yw[RB];          // the rows as the packed bf16 words that were loaded; unpacked in both phases
+    float mu[RB], rs[RB], s1[RB], s2[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int64_t row = row0 + r;
+      dw[r] = make_uint4(0, 0, 0, 0);
+      yw[r] = make_uint4(0, 0, 0, 0);
+      if (cok && row < M) {
+        dw[r] = *reinterpret_cast<const uint4*>(dx + row * lddx + col);
+        yw[r] = *reinterpret_cast<const uint4*>(y + row * ldy + col);
+      }
+      mu[r] = row < M ? mean[row] : 0.0f;
+      rs[r] = row < M ? rstd[row] : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float d[8], yy[8];
+      unpack8(dw[r], d);
+      if (HAS_DX2 && cok && row0 + r < M) {
+        // d = dx + dx2 in fp32; the second stream is re-read in phase 2 (an L1 hit) rather than kept
+        float t[8];
+        ld8(dx2 + (row0 + r) * lddx2 + col, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += t[e];
+      }
+      unpack8(yw[r], yy);
+      float a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (yy[e] - mu[r]) * rs[r];
+        const float dg = d[e] * g[e];
+        a1 += dg;
+        a2 += dg * xh;
+        ag[e] += d[e] * xh;
+        ab[e] += d[e];
+      }
+      s1[r] = warp_sum(a1);
+      s2[r] = warp_sum(a2);
+    }
+    if (WPR > 1) {
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) { sStat[par][grp][wig][r][0] = s1[r]; sStat[par][grp][wig][r][1] = s2[r]; }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) { t1 += sStat[par][grp][w][r][0]; t2 += sStat[par][grp][w][r][1]; }
+        s1[r] = t1; s2[r] = t2;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int64_t row = row0 + r;
+      if (!(cok && row < M)) continue;
+      float d[8], yy[8], o[8];
+      unpack8(dw[r], d);
+      if (HAS_DX2) {
+        float t[8];
+        ld8(dx2 + row * lddx2 + col, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += t[e];
+      }
+      unpack8(yw[r], yy);
+      const float m1 = s1[r] * invH, m2 = s2[r] * invH;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rs[r] * (d[e] * g[e] - m1 - ((yy[e] - mu[r]) * rs[r]) * m2);
+      if (dy != nullptr) st8(dy + row * lddy + col, o);
+      if (dmask != nullptr) {
+        const uint32_t w = __ldg(dmask + row * ldmask + (col >> 5));
+        const uint32_t bits = (w >> (col & 31)) & 0xFFu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = ((bits >> e) & 1u) ? o[e] * dscale : 0.0f;
+        st8(dz + row * lddz + col, o);
+      } else if (dz != nullptr && dz != dy) {
+        st8(dz + row * lddz + col, o);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) az[e] += o[e];
+    }
+  }
+  // block reduction over the G groups, then one atomic per column and statistic
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sRed[grp][(wig * 32 + lane) * 8 + e] = which == 0 ? ag[e] : (which == 1 ? ab[e] : az[e]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < WPR * 256; c += WPR * G * 32) {
+      float t = 0.0f;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) t += sRed[gg][c];
+      if (c < H) atomicAdd(dst + c, t);
+    }
+  }
+}
+
 // Row-only LayerNorm backward (no column statistics): few registers, high occupancy.  dy, dz as above.
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
@@ -670,6 +803,29 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   // read per call (not cached) so that one test process can run both variants back to back
   const char* lean_env = getenv("MMFB_LN_BWD");
   const bool lean = lean_env != nullptr && lean_env[0] == 'l';
+  const bool tile = lean_env != nullptr && lean_env[0] == 't';
+  if (tile && nv_ <= 4) {
+    const int64_t n_steps = (static_cast<int64_t>(a.M) + 3) / 4;
+#define LN_TILE(WPR, G)                                                                                                \
+  {                                                                                                                    \
+    int64_t want = (n_steps + (G) - 1) / (G);                                                                          \
+    int grid = static_cast<int>(want < num_sms() ? want : num_sms());                                                  \
+    if (grid < 1) grid = 1;                                                                                            \
+    if (a.dx2 != nullptr)                                                                                              \
+      ln_bwd_tile_kernel<WPR, G, true><<<grid, (WPR) * (G) * 32, 0, s>>>(                                              \
+          (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy, a.mean, a.rstd,             \
+          (const bf16*)a.gamma, (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, a.drop_scale,         \
+          a.dgamma, a.dbeta, a.dbias, a.M, a.H);                                                                       \
+    else                                                                                                               \
+      ln_bwd_tile_kernel<WPR, G, false><<<grid, (WPR) * (G) * 32, 0, s>>>(                                             \
+          (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy, a.mean, a.rstd,             \
+          (const bf16*)a.gamma, (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, a.drop_scale,         \
+          a.dgamma, a.dbeta, a.dbias, a.M, a.H);                                                                       \
+  }
+    if (nv_ <= 1) LN_TILE(1, 12) else if (nv_ == 2) LN_TILE(2, 6) else if (nv_ == 3) LN_TILE(3, 4) else LN_TILE(4, 3)
+#undef LN_TILE
+    return launch_ok("layernorm_bwd(tile)");
+  }
   if (lean && nv_ <= 4) {
     int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
     const int cap = num_sms() * 2;      // two resident blocks per SM, rows strided over them

@@ -31,10 +31,11 @@ def test_async_dropout_state_draws_the_same_bits():
         a.bits((1,), 32, 0.1, "cuda")                   # asked out of order
 
 
-def test_lean_layernorm_backward_matches_the_default_pair():
+@pytest.mark.parametrize("variant,M,H", [("lean", 1000, 768), ("tile", 1000, 768), ("tile", 37848, 768), ("tile", 333, 1024),
+                                         ("tile", 50, 128), ("tile", 7, 512)])
+def test_lean_layernorm_backward_matches_the_default_pair(variant, M, H):
     from mmf_b200 import functional as F
     torch.manual_seed(0)
-    M, H = 1000, 768
     dx = torch.randn(M, H, device="cuda").to(torch.bfloat16)
     dx2 = torch.randn(M, H, device="cuda").to(torch.bfloat16)
     y = torch.randn(M, H, device="cuda").to(torch.bfloat16)
@@ -57,7 +58,7 @@ def test_lean_layernorm_backward_matches_the_default_pair():
         for with_dx2 in (False, True):
             for with_drop in (False, True):
                 ref = run(None, with_dx2, with_drop)
-                got = run("lean", with_dx2, with_drop)
+                got = run(variant, with_dx2, with_drop)
                 for r, t in zip(ref[:2], got[:2]):      # same row arithmetic; FMA contraction may flip a last bf16 bit
                     assert (r - t).abs().max() <= 1e-2 * r.abs().max() and (r != t).float().mean() < 0.01
                 for r, t in zip(ref[2:], got[2:]):                                         # sums: different order

@@ -15,12 +15,13 @@ for t in $(grep -o "^def test_[a-z0-9_]*" tests/test_staged_gpu.py | sed 's/def 
 done
 MMFB_LIB=$PWD/mmf_b200/csrc/libmmfb200_x2.so timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 MMFB_LN_BWD=lean timeout 300 python -m pytest tests/test_rowops_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
+MMFB_LN_BWD=tile timeout 300 python -m pytest tests/test_rowops_gpu.py tests/test_encoder_gpu.py tests/test_frontends_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_ATTN_FWD=2 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_ATTN_BWD_OVERLAP=1 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_ATTN_BWD=16 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -5
 MMFB_DROPOUT_ASYNC=1 MMFB_SIDE_REDUCE=1 timeout 300 python -m pytest tests/test_encoder_gpu.py tests/test_visual_bert_gpu.py -m gpu -q -x 2>&1 | tail -5
-timeout 900 python tools/ab.py sweep x2 lnlean:MMFB_LN_BWD=lean rng:MMFB_DROPOUT_ASYNC=1 side:MMFB_SIDE_REDUCE=1 \
+timeout 900 python tools/ab.py sweep x2 lnlean:MMFB_LN_BWD=lean lntile:MMFB_LN_BWD=tile rng:MMFB_DROPOUT_ASYNC=1 side:MMFB_SIDE_REDUCE=1 \
     attn2:MMFB_ATTN_FWD=2 bwdovl:MMFB_ATTN_BWD_OVERLAP=1 bwd16:MMFB_ATTN_BWD=16 \
-    all:MMFB_LN_BWD=lean,MMFB_DROPOUT_ASYNC=1,MMFB_SIDE_REDUCE=1,MMFB_ATTN_FWD=2,MMFB_ATTN_BWD=16 \
-    allx2:MMFB_LN_BWD=lean,MMFB_DROPOUT_ASYNC=1,MMFB_SIDE_REDUCE=1,MMFB_ATTN_FWD=2,MMFB_ATTN_BWD=16 --steps 12
+    all:MMFB_LN_BWD=tile,MMFB_DROPOUT_ASYNC=1,MMFB_SIDE_REDUCE=1,MMFB_ATTN_FWD=2,MMFB_ATTN_BWD=16 \
+    allx2:MMFB_LN_BWD=tile,MMFB_DROPOUT_ASYNC=1,MMFB_SIDE_REDUCE=1,MMFB_ATTN_FWD=2,MMFB_ATTN_BWD=16 --steps 12
 timeout 200 python tools/bench_vilbert.py --steps 5 --warmup 3
