@@ -710,6 +710,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--ddp-mode", default=os.environ.get("MMFB_DDP_MODE", "end"), choices=["end", "bucket"],
+                    help="gradient exchange: one all-reduce per flat buffer after the backward, or bucket slices "
+                         "overlapped with it (mmf_b200/ddp.py)")
     ap.add_argument("--profile", action="store_true", help="device-resident steps only (for ncu launch lists)")
     args = ap.parse_args()
 
@@ -764,7 +767,8 @@ def main():
     ddp = None
     if world > 1:
         from mmf_b200.ddp import B200DataParallel
-        ddp = B200DataParallel(model)
+        ddp = B200DataParallel(model, mode=args.ddp_mode)
+        config["ddp_mode"] = args.ddp_mode
     net = ddp if ddp is not None else model
     host = _pin(wl.host_batch(B, 1234 + rank))
     dev_batch = to_device(host, dev)
@@ -841,6 +845,11 @@ def main():
             ev.record(copy_stream)
         return batch, ev
 
+    # Every step's loss is copied D2H into pinned memory and READ on the host; the read of step i happens after step i+1
+    # has been enqueued (the trainer's logging does the same), so the host never drains the device queue between steps.
+    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event() for _ in range(args.steps)]
+    read_back = []
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     nxt = prefetch()
@@ -852,9 +861,16 @@ def main():
         loss = step(batch)
         for t in tensors_of(batch):      # keep the copy-stream allocations alive until the compute stream has used them
             t.record_stream(torch.cuda.current_stream())
-        _ = float(loss.detach())   # D2H read of the step's result
+        loss_host[i:i + 1].copy_(loss.detach().float().reshape(1), non_blocking=True)      # D2H of the step's result
+        loss_ev[i].record()
+        if i >= 1:
+            loss_ev[i - 1].synchronize()
+            read_back.append(float(loss_host[i - 1]))
+    loss_ev[args.steps - 1].synchronize()
+    read_back.append(float(loss_host[args.steps - 1]))
     f1.record()
     barrier()
+    assert len(read_back) == args.steps and all(v == v for v in read_back), "a step's loss was not read back / is NaN"
     ms_e2e = f0.elapsed_time(f1)
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:

@@ -7,6 +7,12 @@ never touches, e.g. ViLBERT's q_dense*, are simply not in the pack).  As soon as
 enqueued its last kernel, the slice holding layers >= l that has not been sent yet is all-reduced (AVG) on a
 side stream, overlapping the remaining backward kernels; the end-of-backward callback joins the streams.
 
+`mode`: "bucket" (above) or "end" - ONE all-reduce per flat buffer after the backward.  The exchange is small next to the
+step (config 2: 346 MB fp32 = ~0.9 ms at the measured 725 GB/s bus bandwidth against a 29 ms step), while an NCCL kernel
+that is co-scheduled with the persistent one-CTA-per-SM GEMMs (static tile schedule, 2-CTA clusters that need a whole
+TPC) takes SMs away for as long as it runs and stretches every GEMM it overlaps: r1 lost 7-9 % that way at N = 2..8.
+"end" gives the collective the idle machine at full bandwidth.  Both are measured by bench.py (MMFB_DDP_MODE).
+
 Gradient accumulation: inside `no_sync()` nothing is communicated (the reference all-reduces on every micro-batch,
 SURVEY.md 2.3); the final micro-batch reduces the accumulated buffer.
 """
@@ -28,8 +34,12 @@ def _runners(module):
 
 
 class B200DataParallel(nn.Module):
-    def __init__(self, module, process_group=None, bucket_bytes=64 << 20, overlap=True):
+    def __init__(self, module, process_group=None, bucket_bytes=64 << 20, overlap=True, mode=None):
         super().__init__()
+        import os
+        self.mode = mode or os.environ.get("MMFB_DDP_MODE", "bucket")
+        if self.mode not in ("bucket", "end"):
+            raise ValueError("B200DataParallel mode must be 'bucket' or 'end', got %r" % (self.mode,))
         if not dist.is_initialized():
             raise RuntimeError("B200DataParallel needs an initialised torch.distributed process group")
         self.module = module
@@ -64,7 +74,7 @@ class B200DataParallel(nn.Module):
             self._queue_finalize()
             pack = runner.pack
             st = self._state.setdefault(id(runner), {"hi": None})
-            if st.get("deferred") or self._must_defer(pack):
+            if self.mode == "end" or st.get("deferred") or self._must_defer(pack):
                 # some parameter's .grad is (or will be) a tensor of its own - a weight tied to a torch-side head whose
                 # gradient autograd installed first, or a bf16 pack whose .grad are cast copies: the flat slices are not
                 # what the optimizer reads, and autograd may still be reading them on the main stream.  Reduce this

@@ -223,3 +223,54 @@ def test_data_parallel_tied_and_bf16_pack_world2():
     result = mgr.dict()
     mp.spawn(_tied_bf16_worker, args=(2, port, result), nprocs=2, join=True)
     assert result.get(0) and result.get(1)
+
+
+def _end_mode_worker(rank, world, port, result):
+    """mode="end": hooks send nothing, the end-of-backward callback all-reduces each flat buffer once"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_kernels as FK
+        import mmf_b200.engine as E
+        import mmf_b200.modules as M
+        from mmf_b200.ddp import B200DataParallel
+        E.F = FK
+        M._require_cuda = lambda t, what: None
+        cfg = types.SimpleNamespace(hidden_size=64, num_attention_heads=1, intermediate_size=128, num_hidden_layers=3,
+                                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12)
+        torch.manual_seed(300 + rank)
+        enc = M.B200BertEncoder(cfg).eval()
+        ddp = B200DataParallel(enc, mode="end", overlap=False)
+        calls = []
+        orig = ddp._avg
+        ddp._avg = lambda flat: (calls.append(flat.numel()), orig(flat))[1]
+        g = torch.Generator().manual_seed(17)
+        xs = [torch.randn(2, 6, 64, generator=g) for _ in range(world)]
+        ws = [torch.randn(2, 6, 64, generator=g) for _ in range(world)]
+        (ddp(xs[rank], None)[0] * ws[rank]).sum().backward()
+        assert calls == [enc._runner.pack.total], calls                  # one collective for the whole flat buffer
+        ref_enc = M.B200BertEncoder(cfg).eval()
+        ref_enc.load_state_dict(enc.state_dict())
+        acc = None
+        for r in range(world):
+            ref_enc.zero_grad(set_to_none=True)
+            (ref_enc(xs[r], None)[0] * ws[r]).sum().backward()
+            cur = {k: p.grad.detach().clone() for k, p in ref_enc.named_parameters()}
+            acc = cur if acc is None else {k: acc[k] + cur[k] for k in acc}
+        for k, p in enc.named_parameters():
+            ref = acc[k] / world
+            assert (p.grad - ref).norm() / ref.norm().clamp_min(1e-3 * ref.numel() ** 0.5) < 1e-3, k
+        result[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_end_mode_world2():
+    port = 35500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_end_mode_worker, args=(2, port, result), nprocs=2, join=True)
+    assert result.get(0) and result.get(1)
