@@ -363,7 +363,7 @@ class VilbertRunner:
         d = getattr(mod, "dropout", None)
         return float(getattr(d, "p", 0.0)) if d is not None else 0.0
 
-    def forward(self, txt, img, tmask, imask, B, T, R, training, need_grad):
+    def forward(self, txt, img, tmask, imask, B, T, R, training, need_grad, block_states=None):
         ds = _fresh_dropout_state() if training else None
         saved = []
         for kind, i in self.steps:
@@ -384,6 +384,8 @@ class VilbertRunner:
                 else:
                     pva = pta = pvh = pth = 0.0
                 img, txt, s = E.connection_fwd(img, txt, imask, tmask, w, B, R, T, pva, pta, pvh, pth, ds)
+                if block_states is not None:
+                    block_states.append((txt, img))      # the states the reference appends per co-attention block
             saved.append(s if need_grad else None)
         return txt, img, saved
 
@@ -406,19 +408,25 @@ class VilbertRunner:
 
 class _VilbertEncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, tmask, imask, training, txt, img, *params):
+    def forward(ctx, runner, tmask, imask, training, want_blocks, txt, img, *params):
         B, T, Ht = txt.shape
         _, R, Hv = img.shape
         need_grad = any(ctx.needs_input_grad)
         runner.pack.refresh()
         t = txt.detach().to(torch.bfloat16).contiguous().view(B * T, Ht)
         v = img.detach().to(torch.bfloat16).contiguous().view(B * R, Hv)
-        t, v, saved = runner.forward(t, v, tmask, imask, B, T, R, training, need_grad)
+        blocks = [] if want_blocks else None
+        t, v, saved = runner.forward(t, v, tmask, imask, B, T, R, training, need_grad, blocks)
         ctx.runner, ctx.saved, ctx.masks, ctx.dims, ctx.dtypes = runner, saved, (tmask, imask), (B, T, R, Ht, Hv), (txt.dtype, img.dtype)
-        return t.view(B, T, Ht).to(txt.dtype), v.view(B, R, Hv).to(img.dtype)
+        outs = [t.view(B, T, Ht).to(txt.dtype), v.view(B, R, Hv).to(img.dtype)]
+        if want_blocks:
+            for bt, bv in blocks:
+                outs += [bt.view(B, T, Ht).to(txt.dtype), bv.view(B, R, Hv).to(img.dtype)]
+            ctx.mark_non_differentiable(*outs[2:])
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, dtxt, dimg):
+    def backward(ctx, dtxt, dimg, *unused):
         runner = ctx.runner
         B, T, R, Ht, Hv = ctx.dims
         if ctx.saved is None:
@@ -428,7 +436,7 @@ class _VilbertEncoderFn(torch.autograd.Function):
         dv = (dimg if dimg is not None else torch.zeros(B, R, Hv, device=runner.pack.device)).to(torch.bfloat16).contiguous().view(B * R, Hv)
         dt, dv = runner.backward(dt, dv, ctx.saved, ctx.masks[0], ctx.masks[1], B, T, R)
         ctx.saved = None
-        return (None, None, None, None, dt.view(B, T, Ht).to(ctx.dtypes[0]), dv.view(B, R, Hv).to(ctx.dtypes[1])) + tuple(
+        return (None, None, None, None, None, dt.view(B, T, Ht).to(ctx.dtypes[0]), dv.view(B, R, Hv).to(ctx.dtypes[1])) + tuple(
             runner.pack.autograd_grads(aliased))
 
 
@@ -465,8 +473,10 @@ class B200ViLBertEncoder(nn.Module):
                 co_attention_mask=None, output_all_encoded_layers=True, output_all_attention_masks=False):
         """Same signature / return structure as vilbert.BertEncoder.forward (vilbert.py:590-796):
         ([text layers], [image layers], ([], [], [])).  co_attention_mask is accepted and, like in the reference
-        (vilbert.py:424-425,448-449), not applied.  With output_all_encoded_layers=True the reference returns one
-        entry per co-attention block; only the final states are produced here (the list has one entry)."""
+        (vilbert.py:424-425,448-449), not applied.  output_all_encoded_layers=True reproduces the reference's lists: ONE
+        entry per co-attention block - the states right after that block - and NOT the final states (vilbert.py:761-763,
+        787-790).  Those per-block tensors are outputs for inspection: they carry no gradient here (the reference would
+        back-propagate through them); the differentiable result is the default output_all_encoded_layers=False path."""
         if output_all_attention_masks:
             raise NotImplementedError("attention probabilities are never materialised on the B200 path")
         _require_cuda(txt_embedding, "txt_embedding")
@@ -475,6 +485,8 @@ class B200ViLBertEncoder(nn.Module):
         self._runner.ensure(txt_embedding.device)
         tmask = E.additive_mask_2d(txt_attention_mask, B, T)
         imask = E.additive_mask_2d(image_attention_mask, B, R)
-        t, v = _VilbertEncoderFn.apply(self._runner, tmask, imask, self.training, txt_embedding, image_embedding,
-                                       *self._runner.pack.params)
-        return [t], [v], ([], [], [])
+        outs = _VilbertEncoderFn.apply(self._runner, tmask, imask, self.training, bool(output_all_encoded_layers),
+                                       txt_embedding, image_embedding, *self._runner.pack.params)
+        if output_all_encoded_layers:
+            return list(outs[2::2]), list(outs[3::2]), ([], [], [])
+        return [outs[0]], [outs[1]], ([], [], [])

@@ -235,6 +235,25 @@ def test_vilbert_encoder_module_vs_reference_golden_cpu(cpu_modules):
             continue
         else:
             assert _golden_bound(rel(p.grad, g["grads"][n]), 8e-2), n
+    # output_all_encoded_layers=True: one entry per co-attention block = the states right after that block, and NOT the
+    # final states (vilbert.py:761-763, 787-790) - against the oracle's walk of the same schedule
+    with torch.no_grad():
+        tl_all, vl_all, _ = enc(g["txt"], g["img"], tadd, tadd, iadd, None, output_all_encoded_layers=True)
+        c = dict(g["cfg"])
+        assert len(tl_all) == len(vl_all) == len(c["v_biattention_id"])
+        sd = {k: v.to(torch.bfloat16).float() for k, v in g["state_dict"].items()}
+        t, v, k = g["txt"].to(torch.bfloat16).float(), g["img"].to(torch.bfloat16).float(), 0
+        for kind, i in O.vilbert_schedule(c["v_biattention_id"], c["t_biattention_id"], c["num_hidden_layers"],
+                                          c["v_num_hidden_layers"]):
+            if kind == "t":
+                t, _ = O.bert_layer(t, tadd, sd, "layer.%d" % i, c["num_attention_heads"])
+            elif kind == "v":
+                v, _ = O.bert_layer(v, iadd, sd, "v_layer.%d" % i, c["v_num_attention_heads"])
+            else:
+                v, t = O.connection_layer(v, iadd, t, tadd, sd, "c_layer.%d" % i, c["bi_num_attention_heads"])
+                assert rel(tl_all[k], t) < 2e-2 and rel(vl_all[k], v) < 2e-2, k
+                k += 1
+        assert rel(tl_all[-1], g["t_out"]) > 1e-2        # the last entry is NOT the final state (trailing layers follow)
 
 
 def test_train_mode_dropout_is_repeatable_under_manual_seed_cpu(cpu_modules):
