@@ -162,6 +162,15 @@ int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_strea
  * Contiguous bf16 buffers of n elements. */
 int mmfb_gelu_bwd(const void* dh, const void* u, void* du, int64_t n, mmfb_stream stream);
 
+/* out = a + b; contiguous bf16 buffers of n elements.  The residual-gradient join of a pre-LN layer (ViT: the residual
+ * branches off BEFORE the LayerNorm, mmf/modules/vit.py:96-108), which a post-LN layer gets for free from the GEMM epilogue. */
+int mmfb_add_bf16(const void* a, const void* b, void* out, int64_t n, mmfb_stream stream);
+
+/* out[m, h] = keep-bit(m, h) ? x[m, h] * scale : 0  (bf16 [M, H] with row strides, bits = int32 words [M, ldm] as produced by
+ * mmfb_dropout_bits).  Backward of a dropout that no LayerNorm follows: HF ViTSelfOutput / ViTOutput via vit.py:66-68. */
+int mmfb_dropout_apply(const void* x, int64_t ldx, const uint32_t* bits, int64_t ldm, float scale, void* out, int64_t ldo,
+                       int M, int H, mmfb_stream stream);
+
 /* fp32 -> bf16 cast of a flat (parameter) buffer */
 int mmfb_cast_f32_bf16(const float* in, void* out, int64_t n, mmfb_stream stream);
 

@@ -182,6 +182,17 @@ int mmfb_gelu_bwd(const void* dh, const void* u, void* du, int64_t n, mmfb_strea
   MMFB_REQUIRE_DEVICE();
   return gelu_bwd(dh, u, du, n, reinterpret_cast<cudaStream_t>(stream));
 }
+int mmfb_add_bf16(const void* a, const void* b, void* out, int64_t n, mmfb_stream stream) {
+  if (!a || !b || !out) return set_error(MMFB_ERR_ARG, "mmfb_add_bf16: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return add_bf16(a, b, out, n, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_dropout_apply(const void* x, int64_t ldx, const uint32_t* bits, int64_t ldm, float scale, void* out, int64_t ldo,
+                       int M, int H, mmfb_stream stream) {
+  if (!x || !bits || !out) return set_error(MMFB_ERR_ARG, "mmfb_dropout_apply: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return dropout_apply(x, ldx, bits, ldm, scale, out, ldo, M, H, reinterpret_cast<cudaStream_t>(stream));
+}
 int mmfb_adamw(const mmfb_adamw_args* args, mmfb_stream stream) {
   if (!args) return set_error(MMFB_ERR_ARG, "mmfb_adamw: null args");
   MMFB_REQUIRE_DEVICE();

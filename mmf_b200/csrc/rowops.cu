@@ -750,6 +750,39 @@ __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
   }
 }
 
+// out = a + b (bf16, 16-byte vectors): the residual-gradient join of the pre-LN (ViT) layer, mmf/modules/vit.py:96-108
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float x[8], y[8];
+    ld8(a + i, x);
+    ld8(b + i, y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    st8(out + i, x);
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __float2bfloat16_rn(__bfloat162float(a[j]) + __bfloat162float(b[j]));
+  }
+}
+
+// out[m, h] = keep-bit(m, h) ? x[m, h] * scale : 0 : the backward of a dropout that is NOT followed by a LayerNorm
+// (whose backward kernel otherwise applies the mask): one warp per row, 8 columns per lane and step
+__global__ void dropout_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const uint32_t* __restrict__ bits, int64_t ldm,
+                                     float scale, bf16* __restrict__ out, int64_t ldo, int M, int H) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  for (int col = lane * 8; col < H; col += 256) {
+    float v[8];
+    ld8(x + row * ldx + col, v);
+    const uint32_t w = __ldg(bits + row * ldm + (col >> 5));
+    const uint32_t b8 = (w >> (col & 31)) & 0xFFu;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = ((b8 >> e) & 1u) ? v[e] * scale : 0.0f;
+    st8(out + row * ldo + col, v);
+  }
+}
+
 // fp32 -> bf16 cast of the flat parameter buffer (done every forward, like autocast does)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
@@ -945,6 +978,25 @@ int relu_bwd(const void* dy, const void* y, void* dz, int64_t n, cudaStream_t s)
   const int64_t thr = (n + 7) / 8;
   relu_bwd_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)y, (bf16*)dz, n);
   return launch_ok("relu_bwd");
+}
+
+int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return set_error(MMFB_ERR_ARG, "add_bf16: empty");
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(MMFB_ERR_ARG, "add_bf16: buffers must be 16-byte aligned");
+  const int64_t thr = (n + 7) / 8;
+  add_bf16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+  return launch_ok("add_bf16");
+}
+
+int dropout_apply(const void* x, int64_t ldx, const uint32_t* bits, int64_t ldm, float scale, void* out, int64_t ldo, int M,
+                  int H, cudaStream_t s) {
+  int rc = check_rows(M, H, "dropout_apply");
+  if (rc) return rc;
+  const int64_t threads = static_cast<int64_t>(M) * 32;
+  dropout_apply_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>((const bf16*)x, ldx, bits, ldm, scale,
+                                                                                   (bf16*)out, ldo, M, H);
+  return launch_ok("dropout_apply");
 }
 
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s) {

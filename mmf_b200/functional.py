@@ -233,6 +233,26 @@ def relu_bwd(dy, y):
     return dz
 
 
+def add(a, b):
+    """a + b (bf16, contiguous, same size)."""
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    if not (a.is_contiguous() and b.is_contiguous()) or a.numel() != b.numel():
+        raise ValueError("add: contiguous, equally sized buffers required")
+    out = torch.empty_like(a)
+    check(LIB.mmfb_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream_ptr()))
+    return out
+
+
+def dropout_apply(x, drop_mask, drop_scale):
+    """keep-bit ? x * scale : 0 for x bf16 [M, H] and keep-bit words int32 [M, ceil(H/32)]."""
+    _req(x, torch.bfloat16, "x"); _req(drop_mask, torch.int32, "drop_mask")
+    M, H = x.shape
+    out = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
+    check(LIB.mmfb_dropout_apply(x.data_ptr(), x.stride(0), drop_mask.data_ptr(), drop_mask.stride(0), float(drop_scale),
+                                 out.data_ptr(), out.stride(0), M, H, _stream_ptr()))
+    return out
+
+
 def gelu_bwd(dh, u):
     """du = dh * GELU'(u) (bf16, contiguous) - for a GELU that is followed by a LayerNorm instead of a GEMM."""
     _req(dh, torch.bfloat16, "dh"); _req(u, torch.bfloat16, "u")

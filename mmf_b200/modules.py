@@ -74,6 +74,10 @@ def _fresh_dropout_state(prefetchable=False):
 class EncoderRunner:
     """Engine state of one BERT-style layer stack (built lazily on the first CUDA forward)."""
 
+    W = E.BertLayerW                       # parameter handles of one layer
+    _fwd = staticmethod(E.bert_layer_fwd)  # (x, add_mask, w, B, S, p_attn, p_hidden, ds) -> (out, saved)
+    _bwd = staticmethod(E.bert_layer_bwd)  # (dout, saved, add_mask, w, B, S) -> dx
+
     def __init__(self, layers):
         self.layers = list(layers)
         self.pack = None
@@ -92,13 +96,13 @@ class EncoderRunner:
         params = []
         for m in self.layers:
             _check_erf_gelu(m)
-            params += E.BertLayerW.params(m)
+            params += self.W.params(m)
         for p in params:
             _require_cuda(p, "encoder parameter")
         self.pack = E.ParamPack(params, device)
-        self.weights = [E.BertLayerW(self.pack, m) for m in self.layers]
+        self.weights = [self.W(self.pack, m) for m in self.layers]
         self.layer_param_ranges = []
-        per = len(E.BertLayerW.params(self.layers[0])) if self.layers else 0
+        per = len(self.W.params(self.layers[0])) if self.layers else 0
         for i in range(len(self.layers)):
             o0 = self.pack.offsets[i * per]
             o1 = self.pack.offsets[(i + 1) * per] if (i + 1) * per < len(self.pack.offsets) else self.pack.total
@@ -124,7 +128,7 @@ class EncoderRunner:
             hiddens.append(h)
             if ahead and i + 1 < last_layer:
                 ds.prefetch(sites(i + 1), x.device)      # generated while layer i runs
-            h, s = E.bert_layer_fwd(h, add_mask, self.weights[i], B, S, pa, ph, ds)
+            h, s = self._fwd(h, add_mask, self.weights[i], B, S, pa, ph, ds)
             saved.append(s if need_grad else None)
         return h, saved, hiddens
 
@@ -132,7 +136,7 @@ class EncoderRunner:
         d = dout
         for j in range(len(saved) - 1, -1, -1):
             i = first_layer + j
-            d = E.bert_layer_bwd(d, saved[j], add_mask, self.weights[i], B, S)
+            d = self._bwd(d, saved[j], add_mask, self.weights[i], B, S)
             saved[j] = None
             if self.grad_ready_hook is not None:
                 E.join_side(d.device)

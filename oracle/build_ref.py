@@ -22,6 +22,7 @@ DST = os.path.join(HERE, "_ref")
 FILES = [
     "mmf/modules/hf_layers.py",
     "mmf/modules/embeddings.py",
+    "mmf/modules/vit.py",
     "mmf/models/visual_bert.py",
     "mmf/models/vilbert.py",
     "mmf/models/mmbt.py",

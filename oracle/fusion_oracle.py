@@ -521,6 +521,25 @@ def lxmert_encoder(lang, lang_mask, feats, boxes, visn_mask, sd, prefix, l_layer
 # ----------------------------------------------------------------------------------------------
 # masked-LM pre-training head
 # ----------------------------------------------------------------------------------------------
+def vit_layer(x, add_mask, sd, prefix, heads):
+    """ViTLayer.forward, mmf/modules/vit.py:79-108 (pre-LN block; eval-mode dropout).  ViTAttention = BertSelfAttention on
+    layernorm_before(x) -> ViTSelfOutput.dense (no residual inside, HF modeling_vit) ; the two residuals are added in the
+    layer: h = attn + x (:96), out = output.dense(intermediate(layernorm_after(h))) + h (:99-105)."""
+    a = layer_norm(x, sd, prefix + ".layernorm_before")
+    ctx, _ = bert_self_attention(a, add_mask, sd, prefix + ".attention.attention", heads)
+    h = linear(ctx, sd, prefix + ".attention.output.dense") + x
+    b = layer_norm(h, sd, prefix + ".layernorm_after")
+    return linear(gelu_erf(linear(b, sd, prefix + ".intermediate.dense")), sd, prefix + ".output.dense") + h
+
+
+def vit_encoder(x, add_mask, sd, prefix, num_layers, heads):
+    """ViTEncoder.forward, vit.py:118-175"""
+    pre = prefix + "." if prefix else ""
+    for i in range(num_layers):
+        x = vit_layer(x, add_mask, sd, "%slayer.%d" % (pre, i), heads)
+    return x
+
+
 def bert_pretraining_heads(sequence_output, pooled_output, sd, prefix):
     """HF BertPreTrainingHeads (transformers, pinned <= 4.10), the reference's `self.cls`
     (mmf/models/visual_bert.py:205-214): transform = LayerNorm(gelu(dense(h))), decoder = h W^T + bias (W tied to the

@@ -474,6 +474,61 @@ def golden_adamw():
                     "adam_w_is": opt.AdamW.__module__})
 
 
+def golden_vit():
+    """ViTEncoder (pre-LN blocks with a key-padding mask, mmf/modules/vit.py:63-175) and the ViTModel tail (final LayerNorm +
+    pooler, vit.py:178-274) fed already-embedded tokens (`do_patch_embeddings=False`, the ViLT use, vit.py:187) and pixel
+    values (HF ViTEmbeddings: patch conv + [CLS] + position table)."""
+    from transformers import ViTConfig
+    import transformers.models.vit.modeling_vit as hv
+    vit = R.vit()
+    cfg = ViTConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=2, intermediate_size=128,
+                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, image_size=32, patch_size=8,
+                    layer_norm_eps=1e-12)
+    cfg.chunk_size_feed_forward, cfg.is_decoder, cfg.position_embedding_type, cfg.max_position_embeddings = 0, False, "absolute", 64
+    enc = vit.ViTEncoder(cfg).eval()
+    _perturb(enc, 91)
+    with torch.no_grad():                               # _perturb's LayerNorm rule keys on "LayerNorm.weight": ViT's are
+        for n, p_ in enc.named_parameters():            # `layernorm_before/after.weight`
+            if "layernorm" in n and n.endswith("weight"):
+                p_.add_(1.0)
+    g = torch.Generator().manual_seed(92)
+    B, S = 3, 17
+    x = torch.randn(B, S, 64, generator=g, requires_grad=True)
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[1, 12:] = 0
+    add = (1.0 - mask[:, None, None, :].float()) * -10000.0
+    out = enc(x, attention_mask=add, output_hidden_states=True, return_dict=False)
+    w = torch.randn(out[0].shape, generator=g)
+    (out[0] * w).sum().backward()
+    names = [n for n, _ in enc.named_parameters()]
+    # model tail + embeddings from pixels
+    emb = hv.ViTEmbeddings(cfg).eval()
+    ln = torch.nn.LayerNorm(64, eps=1e-12)
+    pool = hv.ViTPooler(cfg).eval()
+    for m_, sd_ in ((emb, 93), (ln, 94), (pool, 95)):
+        _perturb(m_, sd_)
+    with torch.no_grad():
+        ln.weight.add_(1.0)
+        emb.cls_token.copy_(torch.randn(emb.cls_token.shape, generator=g) * 0.02)
+        emb.position_embeddings.copy_(torch.randn(emb.position_embeddings.shape, generator=g) * 0.02)
+    pix = torch.randn(B, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        e = emb(pix)
+        seq = ln(enc(e, attention_mask=None, return_dict=False)[0])
+        pooled = pool(seq)
+    sd = {"encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    sd.update({"embeddings." + k: v.detach().clone() for k, v in emb.state_dict().items()})
+    sd.update({"layernorm." + k: v.detach().clone() for k, v in ln.state_dict().items()})
+    sd.update({"pooler." + k: v.detach().clone() for k, v in pool.state_dict().items()})
+    _save("vit", {
+        "cfg": {"hidden": 64, "heads": 2, "inter": 128, "layers": 2, "image_size": 32, "patch_size": 8},
+        "state_dict": sd, "x": x.detach(), "mask": mask, "out": out[0].detach(), "hidden_1": out[1][1].detach(),
+        "n_hidden": len(out[1]), "w_rand": w, "dx": x.grad.detach(),
+        "grads": {"encoder." + k: v for k, v in _grads(enc, names).items()},
+        "pixels": pix, "embedded": e, "seq_from_pixels": seq, "pooled_from_pixels": pooled,
+    })
+
+
 class _OmegaConfShim:
     """the two OmegaConf calls the reference's model classes make on this path (visual_bert.py:171-173, vilbert.py:1061-1063)"""
 
@@ -619,6 +674,7 @@ def main():
     golden_mlm_head()
     golden_visual_bert_bypass()
     golden_models()
+    golden_vit()
 
 
 if __name__ == "__main__":

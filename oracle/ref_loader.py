@@ -167,6 +167,12 @@ def lxmert():
     return load("mmf/models/lxmert.py", "mmf.models.lxmert")
 
 
+def vit():
+    """mmf/modules/vit.py: HF ViT blocks with BertSelfAttention inside (maskable) - ViTLayer / ViTEncoder / ViTModel"""
+    hf_layers()
+    return load("mmf/modules/vit.py", "mmf.modules.vit")
+
+
 def visual_bert():
     """mmf/models/visual_bert.py.  VisualBERTBase.__init__ ends in HF's init_weights(), which in transformers 5 needs the
     post_init() bookkeeping the <= 4.10-era class never did; callers that construct it neutralise that one call (weights

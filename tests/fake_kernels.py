@@ -204,6 +204,15 @@ def embed_scatter_sorted(dy, dtab, sorted_idx, order):
     dtab.index_add_(0, i[ok], dy.float()[order.long()[ok]])
 
 
+def add(a, b):
+    return (a.float() + b.float()).to(BF)
+
+
+def dropout_apply(x, drop_mask, drop_scale):
+    keep = unpack_keep_bits(drop_mask, x.shape[-1])
+    return torch.where(keep, x.float() * drop_scale, torch.zeros_like(x, dtype=torch.float32)).to(BF)
+
+
 def relu_bwd(dy, y):
     return torch.where(y > 0, dy, torch.zeros_like(dy))
 

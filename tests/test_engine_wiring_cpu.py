@@ -645,3 +645,55 @@ def test_vilbert_base_front_to_back_vs_oracle_cpu(cpu_frontends):
     assert rel(out[2], pt) < 3e-2 and rel(out[3], pv) < 3e-2
     seq_t, seq_v, _ = m(ids, feats, loc, attention_mask=tmask, image_attention_mask=imask)      # default: trunk outputs only
     assert torch.equal(seq_t, out[0]) and torch.equal(seq_v, out[1])
+
+
+def test_vit_model_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
+    """pre-LN (ViT) layer = the post-LN layer's kernels in a different order (engine.vit_layer_fwd / _bwd): encoder with a
+    key-padding mask (forward, hidden states, input and parameter gradients) and the model tail from pixels (patch
+    projection as a GEMM over unfolded patches, [CLS] + position table, final LayerNorm, pooler) vs mmf/modules/vit.py"""
+    import mmf_b200.vit as VT
+    monkeypatch.setattr(VT, "_require_cuda", lambda t, what: None)
+    g = torch.load(os.path.join(GOLD, "vit.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12, hidden_act="gelu", image_size=c["image_size"], patch_size=c["patch_size"],
+                                num_channels=3, initializer_range=0.02)
+    m = VT.B200ViTModel(cfg)
+    assert set(m.state_dict().keys()) == set(g["state_dict"].keys())          # HF ViT / reference parameter names
+    m.load_state_dict(g["state_dict"])
+    m.eval()
+    x = g["x"].clone().requires_grad_(True)
+    add = O.extended_attention_mask(g["mask"])
+    out = m.encoder(x, attention_mask=add, output_hidden_states=True, return_dict=False)
+    assert len(out[1]) == g["n_hidden"]
+    assert rel(out[0], g["out"]) < 2e-2 and rel(out[1][1], g["hidden_1"]) < 2e-2
+    (out[0] * g["w_rand"]).sum().backward()
+    assert rel(x.grad, g["dx"]) < 3e-2
+    named = dict(m.named_parameters())
+    for k, gr in g["grads"].items():
+        if "key.bias" in k:
+            continue
+        assert rel(named[k].grad, gr) < 8e-2, k
+    with torch.no_grad():
+        seq, pooled = m(g["pixels"])
+        assert rel(m.embeddings(g["pixels"]), g["embedded"]) < 2e-2
+        assert rel(seq, g["seq_from_pixels"]) < 2e-2 and rel(pooled, g["pooled_from_pixels"]) < 2e-2
+    # train mode with dropout: the masks reach the backward through mmfb_dropout_apply; repeatable under manual_seed
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.1
+    enc = VT.B200ViTEncoder(cfg).train()
+    xx = torch.randn(2, 9, c["hidden"])
+
+    def run():
+        torch.manual_seed(3)
+        cpu_frontends_seed_reset()
+        xi = xx.clone().requires_grad_(True)
+        o = enc(xi, return_dict=False)[0]
+        o.square().sum().backward()
+        return o.detach().clone(), xi.grad.clone()
+    import mmf_b200.modules as MM
+
+    def cpu_frontends_seed_reset():
+        MM._SEED_COUNTER[0] = 0
+    (o1, g1), (o2, g2) = run(), run()
+    assert torch.equal(o1, o2) and torch.equal(g1, g2) and torch.isfinite(g1).all()

@@ -150,3 +150,41 @@ def test_visual_bert_bypass_transformer_vs_reference_golden():
     assert rel(seq, g["seq"]) < 1e-2 and rel(pooled, g["pooled"]) < 1e-2
     (seq * g["w_rand"].cuda()).sum().backward()
     assert rel(feats.grad, g["dfeats"]) < 3e-2
+
+
+def test_vit_pre_ln_model_vs_reference_golden():
+    """SURVEY.md 8f item 3 / kernel row K7: pre-LN (ViT) layers on the B200 kernels vs mmf/modules/vit.py (golden)"""
+    import types
+    from mmf_b200.vit import B200ViTModel
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vit.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12, hidden_act="gelu", image_size=c["image_size"], patch_size=c["patch_size"],
+                                num_channels=3, initializer_range=0.02)
+    m = B200ViTModel(cfg)
+    m.load_state_dict(g["state_dict"])
+    m = m.cuda().eval()
+    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
+    x = g["x"].cuda().requires_grad_(True)
+    add = ((1.0 - g["mask"][:, None, None, :].float()) * -10000.0).cuda()
+    out = m.encoder(x, attention_mask=add, output_hidden_states=True, return_dict=False)
+    e_out, e_h = rel(out[0], g["out"]), rel(out[1][1], g["hidden_1"])
+    (out[0] * g["w_rand"].cuda()).sum().backward()
+    e_dx = rel(x.grad, g["dx"])
+    named = dict(m.named_parameters())
+    worst = max((rel(named[k].grad, gr), k) for k, gr in g["grads"].items() if "key.bias" not in k)
+    print("vit golden: out %.2e hidden %.2e dx %.2e worst dW %.2e (%s)" % (e_out, e_h, e_dx, worst[0], worst[1]))
+    assert e_out < 1e-2 and e_h < 1e-2 and e_dx < 1.5e-2 and worst[0] < 3e-2
+    with torch.no_grad():
+        seq, pooled = m(g["pixels"].cuda())
+    assert rel(seq, g["seq_from_pixels"]) < 1e-2 and rel(pooled, g["pooled_from_pixels"]) < 1e-2
+    # dropout on: finite, and the two new row kernels agree with torch on the same bits
+    from mmf_b200 import functional as F
+    xb = torch.randn(300, 768, device="cuda").to(torch.bfloat16)
+    yb = torch.randn(300, 768, device="cuda").to(torch.bfloat16)
+    assert torch.equal(F.add(xb, yb), (xb.float() + yb.float()).to(torch.bfloat16))
+    bits = F.dropout_bits((300,), 768, 0.1, 5, 0, "cuda")
+    keep = F.unpack_keep_bits(bits, 768)
+    ref = torch.where(keep, xb.float() * (1 / 0.9), torch.zeros(1, device="cuda")).to(torch.bfloat16)
+    assert torch.equal(F.dropout_apply(xb, bits, 1 / 0.9), ref)
