@@ -27,6 +27,7 @@ FILES = [
     "mmf/models/vilbert.py",
     "mmf/models/mmbt.py",
     "mmf/models/uniter.py",
+    "mmf/models/vinvl.py",
     "mmf/models/transformers/backends/huggingface.py",
     "mmf/utils/transform.py",
     "mmf/utils/torchscript.py",

@@ -521,6 +521,18 @@ def lxmert_encoder(lang, lang_mask, feats, boxes, visn_mask, sd, prefix, l_layer
 # ----------------------------------------------------------------------------------------------
 # masked-LM pre-training head
 # ----------------------------------------------------------------------------------------------
+def vinvl_forward(input_ids, img_feats, attention_mask, sd, num_layers, heads, token_type_ids=None, use_img_layernorm=True):
+    """VinVLBase.forward, mmf/models/vinvl.py:68-122 (eval): BertEmbeddings(text) ++ img_embedding(regions) -> BertEncoder"""
+    if token_type_ids is None:
+        token_type_ids = torch.zeros_like(input_ids)
+    text = bert_embeddings(input_ids, token_type_ids, sd, "embeddings")
+    img = linear(img_feats, sd, "img_embedding.0")
+    if use_img_layernorm:
+        img = layer_norm(img, sd, "img_embedding.1")
+    emb = torch.cat((text, img), 1)
+    return bert_encoder(emb, extended_attention_mask(attention_mask, emb.dtype), sd, "encoder", num_layers, heads)
+
+
 def vit_layer(x, add_mask, sd, prefix, heads):
     """ViTLayer.forward, mmf/modules/vit.py:79-108 (pre-LN block; eval-mode dropout).  ViTAttention = BertSelfAttention on
     layernorm_before(x) -> ViTSelfOutput.dense (no residual inside, HF modeling_vit) ; the two residuals are added in the

@@ -529,6 +529,49 @@ def golden_vit():
     })
 
 
+def golden_vinvl():
+    """VinVLBase.forward (vinvl.py:43-122), with the 2054-wide VinVL region features scaled down to 46 (46 % 8 = 6, like
+    2054 % 8 = 6: the column padding of the GEMM is exercised the same way)."""
+    from transformers import BertConfig
+    vv = R.vinvl()
+    cfg = BertConfig(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_hidden_layers=2, vocab_size=50,
+                     max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg.img_feature_dim, cfg.use_img_layernorm, cfg.img_layer_norm_eps = 46, True, 1e-12
+    m = vv.VinVLBase(cfg).eval()
+    # with the pinned transformers (<= 4.10) HF's BertEncoder honours output_hidden_states; transformers 5 moved that into
+    # model-level hooks, so the encoder runs under the reference's own replace_with_jit() (BertEncoderJit.forward,
+    # hf_layers.py:316-355 - the implementation MMF installs process-wide from its model constructors)
+    hl = R.hf_layers()
+    hl.replace_with_jit()
+    try:
+        return _golden_vinvl_body(m)
+    finally:
+        hl.undo_replace_with_jit()
+
+
+def _golden_vinvl_body(m):
+    _perturb(m, 171)
+    with torch.no_grad():
+        m.img_embedding[1].weight.add_(1.0)           # "img_embedding.1.weight" is a LayerNorm scale
+    g = torch.Generator().manual_seed(172)
+    B, T, Rr = 3, 7, 5
+    ids = torch.randint(1, 50, (B, T), generator=g)
+    feats = torch.randn(B, Rr, 46, generator=g, requires_grad=True)
+    att = torch.ones(B, T + Rr, dtype=torch.long)
+    att[1, 5:T] = 0
+    att[2, T + 3:] = 0
+    out = m(ids, feats, attention_mask=att)
+    w = torch.randn(out.last_hidden_state.shape, generator=g)
+    (out.last_hidden_state * w).sum().backward()
+    names = [n for n, p_ in m.named_parameters() if p_.grad is not None]
+    _save("vinvl", {
+        "cfg": {"hidden": 64, "heads": 2, "inter": 128, "layers": 2, "vocab": 50, "max_pos": 32, "img_dim": 46},
+        "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items() if v.dtype.is_floating_point},
+        "ids": ids, "feats": feats.detach(), "att": att, "last": out.last_hidden_state.detach(),
+        "n_hidden": len(out.hidden_layers), "hidden_1": out.hidden_layers[1].detach(), "w_rand": w,
+        "dfeats": feats.grad.detach(), "grads": _grads(m, names)})
+
+
 class _OmegaConfShim:
     """the two OmegaConf calls the reference's model classes make on this path (visual_bert.py:171-173, vilbert.py:1061-1063)"""
 
@@ -675,6 +718,7 @@ def main():
     golden_visual_bert_bypass()
     golden_models()
     golden_vit()
+    golden_vinvl()
 
 
 if __name__ == "__main__":

@@ -173,6 +173,12 @@ def vit():
     return load("mmf/modules/vit.py", "mmf.modules.vit")
 
 
+def vinvl():
+    """mmf/models/vinvl.py: VinVLBase (text BertEmbeddings + projected region features -> HF BertEncoder)"""
+    hf_layers()
+    return load("mmf/models/vinvl.py", "mmf.models.vinvl")
+
+
 def visual_bert():
     """mmf/models/visual_bert.py.  VisualBERTBase.__init__ ends in HF's init_weights(), which in transformers 5 needs the
     post_init() bookkeeping the <= 4.10-era class never did; callers that construct it neutralise that one call (weights

@@ -697,3 +697,31 @@ def test_vit_model_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
         MM._SEED_COUNTER[0] = 0
     (o1, g1), (o2, g2) = run(), run()
     assert torch.equal(o1, o2) and torch.equal(g1, g2) and torch.isfinite(g1).all()
+
+
+def test_vinvl_base_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
+    import mmf_b200.vinvl as VV
+    monkeypatch.setattr(VV, "_require_cuda", lambda t, what: None)
+    g = torch.load(os.path.join(GOLD, "vinvl.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                type_vocab_size=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12, initializer_range=0.02, img_feature_dim=c["img_dim"],
+                                use_img_layernorm=True, img_layer_norm_eps=1e-12)
+    m = VV.B200VinVLBase(cfg)
+    assert set(m.state_dict().keys()) == set(g["state_dict"].keys())
+    m.load_state_dict(g["state_dict"])
+    m.eval()
+    feats = g["feats"].clone().requires_grad_(True)
+    out = m(g["ids"], feats, attention_mask=g["att"])
+    assert len(out.hidden_layers) == g["n_hidden"]
+    assert rel(out.last_hidden_state, g["last"]) < 2e-2 and rel(out.hidden_layers[1], g["hidden_1"]) < 2e-2
+    (out.last_hidden_state * g["w_rand"]).sum().backward()
+    assert rel(feats.grad, g["dfeats"]) < 4e-2
+    named = dict(m.named_parameters())
+    for k in ("img_embedding.0.weight", "img_embedding.1.weight", "embeddings.word_embeddings.weight",
+              "encoder.layer.1.output.dense.weight"):
+        assert rel(named[k].grad, g["grads"][k]) < 8e-2, k
+    with pytest.raises(NotImplementedError):
+        m(g["ids"], g["feats"], attention_mask=torch.ones(3, 12, 12))

@@ -188,3 +188,28 @@ def test_vit_pre_ln_model_vs_reference_golden():
     keep = F.unpack_keep_bits(bits, 768)
     ref = torch.where(keep, xb.float() * (1 / 0.9), torch.zeros(1, device="cuda")).to(torch.bfloat16)
     assert torch.equal(F.dropout_apply(xb, bits, 1 / 0.9), ref)
+
+
+def test_vinvl_base_vs_reference_golden():
+    """VinVLBase (mmf/models/vinvl.py:43-122) on the B200 kernels; 46-wide region features exercise the
+    same column padding as VinVL's 2054 (both = 6 mod 8)"""
+    import types
+    from mmf_b200.vinvl import B200VinVLBase
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vinvl.pt"), weights_only=False)
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(hidden_size=c["hidden"], num_attention_heads=c["heads"], intermediate_size=c["inter"],
+                                num_hidden_layers=c["layers"], vocab_size=c["vocab"], max_position_embeddings=c["max_pos"],
+                                type_vocab_size=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                layer_norm_eps=1e-12, initializer_range=0.02, img_feature_dim=c["img_dim"],
+                                use_img_layernorm=True, img_layer_norm_eps=1e-12)
+    m = B200VinVLBase(cfg)
+    m.load_state_dict(g["state_dict"])
+    m = m.cuda().eval()
+    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
+    feats = g["feats"].cuda().requires_grad_(True)
+    out = m(g["ids"].cuda(), feats, attention_mask=g["att"].cuda())
+    e1, e2 = rel(out.last_hidden_state, g["last"]), rel(out.hidden_layers[1], g["hidden_1"])
+    (out.last_hidden_state * g["w_rand"].cuda()).sum().backward()
+    e3 = rel(feats.grad, g["dfeats"])
+    print("vinvl golden: last %.2e hidden %.2e dfeats %.2e" % (e1, e2, e3))
+    assert e1 < 1e-2 and e2 < 1e-2 and e3 < 3e-2
