@@ -182,14 +182,15 @@ class B200MMBTBase(nn.Module):
         else:
             # segment id given to the modal block (mmbt.py:393-414): with a single text segment it is "the other one"
             # (1 if the text uses 0, else 0); with several, the last segment unless the text already ends there
+            # computed on the device (no host round trip in the step): the reference's Python branches on
+            # int(seg.min()) / int(seg.max()) as tensor selects
             seg = sample_list["segment_ids"]
-            lo, hi = int(seg.min()), int(seg.max())
-            if lo == hi:
-                token_value = 1 if hi == 0 else 0
-            else:
-                top = self.num_max_segment - 1
-                token_value = top if hi != top else 0
-            modal_tt = torch.full((input_modal.size(0), 1), token_value, dtype=torch.long, device=input_modal.device)
+            lo, hi = seg.min(), seg.max()
+            top = self.num_max_segment - 1
+            single = torch.where(hi == 0, torch.ones_like(hi), torch.zeros_like(hi))
+            multi = torch.where(hi != top, torch.full_like(hi, top), torch.zeros_like(hi))
+            token_value = torch.where(lo == hi, single, multi).to(torch.long)
+            modal_tt = token_value.reshape(1, 1).expand(input_modal.size(0), 1).to(input_modal.device)
         if input_modal.dim() == 2:
             input_modal = input_modal.unsqueeze(dim=1)
         return self.mmbt(input_modal, input_ids=sample_list["input_ids"], modal_start_tokens=start,
