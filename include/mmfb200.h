@@ -162,6 +162,16 @@ int mmfb_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, mmfb_strea
  * Contiguous bf16 buffers of n elements. */
 int mmfb_gelu_bwd(const void* dh, const void* u, void* du, int64_t n, mmfb_stream stream);
 
+/* Cross-entropy over vocabulary-sized rows, forward and backward in ONE kernel: for every row m of the bf16 logits [M, V]
+ * (row stride ldl, V % 8 == 0) with label[m] != ignore_index,  loss_m = logsumexp(z_m) - z_m[label[m]]  is added to
+ * *loss_sum (and stored in row_loss[m] when given) and the row is OVERWRITTEN by
+ * d(logits) = (softmax(z_m) - onehot(label[m])) * grad_scale;  ignored rows are overwritten by zeros.
+ * Replaces CrossEntropyLoss(ignore_index=-1) over prediction_scores.view(-1, vocab_size) of the masked-LM heads
+ * (mmf/models/visual_bert.py:215,269-277; mmf/models/transformers/heads/mlm.py:46-97) inside the chunked
+ * linear + cross-entropy head: the full [tokens, 30522] logits tensor never exists in HBM. */
+int mmfb_ce_rows(void* logits, int64_t ldl, const int64_t* labels, int64_t ignore_index, int M, int V, float grad_scale,
+                 float* loss_sum, float* row_loss, mmfb_stream stream);
+
 /* out = a + b; contiguous bf16 buffers of n elements.  The residual-gradient join of a pre-LN layer (ViT: the residual
  * branches off BEFORE the LayerNorm, mmf/modules/vit.py:96-108), which a post-LN layer gets for free from the GEMM epilogue. */
 int mmfb_add_bf16(const void* a, const void* b, void* out, int64_t n, mmfb_stream stream);

@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "gemm.cu", "attention.cu", "rowops.cu", "optim.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "attention.cu", "rowops.cu", "optim.cu", "ce.cu"]
 HEADERS = ["common.cuh", "mmfb_internal.h", "../../include/mmfb200.h"]
 LIB = os.path.join(HERE, "libmmfb200.so")
 STAMP = os.path.join(HERE, ".build_stamp")

@@ -182,6 +182,12 @@ int mmfb_gelu_bwd(const void* dh, const void* u, void* du, int64_t n, mmfb_strea
   MMFB_REQUIRE_DEVICE();
   return gelu_bwd(dh, u, du, n, reinterpret_cast<cudaStream_t>(stream));
 }
+int mmfb_ce_rows(void* logits, int64_t ldl, const int64_t* labels, int64_t ignore_index, int M, int V, float grad_scale,
+                 float* loss_sum, float* row_loss, mmfb_stream stream) {
+  if (!logits || !labels) return set_error(MMFB_ERR_ARG, "mmfb_ce_rows: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return ce_rows(logits, ldl, labels, ignore_index, M, V, grad_scale, loss_sum, row_loss, reinterpret_cast<cudaStream_t>(stream));
+}
 int mmfb_add_bf16(const void* a, const void* b, void* out, int64_t n, mmfb_stream stream) {
   if (!a || !b || !out) return set_error(MMFB_ERR_ARG, "mmfb_add_bf16: null pointer");
   MMFB_REQUIRE_DEVICE();

@@ -43,6 +43,8 @@ int scatter(const mmfb_scatter_args& a, cudaStream_t s);
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s);
 int relu_bwd(const void* dy, const void* y, void* dz, int64_t n, cudaStream_t s);
 int adamw(const mmfb_adamw_args& a, cudaStream_t s);
+int ce_rows(void* logits, int64_t ldl, const int64_t* labels, int64_t ignore_index, int M, int V, float grad_scale,
+            float* loss_sum, float* row_loss, cudaStream_t s);
 int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s);
 int dropout_apply(const void* x, int64_t ldx, const uint32_t* bits, int64_t ldm, float scale, void* out, int64_t ldo, int M,
                   int H, cudaStream_t s);

@@ -233,6 +233,22 @@ def relu_bwd(dy, y):
     return dz
 
 
+def ce_rows(logits, labels, ignore_index, grad_scale, loss_sum, row_loss=None):
+    """In place: logits [M, V] bf16 (V % 8 == 0, row stride allowed) -> d(logits) = (softmax - onehot) * grad_scale, zeros for
+    rows whose label is ignore_index; the summed loss of the active rows is ADDED to loss_sum (fp32 scalar tensor)."""
+    _req(logits, torch.bfloat16, "logits"); _req(labels, torch.int64, "labels"); _req(loss_sum, torch.float32, "loss_sum")
+    M, V = logits.shape
+    if labels.numel() != M or not labels.is_contiguous():
+        raise ValueError("ce_rows: one contiguous int64 label per row required")
+    rl = None
+    if row_loss is not None:
+        _req(row_loss, torch.float32, "row_loss")
+        rl = row_loss.data_ptr()
+    check(LIB.mmfb_ce_rows(logits.data_ptr(), logits.stride(0), labels.data_ptr(), int(ignore_index), M, V, float(grad_scale),
+                           loss_sum.data_ptr(), rl, _stream_ptr()))
+    return logits
+
+
 def add(a, b):
     """a + b (bf16, contiguous, same size)."""
     _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")

@@ -76,9 +76,21 @@ class B200BertPreTrainingHeads(nn.Module):
 
 def masked_lm_loss(cls, sequence_output, masked_lm_labels, ignore_index=-1, positions="all"):
     """the reference's loss (visual_bert.py:269-277).  Returns (loss, logits): logits are [B,S,V] for positions="all",
-    [n_masked, V] for positions="masked" (rows in row-major order of the labelled positions)."""
+    [n_masked, V] for positions="masked" (rows in row-major order of the labelled positions).
+    positions="fused": the labelled rows are gathered first (like "masked": identical loss and gradients, the ignored rows
+    contribute nothing), then transform -> vocabulary GEMM -> cross-entropy run chunk by chunk with the loss kernel writing
+    d(logits) in place (ops.linear_cross_entropy): no logits tensor is returned (None) or ever materialised as a whole."""
     labels = masked_lm_labels.reshape(-1)
     H = sequence_output.shape[-1]
+    if positions == "fused":
+        idx = torch.nonzero(labels != ignore_index, as_tuple=False).squeeze(1)
+        if idx.numel() == 0:
+            return sequence_output.sum() * 0.0, None
+        pred = cls.predictions
+        h = pred.transform(sequence_output.reshape(-1, H).index_select(0, idx))
+        loss = ops.linear_cross_entropy(h.reshape(-1, H), pred.decoder.weight, pred.bias, labels.index_select(0, idx),
+                                        ignore_index)
+        return loss, None
     if positions == "masked":
         idx = torch.nonzero(labels != ignore_index, as_tuple=False).squeeze(1)
         if idx.numel() == 0:

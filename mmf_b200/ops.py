@@ -222,3 +222,66 @@ def linear_any(x2d, weight, bias=None):
             bias = torch.nn.functional.pad(bias, (0, pn))
     y = linear(x2d, weight, bias)
     return y[:, :N] if pn else y
+
+
+class _LinearCrossEntropy(torch.autograd.Function):
+    """mean cross-entropy of (h W^T + b) against integer labels WITHOUT the [rows, V] logits tensor: the rows are processed
+    in chunks - vocabulary GEMM -> mmfb_ce_rows (loss + d(logits) in place) -> dgrad and split-K wgrad of the chunk - so at
+    most `chunk_rows` x V logits exist at a time (sized to stay L2-resident between the three kernels that touch them).
+    Gradients are therefore computed in the FORWARD (scaled by 1 / n_active); the backward multiplies them by the incoming
+    scalar.  Reference: prediction scores + CrossEntropyLoss(ignore_index) of mmf/models/visual_bert.py:269-277 and
+    mmf/models/transformers/heads/mlm.py:83-88."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, labels, ignore_index, chunk_rows):
+        hb, wb = _bf16(h), _bf16(weight)
+        V, K = wb.shape
+        pad = (-V) % 8
+        if pad:                                # V = 30522 is not a multiple of 8: zero rows, and a -inf-like bias so that
+            wb = torch.nn.functional.pad(wb, (0, 0, 0, pad))      # the padded logits vanish from the softmax
+        bb = _bf16(bias) if bias is not None else torch.zeros(V, dtype=torch.bfloat16, device=wb.device)
+        if pad:
+            bb = torch.cat([bb, torch.full((pad,), -30000.0, dtype=torch.bfloat16, device=bb.device)])
+        M = hb.shape[0]
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        n_active = (labels != ignore_index).sum()
+        scale = 1.0 / float(max(int(n_active), 1))      # the one host read of the head (the reference's mean reduction)
+        loss_sum = torch.zeros((), dtype=torch.float32, device=wb.device)
+        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_b = bias is not None and ctx.needs_input_grad[2]
+        dh = torch.empty_like(hb) if need_h else None
+        dw = torch.zeros(wb.shape, dtype=torch.float32, device=wb.device) if need_w else None
+        db = torch.zeros(wb.shape[0], dtype=torch.float32, device=wb.device) if need_b else None
+        for r0 in range(0, M, chunk_rows):
+            r1 = min(M, r0 + chunk_rows)
+            z = F.gemm(hb[r0:r1], wb, epi=lib.EPI_BIAS, bias=bb)
+            F.ce_rows(z, labels[r0:r1], ignore_index, scale, loss_sum)      # z now holds d(logits)
+            if need_h:
+                F.gemm(z, wb, b_mn=True, epi=lib.EPI_BIAS, out=dh[r0:r1])
+            if need_w:
+                F.gemm(z, hb[r0:r1], a_mn=True, b_mn=True, epi=lib.EPI_ATOMIC_F32, out=dw,
+                       splits=best_splits(wb.shape[0], K, r1 - r0))
+            if need_b:
+                F.colsum(z, db)
+        ctx.save_for_backward(*[t for t in (dh, dw, db) if t is not None])
+        ctx.have = (need_h, need_w, need_b)
+        ctx.V = V
+        ctx.dtypes = (h.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        return loss_sum * scale
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        need_h, need_w, need_b = ctx.have
+        dh = saved.pop(0) if need_h else None
+        dw = saved.pop(0) if need_w else None
+        db = saved.pop(0) if need_b else None
+        gh = (dh.float() * g).to(ctx.dtypes[0]) if need_h else None
+        gw = (dw[:ctx.V] * g).to(ctx.dtypes[1]) if need_w else None
+        gb = (db[:ctx.V] * g).to(ctx.dtypes[2]) if need_b else None
+        return gh, gw, gb, None, None, None
+
+
+def linear_cross_entropy(h2d, weight, bias, labels, ignore_index=-1, chunk_rows=2048):
+    """mean_i CE((h W^T + b)_i, labels_i) over the rows with labels_i != ignore_index (0 when there is none), fp32 scalar."""
+    return _LinearCrossEntropy.apply(h2d, weight, bias, labels, int(ignore_index), int(chunk_rows))

@@ -204,6 +204,22 @@ def embed_scatter_sorted(dy, dtab, sorted_idx, order):
     dtab.index_add_(0, i[ok], dy.float()[order.long()[ok]])
 
 
+def ce_rows(logits, labels, ignore_index, grad_scale, loss_sum, row_loss=None):
+    z = logits.float()
+    active = (labels != ignore_index) & (labels >= 0) & (labels < z.shape[1])
+    lse = torch.logsumexp(z, dim=1)
+    safe = labels.clamp(0, z.shape[1] - 1)
+    li = torch.where(active, lse - z.gather(1, safe[:, None])[:, 0], torch.zeros_like(lse))
+    d = torch.softmax(z, dim=1)
+    d[torch.arange(z.shape[0]), safe] -= 1.0
+    d = torch.where(active[:, None], d * grad_scale, torch.zeros_like(d))
+    logits.copy_(d.to(BF))
+    loss_sum.add_(li.sum())
+    if row_loss is not None:
+        row_loss.copy_(li)
+    return logits
+
+
 def add(a, b):
     return (a.float() + b.float()).to(BF)
 

@@ -542,6 +542,32 @@ def test_masked_lm_head_vs_reference_golden_cpu(cpu_frontends, monkeypatch):
     cls.zero_grad(set_to_none=True)
     loss_m, logits_m = HD.masked_lm_loss(cls, seq.detach(), g["labels"], positions="masked")
     assert logits_m.shape == (4, cfg.vocab_size) and abs(loss_m.item() - full) < 1e-3 * abs(full)
+    # positions="fused": gather -> transform -> chunked (vocabulary GEMM -> loss kernel writing d(logits) in place -> dgrad /
+    # wgrad): same loss and gradients as the reference's materialised logits, no logits tensor
+    cls.zero_grad(set_to_none=True)
+    seq2 = g["seq"].clone().requires_grad_(True)
+    loss_f, none = HD.masked_lm_loss(cls, seq2, g["labels"], positions="fused")
+    assert none is None and abs(loss_f.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
+    (loss_f * 1.5).backward()                       # a non-unit incoming gradient scales the precomputed gradients
+    assert rel(seq2.grad, 1.5 * g["dseq"]) < 5e-2
+    for k in ("predictions.transform.dense.weight", "predictions.transform.LayerNorm.weight", "predictions.decoder.weight",
+              "predictions.bias"):
+        assert rel(named[k].grad, 1.5 * g["grads"]["cls." + k]) < 6e-2, k
+    # chunking does not change the result
+    import mmf_b200.ops as OPS
+    hh = torch.randn(37, 64).to(torch.bfloat16).float()
+    ww = (torch.randn(203, 64) * 0.1).requires_grad_(True)
+    bbias = (torch.randn(203) * 0.1).requires_grad_(True)
+    lab = torch.randint(0, 203, (37,))
+    lab[::5] = -1
+    ref = torch.nn.functional.cross_entropy(torch.nn.functional.linear(hh, ww.to(torch.bfloat16).float(), bbias.to(torch.bfloat16).float()),
+                                            lab, ignore_index=-1)
+    for chunk in (8, 37, 1000):
+        ww.grad = bbias.grad = None
+        lf = OPS.linear_cross_entropy(hh, ww, bbias, lab, -1, chunk_rows=chunk)
+        assert abs(lf.item() - ref.item()) < 2e-2 * abs(ref.item()), chunk
+        lf.backward()
+        assert ww.grad.shape == ww.shape and torch.isfinite(ww.grad).all() and bbias.grad.abs().sum() > 0
 
 
 def test_visual_bert_for_pretraining_vs_oracle_cpu(cpu_frontends, monkeypatch):

@@ -213,3 +213,56 @@ def test_vinvl_base_vs_reference_golden():
     e3 = rel(feats.grad, g["dfeats"])
     print("vinvl golden: last %.2e hidden %.2e dfeats %.2e" % (e1, e2, e3))
     assert e1 < 1e-2 and e2 < 1e-2 and e3 < 3e-2
+
+
+@pytest.mark.parametrize("M,V", [(300, 30528), (17, 208), (1, 8)])
+def test_ce_rows_kernel_loss_and_gradient(M, V):
+    """mmfb_ce_rows: summed loss and in-place d(logits) vs torch autograd in fp32 on the same bf16 logits"""
+    from mmf_b200 import functional as F
+    torch.manual_seed(M + V)
+    z = (torch.randn(M, V, device="cuda") * 3).to(torch.bfloat16)
+    labels = torch.randint(0, V, (M,), device="cuda")
+    labels[::4] = -1
+    zf = z.float().requires_grad_(True)
+    n = int((labels != -1).sum())
+    ref = torch.nn.functional.cross_entropy(zf, labels, ignore_index=-1, reduction="sum")
+    loss_sum = torch.zeros((), device="cuda")
+    row_loss = torch.empty(M, device="cuda")
+    scale = 1.0 / max(n, 1)
+    F.ce_rows(z, labels, -1, scale, loss_sum, row_loss)
+    if n > 0:
+        (ref * scale).backward()
+        assert abs(loss_sum.item() - ref.item()) <= 2e-3 * abs(ref.item()) + 1e-4
+        g = zf.grad
+        assert ((z.float() - g).norm() / g.norm()).item() < 5e-3
+    assert torch.equal(z[labels == -1].float(), torch.zeros_like(z[labels == -1].float()))       # ignored rows: zero gradient
+    assert torch.equal(row_loss[labels == -1], torch.zeros_like(row_loss[labels == -1]))
+
+
+def test_fused_masked_lm_loss_matches_the_materialised_head():
+    """positions="fused" (gather -> transform -> chunked vocabulary GEMM + loss kernel + dgrad/wgrad) vs positions="all" (the
+    reference's full logits) at the real vocabulary size: same loss, same gradients, no [tokens, 30522] tensor"""
+    import types
+    from mmf_b200 import heads as HD
+    torch.manual_seed(0)
+    cfg = types.SimpleNamespace(hidden_size=768, vocab_size=30522, layer_norm_eps=1e-12, initializer_range=0.02)
+    emb = torch.nn.Embedding(cfg.vocab_size, cfg.hidden_size).cuda()
+    emb.weight.data.normal_(0, 0.02)
+    cls = HD.B200BertPreTrainingHeads(cfg, emb.weight).cuda().eval()
+    B, S = 6, 40
+    seq = torch.randn(B, S, 768, device="cuda")
+    labels = torch.full((B, S), -1, device="cuda")
+    labels[:, 3::7] = torch.randint(0, 30522, (B, len(range(3, S, 7))), device="cuda")
+    out = {}
+    for mode in ("all", "fused"):
+        cls.zero_grad(set_to_none=True)
+        x = seq.clone().requires_grad_(True)
+        loss, logits = HD.masked_lm_loss(cls, x, labels, positions=mode)
+        loss.backward()
+        out[mode] = (loss.item(), x.grad.clone(), emb.weight.grad.clone(), cls.predictions.transform.dense.weight.grad.clone(),
+                     cls.predictions.bias.grad.clone())
+        assert (logits is None) == (mode == "fused")
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    errs = [abs(out["fused"][0] - out["all"][0]) / abs(out["all"][0])] + [rel(a, b) for a, b in zip(out["fused"][1:], out["all"][1:])]
+    print("fused vs materialised MLM head: loss %.2e dseq %.2e dW_vocab %.2e dW_transform %.2e dbias %.2e" % tuple(errs))
+    assert max(errs) < 1e-2
