@@ -713,6 +713,9 @@ def main():
     ap.add_argument("--ddp-mode", default=os.environ.get("MMFB_DDP_MODE", "end"), choices=["end", "bucket"],
                     help="gradient exchange: one all-reduce per flat buffer after the backward, or bucket slices "
                          "overlapped with it (mmf_b200/ddp.py)")
+    ap.add_argument("--optimizer", action="store_true",
+                    help="also time the step WITH the fused AdamW update (mmf_b200.optim.B200AdamW, BERT parameter groups); "
+                         "reported as `with_optimizer`, the headline value stays forward + backward (BASELINE.json metric)")
     ap.add_argument("--profile", action="store_true", help="device-resident steps only (for ncu launch lists)")
     args = ap.parse_args()
 
@@ -872,10 +875,32 @@ def main():
     barrier()
     assert len(read_back) == args.steps and all(v == v for v in read_back), "a step's loss was not read back / is NaN"
     ms_e2e = f0.elapsed_time(f1)
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    ms_opt = 0.0
+    if args.optimizer:
+        from mmf_b200.optim import B200AdamW
+        decay = [p_ for n_, p_ in model.named_parameters() if not any(k in n_ for k in ("bias", "LayerNorm.weight"))]
+        nodecay = [p_ for n_, p_ in model.named_parameters() if any(k in n_ for k in ("bias", "LayerNorm.weight"))]
+        opt = B200AdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}], lr=5e-5, eps=1e-6)
+
+        def opt_step(batch):
+            loss = wl.loss(net, batch, aux)         # no zero_grad: the gradients alias the flat buffer and are re-zeroed by
+            loss.backward()                         # prepare_grads only when .grad was released
+            opt.step()
+            model.zero_grad(set_to_none=True)
+        for _ in range(3):
+            opt_step(dev_batch)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(args.steps):
+            opt_step(dev_batch)
+        o1.record()
+        barrier()
+        ms_opt = o0.elapsed_time(o1)
+    t = torch.tensor([ms_total, ms_e2e, ms_opt], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_opt = t.tolist()
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
     e2e_value = B * world / (ms_e2e / args.steps / 1e3)
@@ -928,7 +953,16 @@ def main():
                         "achieved": l_bytes / (l_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": l_bytes / (l_ms * 1e-3) / 1e9 / hbm, "peak_source": "%s hbm_gbs" % how, "traffic": None,
                         "kernel_ms": l_ms, "bytes_per_launch": l_bytes}
-        del a, w, o1, o2, dx, y, big
+        # fused AdamW over a flat fp32 buffer of this model's size: reads p, g, m, v and writes p, m, v (28 B / parameter)
+        n_par = (sum(p_.numel() for p_ in model.parameters()) + 7) // 8 * 8
+        fp, fg, fm, fv = (torch.zeros(n_par, device=dev) for _ in range(4))
+        fg.normal_()
+        hp = [{"lr": 5e-5, "weight_decay": 0.01, "step_size": 5e-5, "bc2_sqrt": 1.0}]
+        a_ms = time_alone(lambda: F.adamw(fp, fg, fm, fv, hp, beta1=0.9, beta2=0.999, eps=1e-6, mode=0))
+        roofline_adamw = {"bound": "hbm", "kernel": "mmfb_adamw over %d parameters (flat fp32 master / grad / m / v)" % n_par,
+                          "achieved": 28.0 * n_par / (a_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": 28.0 * n_par / (a_ms * 1e-3) / 1e9 / hbm, "kernel_ms": a_ms, "bytes_per_param": 28}
+        del a, w, o1, o2, dx, y, big, fp, fg, fm, fv
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r = run_cpu_arm(wl, 3, 1, cpu_B, args.dropout)
@@ -942,7 +976,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes(host),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
-                "parity": parity, "cpu_baseline": cpu}
+                "roofline_adamw": roofline_adamw, "parity": parity, "cpu_baseline": cpu}
+        if args.optimizer:
+            line["with_optimizer"] = {"value": B * world / (ms_opt / args.steps / 1e3), "unit": "samples/s",
+                                      "ms_per_step": ms_opt / args.steps, "optimizer": "B200AdamW (fused, flat buffers)"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
