@@ -481,9 +481,9 @@ def golden_vit():
     from transformers import ViTConfig
     import transformers.models.vit.modeling_vit as hv
     vit = R.vit()
-    cfg = ViTConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=2, intermediate_size=128,
+    cfg = ViTConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, image_size=32, patch_size=8,
-                    layer_norm_eps=1e-12)
+                    layer_norm_eps=1e-12)           # head size 64: the attention kernels take 64 or 128
     cfg.chunk_size_feed_forward, cfg.is_decoder, cfg.position_embedding_type, cfg.max_position_embeddings = 0, False, "absolute", 64
     enc = vit.ViTEncoder(cfg).eval()
     _perturb(enc, 91)
@@ -493,7 +493,7 @@ def golden_vit():
                 p_.add_(1.0)
     g = torch.Generator().manual_seed(92)
     B, S = 3, 17
-    x = torch.randn(B, S, 64, generator=g, requires_grad=True)
+    x = torch.randn(B, S, 128, generator=g, requires_grad=True)
     mask = torch.ones(B, S, dtype=torch.long)
     mask[1, 12:] = 0
     add = (1.0 - mask[:, None, None, :].float()) * -10000.0
@@ -503,7 +503,7 @@ def golden_vit():
     names = [n for n, _ in enc.named_parameters()]
     # model tail + embeddings from pixels
     emb = hv.ViTEmbeddings(cfg).eval()
-    ln = torch.nn.LayerNorm(64, eps=1e-12)
+    ln = torch.nn.LayerNorm(128, eps=1e-12)
     pool = hv.ViTPooler(cfg).eval()
     for m_, sd_ in ((emb, 93), (ln, 94), (pool, 95)):
         _perturb(m_, sd_)
@@ -521,7 +521,7 @@ def golden_vit():
     sd.update({"layernorm." + k: v.detach().clone() for k, v in ln.state_dict().items()})
     sd.update({"pooler." + k: v.detach().clone() for k, v in pool.state_dict().items()})
     _save("vit", {
-        "cfg": {"hidden": 64, "heads": 2, "inter": 128, "layers": 2, "image_size": 32, "patch_size": 8},
+        "cfg": {"hidden": 128, "heads": 2, "inter": 256, "layers": 2, "image_size": 32, "patch_size": 8},
         "state_dict": sd, "x": x.detach(), "mask": mask, "out": out[0].detach(), "hidden_1": out[1][1].detach(),
         "n_hidden": len(out[1]), "w_rand": w, "dx": x.grad.detach(),
         "grads": {"encoder." + k: v for k, v in _grads(enc, names).items()},
@@ -534,7 +534,7 @@ def golden_vinvl():
     2054 % 8 = 6: the column padding of the GEMM is exercised the same way)."""
     from transformers import BertConfig
     vv = R.vinvl()
-    cfg = BertConfig(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_hidden_layers=2, vocab_size=50,
+    cfg = BertConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2, vocab_size=50,
                      max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     cfg.img_feature_dim, cfg.use_img_layernorm, cfg.img_layer_norm_eps = 46, True, 1e-12
     m = vv.VinVLBase(cfg).eval()
@@ -565,7 +565,7 @@ def _golden_vinvl_body(m):
     (out.last_hidden_state * w).sum().backward()
     names = [n for n, p_ in m.named_parameters() if p_.grad is not None]
     _save("vinvl", {
-        "cfg": {"hidden": 64, "heads": 2, "inter": 128, "layers": 2, "vocab": 50, "max_pos": 32, "img_dim": 46},
+        "cfg": {"hidden": 128, "heads": 2, "inter": 256, "layers": 2, "vocab": 50, "max_pos": 32, "img_dim": 46},
         "state_dict": {k: v.detach().clone() for k, v in m.state_dict().items() if v.dtype.is_floating_point},
         "ids": ids, "feats": feats.detach(), "att": att, "last": out.last_hidden_state.detach(),
         "n_hidden": len(out.hidden_layers), "hidden_1": out.hidden_layers[1].detach(), "w_rand": w,

@@ -67,7 +67,7 @@ def test_bert_encoder_vs_reference_golden():
     e_out, e_dx = rel(out.cpu(), g["out"]), rel(x.grad.cpu(), g["dx"])
     print("golden bert: out %.2e dx %.2e" % (e_out, e_dx))
     assert torch.isfinite(out).all()
-    assert e_out < 1e-2 and e_dx < 1.5e-2
+    assert e_out < 1e-2 and e_dx < 1e-2            # measured 6.0e-3 / 6.3e-3 (2 layers, 10-token fixture)
     worst, wn = check_param_grads(enc.named_parameters(), g["grads"], 2e-2)
     print("golden bert: worst param-grad rel %.2e (%s)" % (worst, wn))
 
@@ -141,8 +141,9 @@ def test_bert_encoder_vs_oracle_config_shapes(B, S, H, heads, I, L):
     o_out, o_dx, o_g = _oracle_run(sd, x.to(torch.bfloat16).float(), add, L, heads, w_rand)
     e_out, e_dx = rel(out, o_out), rel(xg.grad, o_dx)
     print("B%d S%d H%d L%d: out %.2e dx %.2e" % (B, S, H, L, e_out, e_dx))
-    assert e_out < 1e-2 and e_dx < 1.5e-2
-    worst, worst_n = check_param_grads(enc.named_parameters(), o_g, 2e-2)
+    # measured (profiles/r2_parity_errors.txt): L=1 out 3.4e-3 / dx 3.8e-3 / worst dW 5.3e-3; L=2 4.8e-3 / 5.2e-3 / 7.5e-3
+    assert e_out < 1e-2 and e_dx < 1e-2
+    worst, worst_n = check_param_grads(enc.named_parameters(), o_g, 1e-2 if L == 1 else 1.5e-2)
     print("   worst dW %.2e (%s)" % (worst, worst_n))
 
 
@@ -182,8 +183,8 @@ def test_encoder_dropout_matches_oracle_with_same_masks():
     o_out, o_dx, o_g = _oracle_run(sd, x.to(torch.bfloat16).float(), add, 1, heads, w_rand, masks, 0.1)
     e_out, e_dx = rel(out, o_out), rel(xg.grad, o_dx)
     print("dropout parity: out %.2e dx %.2e" % (e_out, e_dx))
-    assert e_out < 1e-2 and e_dx < 1.5e-2
-    check_param_grads(enc.named_parameters(), o_g, 2e-2)
+    assert e_out < 1e-2 and e_dx < 1e-2            # measured 3.1e-3 / 3.7e-3
+    check_param_grads(enc.named_parameters(), o_g, 1.5e-2)
 
 
 def test_grad_accumulation_and_zero_grad():

@@ -37,7 +37,9 @@ def test_layernorm_fwd_bwd(M, H, with_drop):
     dz_ref = yf.grad * keep.float() / 0.9 if with_drop else yf.grad
     assert rel(dz, dz_ref) < 1e-2
     assert rel(dgamma, gf.grad) < 1e-2 and rel(dbeta, bf.grad) < 1e-2
-    assert rel(dbias, dz.float().sum(0)) < 1e-3     # bias gradient = column sum of the stored (bf16) dz
+    # bias gradient = column sum of dz: the default kernel pair sums the STORED bf16 dz, the single-pass variants
+    # (MMFB_LN_BWD=lean / tile) sum the fp32 values before rounding - both within bf16 rounding of each other
+    assert rel(dbias, dz.float().sum(0)) < 4e-3 and rel(dbias, dz_ref.sum(0)) < 1e-2
     # accumulation semantics: a second call adds
     F.layernorm_bwd(dx, y, mean, rstd, g, dgamma, dbeta, dbias=dbias, dx2=dx2, drop_mask=bits, drop_scale=scale or 1.0)
     assert rel(dgamma, 2 * gf.grad) < 1e-2

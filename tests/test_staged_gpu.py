@@ -61,8 +61,8 @@ def test_lean_layernorm_backward_matches_the_default_pair(variant, M, H):
                 got = run(variant, with_dx2, with_drop)
                 for r, t in zip(ref[:2], got[:2]):      # same row arithmetic; FMA contraction may flip a last bf16 bit
                     assert (r - t).abs().max() <= 1e-2 * r.abs().max() and (r != t).float().mean() < 0.01
-                for r, t in zip(ref[2:], got[2:]):                                         # sums: different order
-                    assert (r - t).abs().max() <= 1e-3 * r.abs().max().clamp_min(1.0)
+                for r, t in zip(ref[2:], got[2:]):      # sums: different order; dbias from fp32 values instead of stored bf16
+                    assert (r - t).abs().max() <= 4e-3 * r.abs().max().clamp_min(1.0)
     finally:
         os.environ.pop("MMFB_LN_BWD", None)
 
