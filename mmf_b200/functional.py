@@ -236,7 +236,9 @@ def relu_bwd(dy, y):
 def ce_rows(logits, labels, ignore_index, grad_scale, loss_sum, row_loss=None):
     """In place: logits [M, V] bf16 (V % 8 == 0, row stride allowed) -> d(logits) = (softmax - onehot) * grad_scale, zeros for
     rows whose label is ignore_index; the summed loss of the active rows is ADDED to loss_sum (fp32 scalar tensor)."""
-    _req(logits, torch.bfloat16, "logits"); _req(labels, torch.int64, "labels"); _req(loss_sum, torch.float32, "loss_sum")
+    _req(logits, torch.bfloat16, "logits"); _req(labels, torch.int64, "labels")
+    if not loss_sum.is_cuda or loss_sum.dtype != torch.float32 or loss_sum.numel() != 1:
+        raise ValueError("ce_rows: loss_sum must be a CUDA fp32 tensor with one element")
     M, V = logits.shape
     if labels.numel() != M or not labels.is_contiguous():
         raise ValueError("ce_rows: one contiguous int64 label per row required")
