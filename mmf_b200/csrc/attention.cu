@@ -324,333 +324,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ----------------------------------------------------------------------------------------------
-// forward, pipelined variant (STAGED: selected with MMFB_ATTN_FWD=2, head_dim 64, Skv <= 256; not the default until it
-// has been verified and measured on the GPU)
-//
-// One persistent CTA per SM walks over its (batch, head, 128-query tile) items.  544 threads: warps 0..15 = softmax
-// (FOUR threads per query row: warp w owns TMEM lane quarter w & 3 and the 64 score columns of part w >> 2), warp 16 =
-// TMA + MMA issue (+ the additive-mask rows, loaded by the whole warp).  Differences to attn_fwd_kernel:
-//   * P never touches shared memory: the softmax threads write it back to TENSOR memory (tcgen05.st, bf16 pairs in K
-//     order) and O = P V reads its A operand from there (tcgen05.mma with [a_tmem]); no 64 KB P tile, no proxy fence.
-//   * Q/K/V live in a two-stage ring (2 x 80 KB): the loads of item n+1 are issued while item n is in its softmax,
-//     S(n+1) = Q K^T is issued the moment the softmax threads have finished READING S(n), and the read-out of O(n-1)
-//     sits between the two softmax passes of item n - so the ALUs never wait for a load or an MMA in steady state.
-// TMEM (512 columns allocated): S [0,256) | P [256,384) | O [384,448).
-// Barriers (phase = item parity unless noted): qk_full/v_full/mask_full per ring stage (phase (n>>1)&1), s_ready
-// (S MMA committed), p_ready (512 arrivals: P complete, S no longer read), o_ready (O MMA committed), o_read (512
-// arrivals: O copied out).
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fwd2_chunk_max(const uint32_t (&r)[32], const float4* m4, float scale2, float& mx) {
-#if MMFB_F32X2
-  const uint64_t sc2 = pk2(scale2, scale2);
-#pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) {
-    const float4 m = m4[q4];
-    float a0, a1, a2, a3;
-    upk2(fma2(pk2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])), sc2, pk2(m.x, m.y)), a0, a1);
-    upk2(fma2(pk2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])), sc2, pk2(m.z, m.w)), a2, a3);
-    mx = fmaxf(fmaxf(mx, a0), a1);
-    mx = fmaxf(fmaxf(mx, a2), a3);
-  }
-#else
-#pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) {
-    const float4 m = m4[q4];
-    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 0]), scale2, m.x));
-    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 1]), scale2, m.y));
-    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 2]), scale2, m.z));
-    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 3]), scale2, m.w));
-  }
-#endif
-}
-// exp2(s*scale2 + mask - mx) of one 32-column chunk -> 16 packed bf16 pairs (dropout applied), row sum accumulated
-__device__ __forceinline__ void fwd2_chunk_exp(const uint32_t (&r)[32], const float4* m4, float scale2, float mx,
-                                               uint32_t bits, float& sum, uint32_t (&pk)[16]) {
-#if MMFB_F32X2
-  const uint64_t sc2 = pk2(scale2, scale2), nmx2 = pk2(-mx, -mx);
-  uint64_t sum2 = pk2(sum, 0.0f);
-#endif
-#pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) {
-    const float4 m = m4[q4];
-    const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-    for (int k = 0; k < 4; k += 2) {
-      const int j = q4 * 4 + k;
-#if MMFB_F32X2
-      float a0, a1;
-      upk2(add2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, pk2(mm[k], mm[k + 1])), nmx2), a0, a1);
-      const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-      sum2 = add2(sum2, pk2(e0, e1));
-#else
-      const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, mm[k]) - mx);
-      const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, mm[k + 1]) - mx);
-      sum += e0;
-      sum += e1;
-#endif
-      pk[j >> 1] = pack_bf16x2(((bits >> j) & 1u) ? e0 : 0.0f, ((bits >> (j + 1)) & 1u) ? e1 : 0.0f);
-    }
-  }
-#if MMFB_F32X2
-  float s0, s1;
-  upk2(sum2, s0, s1);
-  sum = s0 + s1;
-#endif
-}
-
-__global__ void __launch_bounds__(544, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, AttnFwdDev p, int n_items) {
-  constexpr int D = 64;
-  constexpr int STAGE = 16384 + 32768 + 32768;     // Q [128 x 128B] | K [256 x 128B] | V [256 x 128B]
-  constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_align1024(smem_raw);
-  const int SK = (p.Skv + 63) & ~63;               // <= 256 (checked by the launcher)
-  const int NB = SK / 64;
-  float* sMask = reinterpret_cast<float*>(smem + 2 * STAGE);      // [2 stages][256]
-  float* sMax = sMask + 512;                                      // [2 parities][4 parts][128 rows]
-  float* sSum = sMax + 1024;                                      // [2 parities][4 parts][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 1024);
-  uint64_t* qk_full = bars;          // [2]
-  uint64_t* v_full = bars + 2;       // [2]
-  uint64_t* mask_full = bars + 4;    // [2]
-  uint64_t* s_ready = bars + 6;
-  uint64_t* p_ready = bars + 7;
-  uint64_t* o_ready = bars + 8;
-  uint64_t* o_read = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int QT = (p.Sq + 127) / 128;
-  const int N = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-
-  if (warp == 16) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&qk_full[s], 1);
-        mbar_init(&v_full[s], 1);
-        mbar_init(&mask_full[s], 32);
-      }
-      mbar_init(s_ready, 1);
-      mbar_init(p_ready, 512);
-      mbar_init(o_ready, 1);
-      mbar_init(o_read, 512);
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 16) {
-    // ------------------------------------ TMA + MMA issue (+ mask rows) ------------------------------------
-    auto item = [&](int n, int& qt, int& h, int& b) {
-      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-      qt = it % QT;
-      const int bh = it / QT;
-      h = bh % p.H;
-      b = bh / p.H;
-    };
-    auto load_qk = [&](int n) {           // lane 0 only
-      int qt, h, b;
-      item(n, qt, h, b);
-      const int s = n & 1;
-      uint8_t* sQ = smem + s * STAGE;
-      uint8_t* sK = sQ + 16384;
-      mbar_expect_tx(&qk_full[s], 16384 + SK * 128);
-      tma_load_3d(sQ, &tmQ, &qk_full[s], h * D, qt * 128, b);
-      for (int rb = 0; rb < NB; ++rb) tma_load_3d(sK + rb * 8192, &tmK, &qk_full[s], h * D, rb * 64, b);
-    };
-    auto load_v = [&](int n) {            // lane 0 only
-      int qt, h, b;
-      item(n, qt, h, b);
-      const int s = n & 1;
-      uint8_t* sV = smem + s * STAGE + 16384 + 32768;
-      mbar_expect_tx(&v_full[s], SK * 128);
-      for (int rb = 0; rb < NB; ++rb) tma_load_3d(sV + rb * 8192, &tmV, &v_full[s], h * D, rb * 64, b);
-    };
-    auto load_mask = [&](int n) {         // whole warp: log2-domain additive mask, -inf on the padded key columns
-      int qt, h, b;
-      item(n, qt, h, b);
-      float* dst = sMask + (n & 1) * 256;
-      for (int i = lane; i < 256; i += 32)
-        dst[i] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
-      mbar_arrive(&mask_full[n & 1]);
-    };
-    auto issue_s = [&](int n) {           // lane 0 only
-      const int s = n & 1;
-      const uint32_t aQ = smem_u32(smem + s * STAGE), aK = aQ + 16384;
-      const uint32_t idesc = umma_idesc_bf16(128, SK, false, false);
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_bf16(tmem_base + COL_S, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc,
-                  kk > 0 ? 1u : 0u);
-      umma_commit(s_ready);
-    };
-    auto issue_o = [&](int n) {           // lane 0 only: O = P V, A = P from tensor memory (8 columns per K = 16 step)
-      const int s = n & 1;
-      const uint32_t aV = smem_u32(smem + s * STAGE + 16384 + 32768);
-      const uint32_t idesc = umma_idesc_bf16(128, D, false, true);
-      const int ksteps = (p.Skv + 15) / 16;
-      for (int kk = 0; kk < ksteps; ++kk)
-        umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_P + kk * 8, umma_desc_sw128(aV + kk * 2048, SK * 128, 1024), idesc,
-                     kk > 0 ? 1u : 0u);
-      umma_commit(o_ready);
-    };
-    // prologue: both ring stages
-    for (int n = 0; n < 2 && n < N; ++n) {
-      if (lane == 0) { load_qk(n); load_v(n); }
-      load_mask(n);
-    }
-    for (int n = 0; n < N; ++n) {
-      if (lane == 0) {
-        mbar_wait(&qk_full[n & 1], (n >> 1) & 1);
-        if (n >= 1) mbar_wait(p_ready, (n - 1) & 1);       // the softmax threads no longer read S(n-1); P(n-1) is complete
-        tc_fence_after();
-        issue_s(n);
-        if (n >= 1) {
-          if (n + 1 < N) load_qk(n + 1);                   // Q, K of item n-1 were consumed by S(n-1)
-          mbar_wait(&v_full[(n - 1) & 1], ((n - 1) >> 1) & 1);
-          if (n >= 2) mbar_wait(o_read, (n - 2) & 1);      // O(n-2) has been copied out
-          tc_fence_after();
-          issue_o(n - 1);
-          if (n + 1 < N) {
-            mbar_wait(o_ready, (n - 1) & 1);               // V of item n-1 consumed
-            load_v(n + 1);
-          }
-        }
-      }
-      __syncwarp();
-      // the mask row of item n+1 replaces the one of item n-1, which nobody reads after p_ready(n-1)
-      if (n >= 1 && n + 1 < N) load_mask(n + 1);
-    }
-    if (lane == 0) {
-      mbar_wait(p_ready, (N - 1) & 1);
-      mbar_wait(&v_full[(N - 1) & 1], ((N - 1) >> 1) & 1);
-      if (N >= 2) mbar_wait(o_read, (N - 2) & 1);
-      tc_fence_after();
-      issue_o(N - 1);
-    }
-  } else {
-    // ------------------------------------ softmax + read-out ------------------------------------
-    const int quarter = warp & 3, part = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int nch = (p.Skv + 31) / 32;
-    const int c0 = part * 2;                                // this thread's 32-column chunks: c0, c0 + 1
-    float prev_mx = 0.0f;
-    int prev_q = 0, prev_h = 0, prev_b = 0;
-
-    // copies O(prev item) out: 16 of the 64 columns per thread, normalised by the row sum of the four parts
-    auto read_out = [&](int n_prev) {
-      const int par = n_prev & 1;
-      const float sum = sSum[(par * 4 + 0) * 128 + row] + sSum[(par * 4 + 1) * 128 + row] +
-                        sSum[(par * 4 + 2) * 128 + row] + sSum[(par * 4 + 3) * 128 + row];
-      mbar_wait(o_ready, par);
-      tc_fence_after();
-      uint32_t r[16];
-      tmem_ld16(trow + COL_O + part * 16, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(o_read);
-      if (prev_q < p.Sq) {
-        const float inv = p.dscale / sum;
-        if (part == 0) p.lse2[static_cast<int64_t>(prev_b * p.H + prev_h) * p.Sq + prev_q] = prev_mx + log2f(sum);
-        const int64_t tok = static_cast<int64_t>(prev_b) * p.Sq + prev_q;
-        uint4* dst = reinterpret_cast<uint4*>(p.ctx + tok * p.ldo + prev_h * D + part * 16);
-#pragma unroll
-        for (int qd = 0; qd < 2; ++qd) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[qd * 8 + 0]) * inv, __uint_as_float(r[qd * 8 + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(r[qd * 8 + 2]) * inv, __uint_as_float(r[qd * 8 + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(r[qd * 8 + 4]) * inv, __uint_as_float(r[qd * 8 + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * inv, __uint_as_float(r[qd * 8 + 7]) * inv);
-          dst[qd] = o;
-        }
-        if (p.ctx32 != nullptr) {
-          float4* d32 = reinterpret_cast<float4*>(p.ctx32 + tok * (p.H * D) + prev_h * D + part * 16);
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-            d32[qd] = make_float4(__uint_as_float(r[qd * 4 + 0]) * inv, __uint_as_float(r[qd * 4 + 1]) * inv,
-                                  __uint_as_float(r[qd * 4 + 2]) * inv, __uint_as_float(r[qd * 4 + 3]) * inv);
-        }
-      }
-    };
-
-    for (int n = 0; n < N; ++n) {
-      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-      const int qt = it % QT, bh = it / QT;
-      const int h = bh % p.H, b = bh / p.H;
-      const int q = qt * 128 + row;
-      const int par = n & 1;
-      const float4* m4 = reinterpret_cast<const float4*>(sMask + par * 256);
-      mbar_wait(&mask_full[par], (n >> 1) & 1);
-      mbar_wait(s_ready, par);
-      tc_fence_after();
-      // ---- pass 1: row maximum over this thread's 64 columns ----
-      float mx = -INFINITY;
-      // (one chunk at a time: 17 warps leave 96 registers per thread, and the other 15 warps cover the TMEM latency)
-#pragma unroll 1
-      for (int c = c0; c < c0 + 2; ++c) {
-        if (c < nch) {
-          uint32_t r[32];
-          tmem_ld32(trow + COL_S + c * 32, r);
-          tmem_ld_wait();
-          fwd2_chunk_max(r, m4 + c * 8, p.scale2, mx);
-        }
-      }
-      sMax[(par * 4 + part) * 128 + row] = mx;
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
-      mx = fmaxf(fmaxf(sMax[(par * 4 + 0) * 128 + row], sMax[(par * 4 + 1) * 128 + row]),
-                 fmaxf(sMax[(par * 4 + 2) * 128 + row], sMax[(par * 4 + 3) * 128 + row]));
-      // ---- O(n-1) is copied out between the passes; this also orders P(n) after the MMA that read P(n-1) ----
-      if (n >= 1) read_out(n - 1);
-      // ---- pass 2: probabilities of this thread's columns -> P in tensor memory ----
-      float sum = 0.0f;
-      const uint32_t* dm = (p.dmask != nullptr && q < p.Sq)
-                               ? p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W
-                               : nullptr;
-#pragma unroll 1
-      for (int c = c0; c < c0 + 2; ++c) {
-        uint32_t pk[16];
-        if (c < nch) {
-          uint32_t r[32];
-          tmem_ld32(trow + COL_S + c * 32, r);
-          tmem_ld_wait();
-          fwd2_chunk_exp(r, m4 + c * 8, p.scale2, mx, dm ? __ldg(dm + c) : 0xFFFFFFFFu, sum, pk);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
-        }
-        tmem_st16(trow + COL_P + c * 16, pk);
-      }
-      sSum[(par * 4 + part) * 128 + row] = sum;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      prev_mx = mx; prev_q = q; prev_h = h; prev_b = b;
-    }
-    // drain: the last item's row sums are exchanged through the same quarter barrier
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
-    read_out(N - 1);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 16) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------------------------
 struct AttnBwdDev {
@@ -986,10 +659,7 @@ struct AttnBwdFusedDev {
   bf16* dv; int64_t ld_dv;
 };
 
-// OVL (staged, MMFB_ATTN_BWD_OVERLAP=1): the score MMAs of pair k+1 are issued BEFORE the accumulations of pair k, and the
-// compute threads wait for those accumulations only right before their first shared-memory store - the first chunk's
-// arithmetic of pair k+1 then overlaps the 24 accumulation MMAs of pair k instead of idling behind them.
-template <bool DROP, bool OVL = false>
+template <bool DROP>
 __global__ void __launch_bounds__(288, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1076,26 +746,13 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         umma_commit(s_ready);
       };
       int pair = 0;
-      if (OVL) {
-        tc_fence_after();
-        issue_scores(0, 0);
-      }
       for (int j = 0; j < nj; ++j) {
         for (int i = 0; i < ni; ++i, ++pair) {
           tc_fence_after();
           const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
           const uint32_t aK = smem_u32(sK + j * TILE);
-          if (!OVL) issue_scores(i, j);
+          issue_scores(i, j);
           mbar_wait(p_ready, pair & 1);
-          if (OVL) {
-            // S and dP of this pair have been read: the next pair's scores go first, its arithmetic starts while the
-            // accumulations below are still running
-            const int i2 = (i + 1 < ni) ? i + 1 : 0, j2 = (i + 1 < ni) ? j : j + 1;
-            if (j2 < nj) {
-              tc_fence_after();
-              issue_scores(i2, j2);
-            }
-          }
           // dK_j / dV_j of the previous key block must have been read out before the first pair of this block overwrites them
           if (i == 0 && j > 0) mbar_wait(kv_read, (j - 1) & 1);
           tc_fence_after();
@@ -1125,7 +782,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int i = 0; i < ni; ++i, ++pair) {
         const int q = i * 128 + row;
         const float l2 = sLse[q], dl = sDel[q];
-        if (!OVL && pair > 0) mbar_wait(acc_done, (pair - 1) & 1);   // P'/dS' buffers are free again
+        if (pair > 0) mbar_wait(acc_done, (pair - 1) & 1);   // P'/dS' buffers are free again
         mbar_wait(s_ready, pair & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -1189,8 +846,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #endif
           uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
           uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
-          // OVL: the accumulations of the previous pair still read P'/dS' while the arithmetic above ran
-          if (OVL && c == half && pair > 0) mbar_wait(acc_done, (pair - 1) & 1);
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
@@ -1625,25 +1280,6 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   p.ctx32 = a.ctx32;
   p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
   p.scale2 = LOG2E / sqrtf(static_cast<float>(D));
-  if (D == 64 && a.Skv <= 256) {
-    const char* v2_env = getenv("MMFB_ATTN_FWD");      // read per call: a test process can run both kernels
-    if (v2_env != nullptr && v2_env[0] == '2') {
-      const int smem2 = 2 * (16384 + 32768 + 32768) + (512 + 1024 + 1024) * 4 + 128 + 1024;
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e2 = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-        if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd2 smem attr (%d B): %s", smem2, cudaGetErrorString(e2));
-        attr_set = true;
-      }
-      const int n_items = ((a.Sq + 127) / 128) * a.heads * a.B;
-      const int grid2 = n_items < num_sms() ? n_items : num_sms();
-      attn_fwd2_kernel<<<grid2, 544, smem2, stream>>>(tmQ, tmK, tmV, p, n_items);
-      cudaError_t e2 = cudaGetLastError();
-      if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd2 launch: %s", cudaGetErrorString(e2));
-      count_launch();
-      return MMFB_OK;
-    }
-  }
   auto kern = attn_fwd_kernel<D>;
   static int smem_set = 0;
   if (smem > smem_set) {
@@ -1719,8 +1355,10 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       fset = true;
     }
     dim3 grid(a.heads, a.B);
-    const char* w16_env = getenv("MMFB_ATTN_BWD");              // staged variant "16" (16 compute warps), read per call
-    if (w16_env != nullptr && w16_env[0] == '1' && w16_env[1] == '6') {
+    // default: the 16-warp kernel (measured 307 us against 336 us per layer at the bench shape, profiles/r2_kbench_before.json);
+    // MMFB_ATTN_BWD=8 (read per call) selects the 8-warp kernel for A/B runs
+    const char* w_env = getenv("MMFB_ATTN_BWD");
+    if (w_env == nullptr || w_env[0] != '8') {
       static bool w16_attr = false;
       if (!w16_attr) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1730,23 +1368,6 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       }
       if (f.dmask != nullptr) attn_bwd_fused16_kernel<true><<<grid, 544, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
       else attn_bwd_fused16_kernel<false><<<grid, 544, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
-      count_launch();
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd_fused16 launch: %s", cudaGetErrorString(e));
-      return MMFB_OK;
-    }
-    const char* ovl_env = getenv("MMFB_ATTN_BWD_OVERLAP");      // staged variant, read per call
-    if (ovl_env != nullptr && ovl_env[0] == '1') {
-      static bool ovl_attr = false;
-      if (!ovl_attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(attn_bwd_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(fused, overlap) smem attr: %s", cudaGetErrorString(e));
-        ovl_attr = true;
-      }
-      if (f.dmask != nullptr) attn_bwd_fused_kernel<true, true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
-      else attn_bwd_fused_kernel<false, true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
     } else if (f.dmask != nullptr) attn_bwd_fused_kernel<true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
     else attn_bwd_fused_kernel<false><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
     count_launch();

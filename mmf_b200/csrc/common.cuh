@@ -366,9 +366,11 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 // ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per FMA-pipe issue slot) ----
 // Lane results are bit-identical to the scalar fmaf / * / + (round-to-nearest, no ftz), so a packed epilogue is a pure
-// issue-slot optimisation.  Built in when MMFB_F32X2=1 (csrc/build.py), see gelu_erf2 / gelu_erf_grad2.
+// issue-slot optimisation.  On by default since round 2 (isolated timings, profiles/r2_kbench_before*.json: FFN-up GEMM
+// + GELU 165 -> 152 us, GELU' dgrad 177 -> 154 us, fused attention backward 307 -> 296 us); -DMMFB_F32X2=0 builds the
+// scalar variant for A/B runs.  See gelu_erf2 / gelu_erf_grad_mul2.
 #ifndef MMFB_F32X2
-#define MMFB_F32X2 0
+#define MMFB_F32X2 1
 #endif
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   uint64_t r;

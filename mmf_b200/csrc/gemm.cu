@@ -30,10 +30,6 @@
 #include "common.cuh"
 #include "mmfb_internal.h"
 
-#ifndef MMFB_EPI_PREFETCH
-#define MMFB_EPI_PREFETCH 0
-#endif
-
 namespace mmfb {
 
 constexpr int BM = 128;
@@ -264,34 +260,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     };
     if (C::AUX_TMA && store_thread) aux_prefetch(0);
-    // REG_PF: the residual / mask words a slice needs are fetched into registers ONE SLICE AHEAD (while the previous slice is
-    // being processed and, across tiles, while this tile's MMAs are still running), instead of sitting as dependent global
-    // loads in the middle of every half-slice.  The epilogue warps have ~200 registers each (320 threads, one CTA per SM).
-    constexpr bool REG_PF = MMFB_EPI_PREFETCH && !C::AUX_TMA && (EPI == EPI_BIAS_DROP_RESID || EPI == EPI_ADD_AUX);
-    uint4 na[REG_PF ? 8 : 1];
-    uint32_t nm[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-    auto reg_prefetch = [&](int k) {
-      int am0, an;
-      const bool have = slice_coords(k, am0, an);
-      const int pm_ = am0 + row;
-#pragma unroll
-      for (int q = 0; q < (REG_PF ? 8 : 1); ++q) na[q] = make_uint4(0, 0, 0, 0);
-      nm[0] = nm[1] = 0xFFFFFFFFu;
-      if (have && pm_ < p.M) {
-        if (p.aux != nullptr) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(pm_) * p.ldaux + an);
-#pragma unroll
-          for (int q = 0; q < (REG_PF ? 8 : 1); ++q)
-            if (an + q * 8 < p.N) na[q] = __ldg(ap + q);
-        }
-        if (EPI == EPI_BIAS_DROP_RESID && p.dmask != nullptr) {
-          const uint32_t* mp = p.dmask + static_cast<int64_t>(pm_) * p.ldmask + (an >> 5);
-          if (an < p.N) nm[0] = __ldg(mp);
-          if (an + 32 < p.N) nm[1] = __ldg(mp + 1);
-        }
-      }
-    };
-    if (REG_PF) reg_prefetch(0);
     for (int u = u_first; u < units; u += u_step) {
       const int t = u / p.splits;
       const int m0 = (MC ? 2 * (t / tiles_n) + crank : (t / tiles_n)) * BM, n0 = (t % tiles_n) * BN;
@@ -331,13 +299,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t pk[32];                       // this thread's 64 output columns, packed bf16 pairs
           uint32_t hk[EPI == EPI_BIAS_GELU ? 32 : 1];
           const uint8_t* auxrow = nullptr;
-          uint4 ca[REG_PF ? 8 : 1];
-          uint32_t cm[2] = {nm[0], nm[1]};
-          if (REG_PF) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) ca[q % (REG_PF ? 8 : 1)] = na[q % (REG_PF ? 8 : 1)];
-            reg_prefetch(gslice + 1);
-          }
           if (C::AUX_TMA) {
             // the slice after this one starts streaming in now (its buffer was last read two slices ago, and every
             // thread of the set has passed that slice's staging barriers since)
@@ -381,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (EPI == EPI_BIAS_DROP_RESID) {
               if (p.dmask != nullptr && row_ok && n < p.N) {
-                const uint32_t bits = REG_PF ? cm[h] : __ldg(p.dmask + static_cast<int64_t>(m) * p.ldmask + (n >> 5));
+                const uint32_t bits = __ldg(p.dmask + static_cast<int64_t>(m) * p.ldmask + (n >> 5));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * p.dscale : 0.0f;
               }
@@ -394,9 +355,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
                     a4[q] = *reinterpret_cast<const uint4*>(auxrow + (((h * 4 + q) ^ (row & 7)) * 16));
-                } else if (REG_PF) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) a4[q] = ca[(h * 4 + q) % (REG_PF ? 8 : 1)];
                 } else {
                   const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(m) * p.ldaux + n);
 #pragma unroll

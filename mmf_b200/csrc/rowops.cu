@@ -834,8 +834,10 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   if (a.drop_mask && !a.dz) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dropout mask given without dz");
   const int nv_ = (a.H + 255) / 256;
   // read per call (not cached) so that one test process can run both variants back to back
+  // default: the single-pass "lean" kernel (74 us against 103 us for the rows + cols pair and 79 us for the tile variant
+  // at [37848, 768], profiles/r2_kbench_before.json); MMFB_LN_BWD=pair / tile select the others for A/B runs
   const char* lean_env = getenv("MMFB_LN_BWD");
-  const bool lean = lean_env != nullptr && lean_env[0] == 'l';
+  const bool lean = lean_env == nullptr || lean_env[0] == 'l';
   const bool tile = lean_env != nullptr && lean_env[0] == 't';
   if (tile && nv_ <= 4) {
     const int64_t n_steps = (static_cast<int64_t>(a.M) + 3) / 4;

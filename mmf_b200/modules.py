@@ -50,21 +50,12 @@ def _check_erf_gelu(layer):
 _SEED_COUNTER = [0]
 
 
-_ASYNC_DROPOUT = os.environ.get("MMFB_DROPOUT_ASYNC", "0") not in ("", "0")
-_RNG_STREAMS = {}
-
-
 def _fresh_dropout_state(prefetchable=False):
     """One Philox stream per forward, derived from torch's seed so `torch.manual_seed` makes runs repeatable.
-    `prefetchable`: the caller announces its sites one layer ahead (EncoderRunner); with MMFB_DROPOUT_ASYNC=1 it then gets
-    the side-stream generator (staged, see engine.AsyncDropoutState)."""
+    (A side-stream generator that drew the next layer's bits ahead was measured in round 2 and dropped: +0.2 %, i.e. noise -
+    the persistent GEMMs leave no SM resources for a concurrent kernel; profiles/r2_ab_sweep_first.txt.)"""
     _SEED_COUNTER[0] += 1
     seed = torch.initial_seed() * 1000003 + _SEED_COUNTER[0]
-    if prefetchable and _ASYNC_DROPOUT and torch.cuda.is_available():
-        dev = torch.cuda.current_device()
-        if dev not in _RNG_STREAMS:
-            _RNG_STREAMS[dev] = torch.cuda.Stream(device=dev)
-        return E.AsyncDropoutState(seed, _RNG_STREAMS[dev])
     return E.DropoutState(seed)
 
 
@@ -115,19 +106,10 @@ class EncoderRunner:
         ds = _fresh_dropout_state(prefetchable=True) if training else None
         last_layer = len(self.layers) if last_layer is None else last_layer
         hiddens = []
-        ahead = isinstance(ds, E.AsyncDropoutState)
-
-        def sites(i):      # the three dropout sites of layer i, in the order bert_layer_fwd draws them
-            pa_, ph_ = self._probs(self.layers[i])
-            return [((B, self.weights[i].heads, S), S, pa_), ((B * S,), H, ph_), ((B * S,), H, ph_)]
-        if ahead and first_layer < last_layer:
-            ds.prefetch(sites(first_layer), x.device)
         for i in range(first_layer, last_layer):
             m = self.layers[i]
             pa, ph = self._probs(m) if training else (0.0, 0.0)
             hiddens.append(h)
-            if ahead and i + 1 < last_layer:
-                ds.prefetch(sites(i + 1), x.device)      # generated while layer i runs
             h, s = self._fwd(h, add_mask, self.weights[i], B, S, pa, ph, ds)
             saved.append(s if need_grad else None)
         return h, saved, hiddens

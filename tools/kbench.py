@@ -105,13 +105,12 @@ def main():
         f_fwd, f_bwd = 4.0 * B * heads * S * S * d, 10.0 * B * heads * S * S * d
         b_fwd = M * 3 * H * 2 + M * H * 2 + M * H * 4 + bits.numel() * 4
         b_bwd = M * 3 * H * 2 * 2 + M * H * 2 + bits.numel() * 4
-        for tag, env in (("default", {}), ("MMFB_ATTN_FWD=2", {"MMFB_ATTN_FWD": "2"})):
+        for tag, env in (("default", {}),):
             timeit("attention_fwd [%s]" % tag, lambda: F.attention_fwd(q, k, v, B, heads, S, S, mask, bits, 1 / 0.9, save_fp32=True),
                    f_fwd, b_fwd, env)
         ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, S, S, mask, bits, 1 / 0.9, save_fp32=True)
         dq = torch.empty_like(qkv)
-        for tag, env in (("default fused", {}), ("MMFB_ATTN_BWD_OVERLAP=1", {"MMFB_ATTN_BWD_OVERLAP": "1"}),
-                         ("MMFB_ATTN_BWD=16", {"MMFB_ATTN_BWD": "16"})):
+        for tag, env in (("default fused, 16 warps", {}), ("MMFB_ATTN_BWD=8", {"MMFB_ATTN_BWD": "8"})):
             timeit("attention_bwd (+delta) [%s]" % tag,
                    lambda: F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, S, S, mask, bits, 1 / 0.9, dq=dq[:, :H],
                                            dk=dq[:, H:2 * H], dv=dq[:, 2 * H:], ctx32=c32), f_bwd, b_bwd, env)
@@ -126,7 +125,7 @@ def main():
         bits = F.dropout_bits((M,), H, 0.1, 1, 0, dev)
         dg, db_, dbias = (torch.zeros(H, device=dev) for _ in range(3))
         nb = M * (8.0 * H + H / 8.0 + 8.0)
-        for tag, env in (("default rows+cols", {}), ("MMFB_LN_BWD=lean", {"MMFB_LN_BWD": "lean"}), ("MMFB_LN_BWD=tile", {"MMFB_LN_BWD": "tile"})):
+        for tag, env in (("default single pass", {}), ("MMFB_LN_BWD=pair", {"MMFB_LN_BWD": "pair"}), ("MMFB_LN_BWD=tile", {"MMFB_LN_BWD": "tile"})):
             timeit("layernorm_bwd +dropout +dgamma/dbeta/dbias [%s]" % tag,
                    lambda: F.layernorm_bwd(dx, y, mean, rstd, g, dg, db_, dbias=dbias, drop_mask=bits, drop_scale=1 / 0.9), None, nb, env)
         timeit("layernorm_fwd", lambda: F.layernorm_fwd(y, g, torch.zeros_like(g)), None, M * (4.0 * H + 8))

@@ -58,9 +58,9 @@ work = [
     lambda: F.gemm(x, w_2, b_mn=True, epi=lib.EPI_GELU_BWD, aux=xi),
     lambda: F.gemm(xi, w_2, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9),
     lambda: F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_fp32=True),
-    lambda: attn_bwd({}),
+    lambda: attn_bwd({"MMFB_ATTN_BWD": "8"}),
     lambda: attn_bwd({"MMFB_ATTN_BWD": "16"}),
-    lambda: ln_bwd(None),
+    lambda: ln_bwd("pair"),
     lambda: ln_bwd("lean"),
     lambda: F.dropout_bits((B, heads, S), S, 0.1, 7, 0, dev),
 ]
