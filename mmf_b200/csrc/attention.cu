@@ -53,6 +53,8 @@ template <int D>
 __global__ void __launch_bounds__(288, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnFwdDev p) {
+  griddep_launch();
+  griddep_wait();
   constexpr int DC = D / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
@@ -349,6 +351,8 @@ template <int D, bool ROWS_ARE_Q, bool DROP, int CB>
 __global__ void __launch_bounds__(160, (CB == 64) ? 2 : 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRg,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCg, AttnBwdDev p) {
+  griddep_launch();
+  griddep_wait();
   constexpr int DC = D / 64;
   constexpr int TILE = DC * 16384;   // one [128 x D] bf16 resident-operand tile
   constexpr int CTILE = DC * CB * 128;  // one [CB x D] bf16 looped-operand tile
@@ -664,6 +668,8 @@ __global__ void __launch_bounds__(288, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       AttnBwdFusedDev p) {
+  griddep_launch();
+  griddep_wait();
   constexpr int D = 64;
   constexpr int TILE = 16384;
   extern __shared__ uint8_t smem_raw[];
@@ -944,6 +950,8 @@ __global__ void __launch_bounds__(544, 1)
 attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         AttnBwdFusedDev p) {
+  griddep_launch();
+  griddep_wait();
   constexpr int D = 64;
   constexpr int TILE = 16384;
   extern __shared__ uint8_t smem_raw[];
@@ -1209,6 +1217,8 @@ attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
                                   int64_t ld_o, const float* __restrict__ O32, float* __restrict__ delta, int B, int H,
                                   int Sq, int D) {
+  griddep_launch();
+  griddep_wait();
   const int64_t tok = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= static_cast<int64_t>(B) * Sq) return;
@@ -1288,7 +1298,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     smem_set = smem;
   }
   dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
-  kern<<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
+  MMFB_LAUNCH(kern, grid, 288, smem, stream, tmQ, tmK, tmV, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -1325,7 +1335,7 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     const int64_t warps = static_cast<int64_t>(a.B) * a.Sq;
     const int threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
-    attn_delta_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+    MMFB_LAUNCH(attn_delta_kernel, static_cast<unsigned>(blocks), threads, 0, stream, 
         reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, a.ctx32, a.delta,
         a.B, a.heads, a.Sq, D);
     count_launch();
@@ -1366,10 +1376,10 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
         if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(fused16) smem attr: %s", cudaGetErrorString(e));
         w16_attr = true;
       }
-      if (f.dmask != nullptr) attn_bwd_fused16_kernel<true><<<grid, 544, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
-      else attn_bwd_fused16_kernel<false><<<grid, 544, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
-    } else if (f.dmask != nullptr) attn_bwd_fused_kernel<true><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
-    else attn_bwd_fused_kernel<false><<<grid, 288, smem, stream>>>(tmQ, tmdO, tmK, tmV, f);
+      if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_fused16_kernel<true>, grid, 544, smem, stream, tmQ, tmdO, tmK, tmV, f);
+      else MMFB_LAUNCH(attn_bwd_fused16_kernel<false>, grid, 544, smem, stream, tmQ, tmdO, tmK, tmV, f);
+    } else if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_fused_kernel<true>, grid, 288, smem, stream, tmQ, tmdO, tmK, tmV, f);
+    else MMFB_LAUNCH(attn_bwd_fused_kernel<false>, grid, 288, smem, stream, tmQ, tmdO, tmK, tmV, f);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd_fused launch: %s", cudaGetErrorString(e));
@@ -1396,16 +1406,16 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   {
     p.out0 = reinterpret_cast<bf16*>(a.dq); p.ld0 = a.ld_dq; p.out1 = nullptr; p.ld1 = 0;
     dim3 grid((a.Sq + 127) / 128, a.heads, a.B);
-    if (p.dmask != nullptr) attn_bwd_kernel<D, true, true, CB><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmKc, tmVc, p);
-    else attn_bwd_kernel<D, true, false, CB><<<grid, 160, smem, stream>>>(tmQ, tmdO, tmKc, tmVc, p);
+    if (p.dmask != nullptr) MMFB_LAUNCH((attn_bwd_kernel<D, true, true, CB>), grid, 160, smem, stream, tmQ, tmdO, tmKc, tmVc, p);
+    else MMFB_LAUNCH((attn_bwd_kernel<D, true, false, CB>), grid, 160, smem, stream, tmQ, tmdO, tmKc, tmVc, p);
     count_launch();
   }
   {
     p.out0 = reinterpret_cast<bf16*>(a.dk); p.ld0 = a.ld_dk;
     p.out1 = reinterpret_cast<bf16*>(a.dv); p.ld1 = a.ld_dv;
     dim3 grid((a.Skv + 127) / 128, a.heads, a.B);
-    if (p.dmask != nullptr) attn_bwd_kernel<D, false, true, CB><<<grid, 160, smem, stream>>>(tmK, tmV, tmQc, tmdOc, p);
-    else attn_bwd_kernel<D, false, false, CB><<<grid, 160, smem, stream>>>(tmK, tmV, tmQc, tmdOc, p);
+    if (p.dmask != nullptr) MMFB_LAUNCH((attn_bwd_kernel<D, false, true, CB>), grid, 160, smem, stream, tmK, tmV, tmQc, tmdOc, p);
+    else MMFB_LAUNCH((attn_bwd_kernel<D, false, false, CB>), grid, 160, smem, stream, tmK, tmV, tmQc, tmdOc, p);
     count_launch();
   }
   cudaError_t e = cudaGetLastError();

@@ -33,6 +33,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 __global__ void __launch_bounds__(256)
 ce_rows_kernel(bf16* __restrict__ z, int64_t ldz, const int64_t* __restrict__ labels, int64_t ignore_index, int M, int V,
                float grad_scale, float* __restrict__ loss_sum, float* __restrict__ row_loss) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[8];
   const int row = blockIdx.x;
   if (row >= M) return;
@@ -97,7 +99,7 @@ int ce_rows(void* logits, int64_t ldl, const int64_t* labels, int64_t ignore_ind
             float* loss_sum, float* row_loss, cudaStream_t s) {
   if (M <= 0 || V <= 0 || (V % 8) || (ldl % 8)) return set_error(MMFB_ERR_ARG, "ce_rows: bad shape %dx%d (ld %lld)", M, V, (long long)ldl);
   if (reinterpret_cast<uintptr_t>(logits) & 15) return set_error(MMFB_ERR_ARG, "ce_rows: logits must be 16-byte aligned");
-  ce_rows_kernel<<<M, 256, 0, s>>>(reinterpret_cast<bf16*>(logits), ldl, labels, ignore_index, M, V, grad_scale, loss_sum, row_loss);
+  MMFB_LAUNCH(ce_rows_kernel, M, 256, 0, s, reinterpret_cast<bf16*>(logits), ldl, labels, ignore_index, M, V, grad_scale, loss_sum, row_loss);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "ce_rows launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -40,6 +40,16 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // --------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel of the library lets the NEXT kernel of the stream start launching as soon
+// as all of its own CTAs have started (griddep_launch at the top), and waits for the PREVIOUS kernel to have completed and
+// flushed its memory before it touches global data (griddep_wait after its own set-up: barrier init, TMEM allocation,
+// descriptor prefetch).  The launch latency and the prologue of kernel n+1 overlap the tail of kernel n; both
+// instructions are no-ops when the kernel was launched without the attribute (MMFB_PDL=0).
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// --------------------------------------------------------------------------------------
 // mbarrier
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -73,13 +83,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Wait with a watchdog: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
+// The spin loop is kept to three instructions per failed probe (try_wait itself suspends the warp in hardware for a
+// while before it returns false): the clock is read only every 2^16 probes.  The round-1 loop read the clock on every
+// probe, and ncu showed 27 % of the attention forward's issued warp-instructions in it (CS2R / ISETP / BRA), taken from
+// the second CTA on the SM.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("mmfb: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+  long long t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 0xFFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+        printf("mmfb: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }

@@ -50,7 +50,11 @@ struct GemmDev {
   float dscale;          // 1/(1-p)
 };
 
-constexpr bool epi_uses_aux(int epi) { return epi == EPI_BIAS_DROP_RESID || epi == EPI_GELU_BWD || epi == EPI_ADD_AUX; }
+// internal epilogue id: EPI_BIAS_DROP_RESID with the residual tile staged by TMA (chosen by the dispatcher for short-K
+// GEMMs, where the mainloop is too short to hide the epilogue's strided global loads of the residual)
+constexpr int EPI_BIAS_DROP_RESID_T = 32;
+constexpr bool is_drop_resid(int epi) { return epi == EPI_BIAS_DROP_RESID || epi == EPI_BIAS_DROP_RESID_T; }
+constexpr bool epi_uses_aux(int epi) { return is_drop_resid(epi) || epi == EPI_GELU_BWD || epi == EPI_ADD_AUX; }
 
 template <int BN, bool MC = false, int EPI = EPI_BIAS>
 struct Cfg {
@@ -60,7 +64,10 @@ struct Cfg {
   // Measured (profiles/README.md): a clear win for the GELU' dgrad (K = hidden: short mainloop, heavy epilogue: 107 -> 79 us);
   // for the residual epilogues of the K = 3072 / 2304 GEMMs the ring shrinking from 6 to 4 stages costs more than
   // the staging saves, so those keep the direct 16-byte global loads.
-  static constexpr bool AUX_TMA = MC && EPI == EPI_GELU_BWD;
+  // Round 2 (ncu source view of the attention out-projection, K = N = 768: 51 % of the stall samples on the first use of the
+  // residual's LDG.128 / the mask word, tensor pipe 40 % active): the short-K residual epilogue stages its tile the same
+  // way (EPI_BIAS_DROP_RESID_T); 4 stages are plenty for 12 k-blocks.
+  static constexpr bool AUX_TMA = MC && (EPI == EPI_GELU_BWD || EPI == EPI_BIAS_DROP_RESID_T);
   static constexpr int AUX_BYTES = AUX_TMA ? 4 * STG_BYTES : 0;
   // MC (CTA pair, 2-SM MMA): each CTA stages only half of the B tile -> 32 KB per stage, deeper ring
   static constexpr int STAGES = MC ? (AUX_TMA ? ((BN == 256) ? 4 : 5) : ((BN == 256) ? 6 : 8)) : ((BN == 256) ? 4 : 6);
@@ -105,6 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* auxfull = bars + 2 * STAGES + 4;  // [2 sets][2 buffers]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
+  griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
@@ -142,6 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (MC) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();        // operands / aux / bias of this GEMM may come from the kernel that is still finishing
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -299,6 +308,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t pk[32];                       // this thread's 64 output columns, packed bf16 pairs
           uint32_t hk[EPI == EPI_BIAS_GELU ? 32 : 1];
           const uint8_t* auxrow = nullptr;
+          uint32_t mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+          if (is_drop_resid(EPI) && p.dmask != nullptr && row_ok) {
+            // the two keep-bit words of this slice are fetched before the accumulator loads, not in the middle of the math
+            const int ns = n0 + sl * 64;
+            const uint32_t* mp = p.dmask + static_cast<int64_t>(m) * p.ldmask + (ns >> 5);
+            if (ns < p.N) mbits[0] = __ldg(mp);
+            if (ns + 32 < p.N) mbits[1] = __ldg(mp + 1);
+          }
           if (C::AUX_TMA) {
             // the slice after this one starts streaming in now (its buffer was last read two slices ago, and every
             // thread of the set has passed that slice's staging barriers since)
@@ -320,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_DROP_RESID || EPI == EPI_BIAS_RELU) {
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || is_drop_resid(EPI) || EPI == EPI_BIAS_RELU) {
               if (p.bias != nullptr && n < p.N) {
                 const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n);
 #pragma unroll
@@ -340,14 +357,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
-            if (EPI == EPI_BIAS_DROP_RESID) {
+            if (is_drop_resid(EPI)) {
               if (p.dmask != nullptr && row_ok && n < p.N) {
-                const uint32_t bits = __ldg(p.dmask + static_cast<int64_t>(m) * p.ldmask + (n >> 5));
+                const uint32_t bits = mbits[h];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * p.dscale : 0.0f;
               }
             }
-            if (EPI == EPI_BIAS_DROP_RESID || EPI == EPI_GELU_BWD || EPI == EPI_ADD_AUX) {
+            if (is_drop_resid(EPI) || EPI == EPI_GELU_BWD || EPI == EPI_ADD_AUX) {
               if (C::AUX_TMA || (p.aux != nullptr && row_ok && n < p.N)) {
                 uint4 a4[4];
                 if (C::AUX_TMA) {
@@ -505,23 +522,12 @@ static int launch(const mmfb_gemm_args& a, cudaStream_t stream) {
     const int pairs = ((tiles_m + 1) / 2) * ((a.N + BN - 1) / BN) * p.splits;
     const int max_clusters = num_sms() / 2;
     const int clusters = pairs < max_clusters ? pairs : max_clusters;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmAux, p);
+    e = launch_k(kern, dim3(2 * clusters), dim3(NUM_THREADS), static_cast<size_t>(C::SMEM_BYTES), stream, 2, tmA, tmB, tmC, tmC2,
+                 tmAux, p);
   } else {
     const int tiles = tiles_m * ((a.N + BN - 1) / BN) * p.splits;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, tmAux, p);
+    MMFB_LAUNCH(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, tmA, tmB, tmC, tmC2, tmAux, p);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
@@ -535,7 +541,9 @@ static int dispatch(const mmfb_gemm_args& a, cudaStream_t s) {
   switch (key) {
     case 0 + EPI_BIAS: return launch<BN, false, false, EPI_BIAS, MC>(a, s);
     case 0 + EPI_BIAS_GELU: return launch<BN, false, false, EPI_BIAS_GELU, MC>(a, s);
-    case 0 + EPI_BIAS_DROP_RESID: return launch<BN, false, false, EPI_BIAS_DROP_RESID, MC>(a, s);
+    case 0 + EPI_BIAS_DROP_RESID:
+      if (MC && a.K <= 1024 && a.aux != nullptr) return launch<BN, false, false, EPI_BIAS_DROP_RESID_T, MC>(a, s);
+      return launch<BN, false, false, EPI_BIAS_DROP_RESID, MC>(a, s);
     case 0 + EPI_BIAS_RELU: return launch<BN, false, false, EPI_BIAS_RELU, MC>(a, s);
     case 10 + EPI_BIAS: return launch<BN, false, true, EPI_BIAS, MC>(a, s);
     case 10 + EPI_GELU_BWD: return launch<BN, false, true, EPI_GELU_BWD, MC>(a, s);

@@ -16,6 +16,8 @@ struct AdamWDev {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 adamw_kernel(const __grid_constant__ AdamWDev a) {
+  griddep_launch();
+  griddep_wait();
   const int64_t blk = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // 8-element block
   const int64_t i = blk * 8;
   if (i >= a.n) return;
@@ -84,8 +86,8 @@ int adamw(const mmfb_adamw_args& a, cudaStream_t s) {
   d.b1 = a.beta1; d.b2 = a.beta2; d.eps = a.eps; d.gscale = a.grad_scale;
   const int64_t blocks8 = a.n / 8;
   const unsigned grid = static_cast<unsigned>((blocks8 + 255) / 256);
-  if (a.mode == 0) adamw_kernel<0><<<grid, 256, 0, s>>>(d);
-  else adamw_kernel<1><<<grid, 256, 0, s>>>(d);
+  if (a.mode == 0) MMFB_LAUNCH(adamw_kernel<0>, grid, 256, 0, s, d);
+  else MMFB_LAUNCH(adamw_kernel<1>, grid, 256, 0, s, d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "adamw launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -94,6 +96,8 @@ int adamw(const mmfb_adamw_args& a, cudaStream_t s) {
 
 // du = dh * GELU'(u), 16-byte vectors (staged with the MLM head)
 __global__ void gelu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ u, bf16* __restrict__ du, int64_t n) {
+  griddep_launch();
+  griddep_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const uint4 a = *reinterpret_cast<const uint4*>(dh + i);
@@ -117,7 +121,7 @@ int gelu_bwd(const void* dh, const void* u, void* du, int64_t n, cudaStream_t s)
   if ((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(du)) & 15)
     return set_error(MMFB_ERR_ARG, "gelu_bwd: buffers must be 16-byte aligned");
   const int64_t thr = (n + 7) / 8;
-  gelu_bwd_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)dh, (const bf16*)u, (bf16*)du, n);
+  MMFB_LAUNCH(gelu_bwd_kernel, static_cast<unsigned>((thr + 255) / 256), 256, 0, s, (const bf16*)dh, (const bf16*)u, (bf16*)du, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "gelu_bwd launch: %s", cudaGetErrorString(e));
   count_launch();

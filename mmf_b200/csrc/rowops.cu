@@ -40,6 +40,8 @@ ln_fwd_kernel(const bf16* __restrict__ y, int64_t ldy, const bf16* __restrict__ 
               const bf16* __restrict__ beta, bf16* __restrict__ x, int64_t ldx, float* __restrict__ mean,
               float* __restrict__ rstd, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale, int M,
               int H, float eps) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -104,6 +106,8 @@ ln_bwd_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict_
               const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
               bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[ROW_WARPS][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[NV][8], ab[NV][8], az[NV][8];
@@ -206,6 +210,8 @@ ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
                    const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
                    bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[ROW_WARPS][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[NV][8], ab[NV][8], az[NV][8];
@@ -320,6 +326,8 @@ ln_bwd_tile_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
                    const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
                    bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   constexpr int RB = 4;
   __shared__ float sStat[2][G][WPR][RB][2];
   __shared__ float sRed[G][WPR * 256];
@@ -449,6 +457,8 @@ ln_bwd_rows_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
                    const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
                    bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
                    int M, int H) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -508,6 +518,8 @@ ln_bwd_cols_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
                    const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const bf16* __restrict__ dz, int64_t lddz,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -557,6 +569,8 @@ ln_bwd_cols_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ X, int64_t ldx, float* __restrict__ out, int M, int N) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -586,6 +600,8 @@ colsum_kernel(const bf16* __restrict__ X, int64_t ldx, float* __restrict__ out, 
 // ----------------------------------------------------------------------------------------------
 __global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t nwords, uint64_t seed, uint64_t offset,
                                     uint32_t thresh16) {
+  griddep_launch();
+  griddep_wait();
   const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (w >= nwords) return;
   uint32_t bits = 0;
@@ -613,6 +629,8 @@ struct ComposeDev {
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 compose_kernel(ComposeDev c, bf16* __restrict__ y, int64_t ldy, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -657,6 +675,8 @@ struct ScatterDev {
 // backward of compose: dsrc_k[s_k[r]] = dy[r]  (rows are unique) ; dtab_k[i_k[r]] += dy[r]  (fp32 atomics)
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 scatter_kernel(ScatterDev c, const bf16* __restrict__ dy, int64_t lddy, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -692,6 +712,8 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 scatter_sorted_kernel(const bf16* __restrict__ dy, int64_t lddy, const int32_t* __restrict__ order,
                       const int32_t* __restrict__ sorted_idx, float* __restrict__ dtab, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t w = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + (threadIdx.x >> 5);
   const int64_t p0 = w * 32;
@@ -737,6 +759,8 @@ scatter_sorted_kernel(const bf16* __restrict__ dy, int64_t lddy, const int32_t* 
 
 // backward of the ReLU epilogue: dz = (y > 0) ? dy : 0, 16-byte vectors
 __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ dz, int64_t n) {
+  griddep_launch();
+  griddep_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float a[8], b[8];
@@ -752,6 +776,8 @@ __global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
 
 // out = a + b (bf16, 16-byte vectors): the residual-gradient join of the pre-LN (ViT) layer, mmf/modules/vit.py:96-108
 __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int64_t n) {
+  griddep_launch();
+  griddep_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float x[8], y[8];
@@ -769,6 +795,8 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
 // (whose backward kernel otherwise applies the mask): one warp per row, 8 columns per lane and step
 __global__ void dropout_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const uint32_t* __restrict__ bits, int64_t ldm,
                                      float scale, bf16* __restrict__ out, int64_t ldo, int M, int H) {
+  griddep_launch();
+  griddep_wait();
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -785,6 +813,8 @@ __global__ void dropout_apply_kernel(const bf16* __restrict__ x, int64_t ldx, co
 
 // fp32 -> bf16 cast of the flat parameter buffer (done every forward, like autocast does)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  griddep_launch();
+  griddep_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(in + i);
@@ -818,7 +848,7 @@ int ln_fwd(const mmfb_ln_args& a, cudaStream_t s) {
   if (rc) return rc;
   if (!a.y || !a.gamma || !a.beta || !a.x) return set_error(MMFB_ERR_ARG, "layernorm_fwd: null pointer");
 #define LN_FWD(NV)                                                                                         \
-  ln_fwd_kernel<NV><<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(                          \
+  MMFB_LAUNCH(ln_fwd_kernel<NV>, (a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s,                           \
       (const bf16*)a.y, a.ldy, (const bf16*)a.gamma, (const bf16*)a.beta, (bf16*)a.x, a.ldx, a.mean, a.rstd, \
       a.drop_mask, a.ldmask, a.drop_scale, a.M, a.H, a.eps)
   const int nv = (a.H + 255) / 256;
@@ -847,12 +877,12 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
     int grid = static_cast<int>(want < num_sms() ? want : num_sms());                                                  \
     if (grid < 1) grid = 1;                                                                                            \
     if (a.dx2 != nullptr)                                                                                              \
-      ln_bwd_tile_kernel<WPR, G, true><<<grid, (WPR) * (G) * 32, 0, s>>>(                                              \
+      MMFB_LAUNCH((ln_bwd_tile_kernel<WPR, G, true>), grid, (WPR) * (G) * 32, 0, s,                                               \
           (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy, a.mean, a.rstd,             \
           (const bf16*)a.gamma, (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, a.drop_scale,         \
           a.dgamma, a.dbeta, a.dbias, a.M, a.H);                                                                       \
     else                                                                                                               \
-      ln_bwd_tile_kernel<WPR, G, false><<<grid, (WPR) * (G) * 32, 0, s>>>(                                             \
+      MMFB_LAUNCH((ln_bwd_tile_kernel<WPR, G, false>), grid, (WPR) * (G) * 32, 0, s,                                              \
           (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy, a.mean, a.rstd,             \
           (const bf16*)a.gamma, (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, a.drop_scale,         \
           a.dgamma, a.dbeta, a.dbias, a.M, a.H);                                                                       \
@@ -866,7 +896,7 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
     const int cap = num_sms() * 2;      // two resident blocks per SM, rows strided over them
     if (grid > cap) grid = cap;
 #define LN_LEAN(NV)                                                                                                  \
-  ln_bwd_lean_kernel<NV><<<grid, ROW_WARPS * 32, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
+  MMFB_LAUNCH(ln_bwd_lean_kernel<NV>, grid, ROW_WARPS * 32, 0, s, (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
                                                          (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
                                                          (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask,         \
                                                          a.ldmask, a.drop_scale, a.dgamma, a.dbeta, a.dbias, a.M, a.H)
@@ -881,7 +911,7 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
     const bool need_dz_buf = (a.drop_mask != nullptr) || (a.dz != nullptr && a.dz != a.dy);
     const int rgrid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
 #define LN_ROWS(NV)                                                                                              \
-  ln_bwd_rows_kernel<NV><<<rgrid, ROW_WARPS * 32, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, \
+  MMFB_LAUNCH(ln_bwd_rows_kernel<NV>, rgrid, ROW_WARPS * 32, 0, s, (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, \
                                                           (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
                                                           (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, \
                                                           a.drop_scale, a.M, a.H)
@@ -898,7 +928,7 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
       const int cap2 = (num_sms() * 4 + cgrid.x - 1) / cgrid.x;
       cgrid.y = rb < cap2 ? rb : cap2;
       if (cgrid.y < 1) cgrid.y = 1;
-      ln_bwd_cols_kernel<<<cgrid, 256, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy,
+      MMFB_LAUNCH(ln_bwd_cols_kernel, cgrid, 256, 0, s, (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy,
                                                a.mean, a.rstd, (const bf16*)dzp, lddz, a.dgamma, a.dbeta, a.dbias, a.M, a.H);
       return launch_ok("layernorm_bwd(cols)");
     }
@@ -908,7 +938,7 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   const int cap = num_sms() * 2;
   if (grid > cap) grid = cap;
 #define LN_BWD(NV)                                                                                              \
-  ln_bwd_kernel<NV><<<grid, ROW_WARPS * 32, 0, s>>>((const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
+  MMFB_LAUNCH(ln_bwd_kernel<NV>, grid, ROW_WARPS * 32, 0, s, (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
                                                     (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
                                                     (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask,         \
                                                     a.ldmask, a.drop_scale, a.dgamma, a.dbeta, a.dbias, a.M, a.H)
@@ -925,7 +955,7 @@ int colsum(const void* X, int64_t ldx, float* out, int M, int N, cudaStream_t s)
   const int cap = (num_sms() * 4 + grid.x - 1) / grid.x;
   grid.y = rows_blocks < cap ? rows_blocks : cap;
   if (grid.y < 1) grid.y = 1;
-  colsum_kernel<<<grid, 256, 0, s>>>((const bf16*)X, ldx, out, M, N);
+  MMFB_LAUNCH(colsum_kernel, grid, 256, 0, s, (const bf16*)X, ldx, out, M, N);
   return launch_ok("colsum");
 }
 
@@ -933,7 +963,7 @@ int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, 
   if (nwords <= 0) return set_error(MMFB_ERR_ARG, "dropout_bits: empty");
   if (!(p >= 0.0f && p < 1.0f)) return set_error(MMFB_ERR_ARG, "dropout_bits: p must be in [0,1), got %f", p);
   const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  dropout_bits_kernel<<<static_cast<unsigned>((nwords + 255) / 256), 256, 0, s>>>(out, nwords, seed, offset, thresh);
+  MMFB_LAUNCH(dropout_bits_kernel, static_cast<unsigned>((nwords + 255) / 256), 256, 0, s, out, nwords, seed, offset, thresh);
   return launch_ok("dropout_bits");
 }
 
@@ -944,7 +974,7 @@ int compose(const mmfb_compose_args& a, cudaStream_t s) {
   ComposeDev c;
   for (int k = 0; k < 2; ++k) { c.src[k] = (const bf16*)a.src[k]; c.ldsrc[k] = a.ldsrc[k]; c.srow[k] = a.src_row[k]; }
   for (int k = 0; k < 3; ++k) { c.tab[k] = (const bf16*)a.tab[k]; c.tidx[k] = a.tab_idx[k]; }
-  compose_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(c, (bf16*)a.y, a.ldy, a.M, a.H);
+  MMFB_LAUNCH(compose_kernel, (a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s, c, (bf16*)a.y, a.ldy, a.M, a.H);
   return launch_ok("embed_compose");
 }
 
@@ -955,7 +985,7 @@ int scatter(const mmfb_scatter_args& a, cudaStream_t s) {
   ScatterDev c;
   for (int k = 0; k < 2; ++k) { c.dsrc[k] = (bf16*)a.dsrc[k]; c.ldsrc[k] = a.ldsrc[k]; c.srow[k] = a.src_row[k]; }
   for (int k = 0; k < 3; ++k) { c.dtab[k] = a.dtab[k]; c.tidx[k] = a.tab_idx[k]; }
-  scatter_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(c, (const bf16*)a.dy, a.lddy, a.M, a.H);
+  MMFB_LAUNCH(scatter_kernel, (a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s, c, (const bf16*)a.dy, a.lddy, a.M, a.H);
   return launch_ok("embed_scatter");
 }
 
@@ -967,7 +997,7 @@ int scatter_sorted(const void* dy, int64_t lddy, const int32_t* order, const int
   const int warps = (M + 31) / 32;
   const int grid = (warps + ROW_WARPS - 1) / ROW_WARPS;
   const int nv = (H + 255) / 256;
-#define SS(NV) scatter_sorted_kernel<NV><<<grid, ROW_WARPS * 32, 0, s>>>((const bf16*)dy, lddy, order, sorted_idx, dtab, M, H)
+#define SS(NV) MMFB_LAUNCH(scatter_sorted_kernel<NV>, grid, ROW_WARPS * 32, 0, s, (const bf16*)dy, lddy, order, sorted_idx, dtab, M, H)
   if (nv <= 1) SS(1); else if (nv == 2) SS(2); else if (nv == 3) SS(3); else SS(4);
 #undef SS
   return launch_ok("embed_scatter_sorted");
@@ -978,7 +1008,7 @@ int relu_bwd(const void* dy, const void* y, void* dz, int64_t n, cudaStream_t s)
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dz)) & 15)
     return set_error(MMFB_ERR_ARG, "relu_bwd: buffers must be 16-byte aligned");
   const int64_t thr = (n + 7) / 8;
-  relu_bwd_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)y, (bf16*)dz, n);
+  MMFB_LAUNCH(relu_bwd_kernel, static_cast<unsigned>((thr + 255) / 256), 256, 0, s, (const bf16*)dy, (const bf16*)y, (bf16*)dz, n);
   return launch_ok("relu_bwd");
 }
 
@@ -987,7 +1017,7 @@ int add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s)
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(MMFB_ERR_ARG, "add_bf16: buffers must be 16-byte aligned");
   const int64_t thr = (n + 7) / 8;
-  add_bf16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+  MMFB_LAUNCH(add_bf16_kernel, static_cast<unsigned>((thr + 255) / 256), 256, 0, s, (const bf16*)a, (const bf16*)b, (bf16*)out, n);
   return launch_ok("add_bf16");
 }
 
@@ -996,7 +1026,7 @@ int dropout_apply(const void* x, int64_t ldx, const uint32_t* bits, int64_t ldm,
   int rc = check_rows(M, H, "dropout_apply");
   if (rc) return rc;
   const int64_t threads = static_cast<int64_t>(M) * 32;
-  dropout_apply_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>((const bf16*)x, ldx, bits, ldm, scale,
+  MMFB_LAUNCH(dropout_apply_kernel, static_cast<unsigned>((threads + 255) / 256), 256, 0, s, (const bf16*)x, ldx, bits, ldm, scale,
                                                                                    (bf16*)out, ldo, M, H);
   return launch_ok("dropout_apply");
 }
@@ -1006,7 +1036,7 @@ int cast_params(const float* in, void* out, int64_t n, cudaStream_t s) {
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(MMFB_ERR_ARG, "cast: buffers must be 16-byte aligned");
   const int64_t thr = (n + 7) / 8;
-  cast_f32_bf16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, s>>>(in, (bf16*)out, n);
+  MMFB_LAUNCH(cast_f32_bf16_kernel, static_cast<unsigned>((thr + 255) / 256), 256, 0, s, in, (bf16*)out, n);
   return launch_ok("cast_f32_bf16");
 }
 
