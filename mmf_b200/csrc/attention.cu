@@ -326,6 +326,353 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ----------------------------------------------------------------------------------------------
+// forward, paired-tile persistent kernel (head size 64, Sq, Skv <= 256): the default for the VisualBERT / MMBT shapes
+//
+// One persistent CTA per SM walks over (batch, head) PAIRS of 128-query tiles.  Round-2 ncu view of attn_fwd_kernel (one
+// CTA per tile, 2 CTAs per SM): tensor pipe 8.7 % active, IPC 1.4 of 4, 27 % of the issued instructions in barrier spin
+// loops, K and V fetched once per query tile, P through 64 KB of shared memory - a serial chain TMA -> S -> softmax -> P ->
+// O per CTA.  Here:
+//   * K, V of a (batch, head) are loaded ONCE for both query tiles, into a two-stage ring (2 x 96 KB: Q0 Q1 K V), so the
+//     next pair streams in while this one computes;
+//   * each tile owns 256 TMEM columns and one softmax group of 8 warps (2 threads per query row, 128 score columns
+//     each): the S MMA of one tile and the softmax of the other overlap (ping-pong), nobody waits for a load;
+//   * P never touches shared memory: it is written over the score columns that have already been consumed
+//     (tcgen05.st, bf16 pairs in K order) and O = P V reads its A operand from tensor memory;
+//     region map per tile:  S [0,256)  ->  P(keys 0..127) [0,64) | O [64,128) | P(keys 128..255) [128,192).
+// 544 threads: warps 0..7 = softmax group of tile 0, warps 8..15 = tile 1, warp 16 = TMA + MMA issue (+ mask rows).
+// Barriers (phase = pair parity unless noted): qk_full / v_full / mask_full / stage_free per ring stage, and per tile
+// s_ready (S committed), p_ready (256 arrivals: P complete), o_ready (O committed), o_read (256 arrivals: O copied out).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fwd_chunk_max(const uint32_t (&r)[32], const float4* m4, float scale2, float& mx) {
+#if MMFB_F32X2
+  const uint64_t sc2 = pk2(scale2, scale2);
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 m = m4[q4];
+    float a0, a1, a2, a3;
+    upk2(fma2(pk2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])), sc2, pk2(m.x, m.y)), a0, a1);
+    upk2(fma2(pk2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])), sc2, pk2(m.z, m.w)), a2, a3);
+    mx = fmaxf(fmaxf(mx, a0), a1);
+    mx = fmaxf(fmaxf(mx, a2), a3);
+  }
+#else
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 m = m4[q4];
+    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 0]), scale2, m.x));
+    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 1]), scale2, m.y));
+    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 2]), scale2, m.z));
+    mx = fmaxf(mx, fmaf(__uint_as_float(r[q4 * 4 + 3]), scale2, m.w));
+  }
+#endif
+}
+// exp2(s*scale2 + mask - mx) of one 32-column chunk -> 16 packed bf16 pairs (dropout applied), row sum accumulated
+__device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const float4* m4, float scale2, float mx,
+                                              uint32_t bits, float& sum, uint32_t (&pk)[16]) {
+#if MMFB_F32X2
+  const uint64_t sc2 = pk2(scale2, scale2), nmx2 = pk2(-mx, -mx);
+  uint64_t sum2 = pk2(sum, 0.0f);
+#endif
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 m = m4[q4];
+    const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+      const int j = q4 * 4 + k;
+#if MMFB_F32X2
+      float a0, a1;
+      upk2(add2(fma2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, pk2(mm[k], mm[k + 1])), nmx2), a0, a1);
+      const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+      sum2 = add2(sum2, pk2(e0, e1));
+#else
+      const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, mm[k]) - mx);
+      const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, mm[k + 1]) - mx);
+      sum += e0;
+      sum += e1;
+#endif
+      pk[j >> 1] = pack_bf16x2(((bits >> j) & 1u) ? e0 : 0.0f, ((bits >> (j + 1)) & 1u) ? e1 : 0.0f);
+    }
+  }
+#if MMFB_F32X2
+  float s0, s1;
+  upk2(sum2, s0, s1);
+  sum = s0 + s1;
+#endif
+}
+
+__global__ void __launch_bounds__(544, 1)
+attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, AttnFwdDev p, int n_pairs) {
+  griddep_launch();
+  griddep_wait();
+  constexpr int D = 64;
+  constexpr int TILE = 16384;                        // [128 x 128 B]
+  constexpr int STAGE = 6 * TILE;                    // Q0 | Q1 | K0 K1 | V0 V1
+  constexpr uint32_t REG = 256, COL_PLO = 0, COL_O = 64, COL_PHI = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  float* sMask = reinterpret_cast<float*>(smem + 2 * STAGE);      // [2 stages][256]
+  float* sMax = sMask + 512;                                      // [2 tiles][2 halves][128 rows]
+  float* sSum = sMax + 512;                                       // [2 tiles][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 512);
+  uint64_t* qk_full = bars;          // [2]
+  uint64_t* v_full = bars + 2;       // [2]
+  uint64_t* mask_full = bars + 4;    // [2]
+  uint64_t* stage_free = bars + 6;   // [2]
+  uint64_t* s_ready = bars + 8;      // [2 tiles]
+  uint64_t* p_ready = bars + 10;     // [2 tiles]
+  uint64_t* o_ready = bars + 12;     // [2 tiles]
+  uint64_t* o_read = bars + 14;      // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* sAct = tmem_slot + 1;    // [2 stages] bit c: 32-key chunk c has at least one key that is not masked out
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = (p.Sq + 127) / 128;                 // query tiles per pair (1 or 2)
+  const int nkt = (p.Skv + 127) / 128;               // key tiles (1 or 2)
+  const int SKP = nkt * 128;                         // padded key count: N of the score MMA
+  const int N = (n_pairs - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == 16) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&qk_full[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&mask_full[s], 32);
+        mbar_init(&stage_free[s], 1);
+        mbar_init(&s_ready[s], 1);
+        mbar_init(&p_ready[s], 256);
+        mbar_init(&o_ready[s], 1);
+        mbar_init(&o_read[s], 256);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ------------------------------------ TMA + MMA issue (+ mask rows) ------------------------------------
+    auto pair_of = [&](int n, int& h, int& b) {
+      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+      h = it % p.H;
+      b = it / p.H;
+    };
+    auto load_pair = [&](int n) {          // lane 0: Q tiles + K into qk_full, V into v_full of ring stage n & 1
+      int h, b;
+      pair_of(n, h, b);
+      const int s = n & 1;
+      uint8_t* st = smem + s * STAGE;
+      mbar_expect_tx(&qk_full[s], (nt + nkt) * TILE);
+      for (int t = 0; t < nt; ++t) tma_load_3d(st + t * TILE, &tmQ, &qk_full[s], h * D, t * 128, b);
+      for (int j = 0; j < nkt; ++j) tma_load_3d(st + (2 + j) * TILE, &tmK, &qk_full[s], h * D, j * 128, b);
+      mbar_expect_tx(&v_full[s], nkt * TILE);
+      for (int j = 0; j < nkt; ++j) tma_load_3d(st + (4 + j) * TILE, &tmV, &v_full[s], h * D, j * 128, b);
+    };
+    auto load_mask = [&](int n) {          // whole warp: log2-domain additive mask, -inf on the padded key columns
+      int h, b;
+      pair_of(n, h, b);
+      float* dst = sMask + (n & 1) * 256;
+      // Chunks whose 32 keys are ALL masked out (additive -10000, or beyond Skv) contribute exp2(-14427 + ...) = 0 exactly:
+      // they are skipped in both softmax passes and in the P V contraction (identical results; a quarter of the chunks at
+      // the padding rates of the reference's text / region batches).  A sample without any attendable key keeps them all:
+      // its softmax is uniform over the masked keys (hf_layers.py:191-196 semantics).
+      uint32_t act = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = lane + 32 * j;
+        const float mv = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+        dst[i] = mv;
+        if (__any_sync(0xffffffffu, mv > -5000.0f)) act |= 1u << j;
+      }
+      if (act == 0) act = (1u << ((p.Skv + 31) / 32)) - 1u;
+      if (lane == 0) sAct[n & 1] = act;
+      __syncwarp();
+      mbar_arrive(&mask_full[n & 1]);
+    };
+    auto issue_s = [&](int n, int t) {     // lane 0: S_t = Q_t K^T over all (padded) keys
+      const uint32_t st = smem_u32(smem + (n & 1) * STAGE);
+      const uint32_t aQ = st + t * TILE, aK = st + 2 * TILE;
+      const uint32_t idesc = umma_idesc_bf16(128, SKP, false, false);
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        umma_bf16(tmem_base + t * REG, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc,
+                  kk > 0 ? 1u : 0u);
+      umma_commit(&s_ready[t]);
+    };
+    auto issue_o = [&](int n, int t) {     // lane 0: O_t = P V, A = P from tensor memory (8 columns per 16 keys)
+      const uint32_t aV = smem_u32(smem + (n & 1) * STAGE + 4 * TILE);
+      const uint32_t idesc = umma_idesc_bf16(128, D, false, true);
+      const int ksteps = (p.Skv + 15) / 16;
+      const uint32_t act = sAct[n & 1];
+      bool first = true;
+      for (int kk = 0; kk < ksteps; ++kk) {
+        if (!((act >> (kk >> 1)) & 1u)) continue;            // P is exactly zero over this chunk
+        const uint32_t a_tm = tmem_base + t * REG + (kk < 8 ? COL_PLO + kk * 8 : COL_PHI + (kk - 8) * 8);
+        // V tile j = kk / 8 (128 keys each), 16 keys per step: 2048 B per step inside the tile, MN-major (LBO = tile pitch unused: D = 64)
+        umma_bf16_ts(tmem_base + t * REG + COL_O, a_tm, umma_desc_sw128(aV + (kk >> 3) * TILE + (kk & 7) * 2048, TILE, 1024), idesc,
+                     first ? 0u : 1u);
+        first = false;
+      }
+      umma_commit(&o_ready[t]);
+    };
+    for (int n = 0; n < 2 && n < N; ++n) {
+      if (lane == 0) load_pair(n);
+      load_mask(n);
+    }
+    if (lane == 0 && N > 0) {
+      mbar_wait(&qk_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < nt; ++t) issue_s(0, t);
+    }
+    // Software-pipelined issue order (ping-pong): O_t(n) as soon as group t has finished P_t(n); then, as soon as group t
+    // has copied O_t(n) out, S_t(n+1) - while the OTHER group is still in its softmax.  The two groups settle half a period
+    // apart, so the tensor core work of one hides behind the arithmetic of the other.
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1;
+      if (lane == 0) {
+        mbar_wait(&v_full[s], (n >> 1) & 1);
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(&p_ready[t], n & 1);
+          tc_fence_after();
+          issue_o(n, t);
+          if (t == nt - 1) umma_commit(&stage_free[s]);       // every MMA that reads ring stage s has been issued
+          if (n + 1 < N) {
+            mbar_wait(&o_read[t], n & 1);                     // O_t(n) has been copied out: region t is free
+            if (t == 0) mbar_wait(&qk_full[s ^ 1], ((n + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_s(n + 1, t);
+          }
+        }
+      }
+      __syncwarp();
+      if (n + 2 < N) {
+        // ring stage s is reloaded for pair n+2 once its MMAs have completed; its mask row is not read after p_ready(n)
+        if (lane == 0) {
+          mbar_wait(&stage_free[s], (n >> 1) & 1);
+          load_pair(n + 2);
+        }
+        __syncwarp();
+        load_mask(n + 2);
+      }
+    }
+  } else {
+    // ------------------------------------ softmax groups ------------------------------------
+    const int t = warp >> 3;                                  // tile / group
+    if (t < nt) {
+      const int quarter = warp & 3, half = (warp >> 2) & 1;
+      const int row = quarter * 32 + lane;
+      const uint32_t treg = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * REG;
+      const int nch = (p.Skv + 31) / 32;
+      const int c0 = half * 4;                                // this thread's chunks: c0 .. c0+3 (keys 128*half ..)
+      const int my_chunks = min(4, max(0, (SKP / 32) - c0));  // chunks inside the padded key range
+      float* gMax = sMax + t * 256;
+      float* gSum = sSum + t * 256;
+      const int bar_id = 1 + t;
+      for (int n = 0; n < N; ++n) {
+        const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+        const int h = it % p.H, b = it / p.H;
+        const int q = t * 128 + row;
+        const bool valid = q < p.Sq;
+        const float4* m4 = reinterpret_cast<const float4*>(sMask + (n & 1) * 256);
+        // keep-bit words of this thread's chunks: fetched before the score barrier
+        uint32_t bits[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (p.dmask != nullptr && valid) {
+          const uint32_t* dm = p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c0 + k < nch) bits[k] = __ldg(dm + c0 + k);
+        }
+        mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
+        const uint32_t act = sAct[n & 1] >> c0;                // bit k: this thread's chunk k has an attendable key
+        mbar_wait(&s_ready[t], n & 1);
+        tc_fence_after();
+        // ---- pass 1: row maximum over this thread's columns ----
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int k = 0; k < my_chunks; ++k) {
+          if (!((act >> k) & 1u)) continue;
+          uint32_t r[32];
+          tmem_ld32(treg + (c0 + k) * 32, r);
+          tmem_ld_wait();
+          fwd_chunk_max(r, m4 + (c0 + k) * 8, p.scale2, mx);
+        }
+        gMax[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        mx = fmaxf(gMax[row], gMax[128 + row]);
+        // ---- pass 2: probabilities -> tensor memory, over score columns this thread has already consumed ----
+        float sum = 0.0f;
+        const uint32_t pcol = half == 0 ? COL_PLO : COL_PHI;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          uint32_t pk[16];
+          if (k < my_chunks && ((act >> k) & 1u)) {
+            uint32_t r[32];
+            tmem_ld32(treg + (c0 + k) * 32, r);
+            tmem_ld_wait();
+            fwd_chunk_exp(r, m4 + (c0 + k) * 8, p.scale2, mx, bits[k], sum, pk);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          if (c0 + k < nkt * 4 && ((act >> k) & 1u)) tmem_st16(treg + pcol + k * 16, pk);
+        }
+        gSum[half * 128 + row] = sum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[t]);
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        sum = gSum[row] + gSum[128 + row];
+        // ---- O_t: 32 of the 64 columns per thread ----
+        mbar_wait(&o_ready[t], n & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(treg + COL_O + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&o_read[t]);
+        if (valid) {
+          const float inv = p.dscale / sum;
+          if (half == 0) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = mx + log2f(sum);
+          const int64_t tok = static_cast<int64_t>(b) * p.Sq + q;
+          uint4* dst = reinterpret_cast<uint4*>(p.ctx + tok * p.ldo + h * D + half * 32);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[qd * 8 + 0]) * inv, __uint_as_float(r[qd * 8 + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(r[qd * 8 + 2]) * inv, __uint_as_float(r[qd * 8 + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(r[qd * 8 + 4]) * inv, __uint_as_float(r[qd * 8 + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * inv, __uint_as_float(r[qd * 8 + 7]) * inv);
+            dst[qd] = o;
+          }
+          if (p.ctx32 != nullptr) {
+            float4* d32 = reinterpret_cast<float4*>(p.ctx32 + tok * (p.H * D) + h * D + half * 32);
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd)
+              d32[qd] = make_float4(__uint_as_float(r[qd * 4 + 0]) * inv, __uint_as_float(r[qd * 4 + 1]) * inv,
+                                    __uint_as_float(r[qd * 4 + 2]) * inv, __uint_as_float(r[qd * 4 + 3]) * inv);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------------------------
 struct AttnBwdDev {
@@ -1021,6 +1368,24 @@ attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // 32-key chunks whose keys are ALL masked out (additive -10000 or beyond Skv) have P = exp2(-14427 + ...) = 0 and dS = 0
+  // exactly: their arithmetic is skipped (zeros are stored).  A sample without any attendable key keeps every chunk.
+  uint32_t my_act = 0;            // bit j: this thread's chunk (warp >> 2) of key block j has an attendable key
+  if (warp < 16) {
+    const int cc = warp >> 2;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float4* m4 = reinterpret_cast<const float4*>(sMsk + j * 128 + cc * 32);
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 m = m4[i];
+        any = any || m.x > -5000.0f || m.y > -5000.0f || m.z > -5000.0f || m.w > -5000.0f;
+      }
+      if (any) my_act |= 1u << j;
+    }
+  }
+  if (!__syncthreads_or(my_act != 0)) my_act = 3u;
 
   if (warp == 16) {
     if (lane == 0) {
@@ -1090,8 +1455,13 @@ attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         uint32_t wds[16], wp[16];                           // packed bf16 pairs of dS' and P' for this thread's 32 columns
         mbar_wait(s_ready, pair & 1);
         tc_fence_after();
+        const bool chunk_on = (my_act >> j) & 1u;
+        if (!chunk_on) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+          for (int e = 0; e < 16; ++e) { wds[e] = 0u; wp[e] = 0u; }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2 && chunk_on; ++hh) {
           uint32_t rs[16], rd[16];
           tmem_ld16(trow + COL_S + c * 32 + hh * 16, rs);
           tmem_ld16(trow + COL_DP + c * 32 + hh * 16, rd);
@@ -1278,6 +1648,11 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmQ, a.q, W, a.Sq, a.B, a.ldq, a.ldq * a.Sq, 64, 128))) return rc;
   if ((rc = make_tmap_3d(&tmK, a.k, W, a.Skv, a.B, a.ldk, a.ldk * a.Skv, 64, 64))) return rc;
   if ((rc = make_tmap_3d(&tmV, a.v, W, a.Skv, a.B, a.ldv, a.ldv * a.Skv, 64, 64))) return rc;
+  CUtensorMap tmK128 = tmK, tmV128 = tmV;      // 128-key boxes for the paired-tile kernel
+  if (D == 64 && a.Sq <= 256 && a.Skv <= 256) {
+    if ((rc = make_tmap_3d(&tmK128, a.k, W, a.Skv, a.B, a.ldk, a.ldk * a.Skv, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tmV128, a.v, W, a.Skv, a.B, a.ldv, a.ldv * a.Skv, 64, 128))) return rc;
+  }
   constexpr int DC = D / 64;
   const int SK = (a.Skv + 63) & ~63, NB = SK / 64;
   const int r0 = NB * 16384 > DC * 16384 + DC * SK * 128 ? NB * 16384 : DC * 16384 + DC * SK * 128;
@@ -1290,6 +1665,27 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   p.ctx32 = a.ctx32;
   p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
   p.scale2 = LOG2E / sqrtf(static_cast<float>(D));
+  if (D == 64 && a.Sq <= 256 && a.Skv <= 256) {
+    // default for head size 64 and sequences within two 128-row tiles; MMFB_ATTN_FWD=1 (read per call) selects the
+    // one-CTA-per-tile kernel below for A/B runs
+    const char* f_env = getenv("MMFB_ATTN_FWD");
+    if (f_env == nullptr || f_env[0] != '1') {
+      const int smem_p = 2 * 6 * 16384 + (512 + 512 + 512) * 4 + 256 + 1024;
+      static bool attr_p = false;
+      if (!attr_p) {
+        cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+        if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd_pair smem attr (%d B): %s", smem_p, cudaGetErrorString(e2));
+        attr_p = true;
+      }
+      const int n_pairs = a.heads * a.B;
+      const int grid_p = n_pairs < num_sms() ? n_pairs : num_sms();
+      MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, 544, smem_p, stream, tmQ, tmK128, tmV128, p, n_pairs);
+      cudaError_t e2 = cudaGetLastError();
+      if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd_pair launch: %s", cudaGetErrorString(e2));
+      count_launch();
+      return MMFB_OK;
+    }
+  }
   auto kern = attn_fwd_kernel<D>;
   static int smem_set = 0;
   if (smem > smem_set) {

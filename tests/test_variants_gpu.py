@@ -80,3 +80,39 @@ def test_8_warp_fused_attention_backward_matches_the_default(Sq, Skv, drop):
         r, t = r.float(), t.float()
         assert (r - t).abs().max() <= 1e-2 * r.abs().max(), name
         assert (r != t).float().mean() < 0.01, (name, (r != t).float().mean().item())
+
+
+@pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (128, 256, False), (100, 36, True), (256, 17, False), (36, 130, True)])
+def test_one_cta_per_tile_attention_forward_matches_the_default(Sq, Skv, drop):
+    """MMFB_ATTN_FWD=1 (one CTA per 128-query tile, P through shared memory) against the default paired-tile persistent kernel
+    (K/V loaded once per (batch, head), P in tensor memory, ping-pong softmax groups): same arithmetic per element"""
+    from mmf_b200 import functional as F
+    torch.manual_seed(Sq + Skv)
+    B, heads, d = 7, 3, 64
+    W = heads * d
+    q = torch.randn(B * Sq, W, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B * Skv, W, device="cuda").to(torch.bfloat16)
+    mask = torch.zeros(B, Skv, device="cuda")
+    mask[1, Skv // 2:] = -10000.0
+    mask[2, :] = -10000.0                                   # fully masked sample: uniform softmax
+    bits = F.dropout_bits((B, heads, Sq), Skv, 0.1, 5, 0, "cuda") if drop else None
+    scale = 1.0 / 0.9 if drop else 1.0
+
+    def run(flag):
+        if flag:
+            os.environ["MMFB_ATTN_FWD"] = "1"
+        else:
+            os.environ.pop("MMFB_ATTN_FWD", None)
+        out = F.attention_fwd(q, k, v, B, heads, Sq, Skv, mask, bits, scale, save_fp32=True)
+        torch.cuda.synchronize()
+        return [t.clone() for t in out]
+    try:
+        ref, got = run(True), run(False)
+    finally:
+        os.environ.pop("MMFB_ATTN_FWD", None)
+    for name, r, t in zip(("ctx", "lse2", "ctx32"), ref, got):
+        r, t = r.float(), t.float()
+        assert torch.isfinite(t).all(), name
+        assert (r - t).abs().max() <= 2e-2 * r.abs().max(), (name, (r - t).abs().max().item())
+        assert ((r - t).norm() / r.norm()).item() < 3e-3, name
