@@ -203,7 +203,21 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
-template <int NV>
+// bf16x2 word -> the two values as a packed fp32 pair (exact: a bf16 is the top half of an fp32)
+__device__ __forceinline__ uint64_t unpack2(uint32_t w) {
+  return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack2(uint64_t v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+// Instruction diet (the first version issued ~42 instructions per element and was issue-bound at 0.48 of the HBM peak):
+// all arithmetic on packed fp32 pairs (FFMA2 / FMUL2 / FADD2), xhat as ONE fma (y * rstd - mean * rstd), the output as
+// two (d * (gamma * rstd) - rstd * m1, then - rstd * m2 * xhat), gamma as fp32 in shared memory (LDS.128, no unpack),
+// dropout applied to the PACKED bf16 result with an AND mask looked up per 8 keep-bits (256 x 16 B table in shared
+// memory) instead of eight bit tests + selects; dbias sums the bf16 values that are stored (what the consumer reads).
+template <int NV, bool HAS_DX2>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 2)
 ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
                    const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
@@ -213,83 +227,113 @@ ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
   griddep_launch();
   griddep_wait();
   __shared__ float red[ROW_WARPS][256];
+  __shared__ __align__(16) float sG[NV * 256];
+  __shared__ __align__(16) uint32_t sKeep[256][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ag[NV][8], ab[NV][8], az[NV][8];
+  for (int c = threadIdx.x; c < NV * 256; c += ROW_WARPS * 32) sG[c] = c < H ? __bfloat162float(gamma[c]) : 0.0f;
+  {
+    const uint32_t b = threadIdx.x;          // 256 threads <-> the 256 patterns of 8 keep-bits
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      sKeep[b][k] = (((b >> (2 * k)) & 1u) ? 0x0000ffffu : 0u) | (((b >> (2 * k + 1)) & 1u) ? 0xffff0000u : 0u);
+  }
+  __syncthreads();
+  uint64_t ag[NV][4], ab[NV][4], az[NV][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { ag[i][e] = 0.0f; ab[i][e] = 0.0f; az[i][e] = 0.0f; }
+    for (int k = 0; k < 4; ++k) { ag[i][k] = 0ull; ab[i][k] = 0ull; az[i][k] = 0ull; }
+  const float invH = 1.0f / static_cast<float>(H);
+  const uint64_t ds2 = pk2(dscale, dscale);
 
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + warp; row < M;
        row += static_cast<int64_t>(gridDim.x) * ROW_WARPS) {
     const float mu = mean[row], rs = rstd[row];
+    const float nmr = -mu * rs;
+    const uint64_t rs2 = pk2(rs, rs), nmr2 = pk2(nmr, nmr);
     uint4 dw[NV], yw[NV];      // packed bf16 rows of dx and y, kept across the two phases
-    float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = i * 256 + lane * 8;
+      dw[i] = make_uint4(0u, 0u, 0u, 0u);
+      yw[i] = make_uint4(0u, 0u, 0u, 0u);
       if (col < H) {
         dw[i] = *reinterpret_cast<const uint4*>(dx + row * lddx + col);
         yw[i] = *reinterpret_cast<const uint4*>(y + row * ldy + col);
       }
     }
+    uint64_t s1 = 0ull, s2 = 0ull;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = i * 256 + lane * 8;
       if (col < H) {
-        float d[8], yy[8], g[8];
-        unpack8(dw[i], d);
-        if (dx2 != nullptr) {
+        const uint32_t da[4] = {dw[i].x, dw[i].y, dw[i].z, dw[i].w};
+        const uint32_t ya[4] = {yw[i].x, yw[i].y, yw[i].z, yw[i].w};
+        uint32_t xa[4] = {0u, 0u, 0u, 0u};
+        if (HAS_DX2) {
           // d = dx + dx2 is formed in fp32; re-packing the sum to bf16 would change the result, so the second
           // stream is not kept but re-read in phase 2 (an L1 hit)
-          float t[8];
-          ld8(dx2 + row * lddx2 + col, t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d[e] += t[e];
+          const uint4 t = *reinterpret_cast<const uint4*>(dx2 + row * lddx2 + col);
+          xa[0] = t.x; xa[1] = t.y; xa[2] = t.z; xa[3] = t.w;
         }
-        unpack8(yw[i], yy);
-        ld8(gamma + col, g);
+        const float4 ga = *reinterpret_cast<const float4*>(sG + col), gb = *reinterpret_cast<const float4*>(sG + col + 4);
+        const uint64_t g2[4] = {pk2(ga.x, ga.y), pk2(ga.z, ga.w), pk2(gb.x, gb.y), pk2(gb.z, gb.w)};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (yy[e] - mu) * rs;
-          const float dg = d[e] * g[e];
-          s1 += dg;
-          s2 += dg * xh;
-          ag[i][e] += d[e] * xh;
-          ab[i][e] += d[e];
+        for (int k = 0; k < 4; ++k) {
+          uint64_t d2 = unpack2(da[k]);
+          if (HAS_DX2) d2 = add2(d2, unpack2(xa[k]));
+          const uint64_t xh2 = fma2(unpack2(ya[k]), rs2, nmr2);
+          const uint64_t dg2 = mul2(d2, g2[k]);
+          s1 = add2(s1, dg2);
+          s2 = fma2(dg2, xh2, s2);
+          ag[i][k] = fma2(d2, xh2, ag[i][k]);
+          ab[i][k] = add2(ab[i][k], d2);
         }
       }
     }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
+    float s1a, s1b, s2a, s2b;
+    upk2(s1, s1a, s1b);
+    upk2(s2, s2a, s2b);
+    const float m1 = warp_sum(s1a + s1b) * invH, m2 = warp_sum(s2a + s2b) * invH;
+    const uint64_t nA2 = pk2(-rs * m1, -rs * m1), nB2 = pk2(-rs * m2, -rs * m2);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = i * 256 + lane * 8;
       if (col < H) {
-        float d[8], yy[8], g[8], o[8];
-        unpack8(dw[i], d);
-        if (dx2 != nullptr) {
-          float t[8];
-          ld8(dx2 + row * lddx2 + col, t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d[e] += t[e];
+        const uint32_t da[4] = {dw[i].x, dw[i].y, dw[i].z, dw[i].w};
+        const uint32_t ya[4] = {yw[i].x, yw[i].y, yw[i].z, yw[i].w};
+        uint32_t xa[4] = {0u, 0u, 0u, 0u};
+        if (HAS_DX2) {
+          const uint4 t = *reinterpret_cast<const uint4*>(dx2 + row * lddx2 + col);
+          xa[0] = t.x; xa[1] = t.y; xa[2] = t.z; xa[3] = t.w;
         }
-        unpack8(yw[i], yy);
-        ld8(gamma + col, g);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (d[e] * g[e] - s1 - ((yy[e] - mu) * rs) * s2);
-        if (dy != nullptr) st8(dy + row * lddy + col, o);
+        const float4 ga = *reinterpret_cast<const float4*>(sG + col), gb = *reinterpret_cast<const float4*>(sG + col + 4);
+        const uint64_t g2[4] = {pk2(ga.x, ga.y), pk2(ga.z, ga.w), pk2(gb.x, gb.y), pk2(gb.z, gb.w)};
+        uint32_t keep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         if (dmask != nullptr) {
           const uint32_t w = __ldg(dmask + row * ldmask + (col >> 5));
-          const uint32_t bits = (w >> (col & 31)) & 0xFFu;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = ((bits >> e) & 1u) ? o[e] * dscale : 0.0f;
-          st8(dz + row * lddz + col, o);
-        } else if (dz != nullptr && dz != dy) {
-          st8(dz + row * lddz + col, o);
+          const uint4 kk = *reinterpret_cast<const uint4*>(sKeep[(w >> (col & 31)) & 0xFFu]);
+          keep[0] = kk.x; keep[1] = kk.y; keep[2] = kk.z; keep[3] = kk.w;
         }
+        uint32_t ow[4], zw[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) az[i][e] += o[e];
+        for (int k = 0; k < 4; ++k) {
+          uint64_t d2 = unpack2(da[k]);
+          if (HAS_DX2) d2 = add2(d2, unpack2(xa[k]));
+          const uint64_t xh2 = fma2(unpack2(ya[k]), rs2, nmr2);
+          const uint64_t o2 = fma2(nB2, xh2, fma2(d2, mul2(g2[k], rs2), nA2));
+          ow[k] = pack2(o2);
+          if (dmask != nullptr) {
+            zw[k] = pack2(mul2(o2, ds2)) & keep[k];
+            az[i][k] = add2(az[i][k], unpack2(zw[k]));
+          } else {
+            zw[k] = ow[k];
+            az[i][k] = add2(az[i][k], o2);
+          }
+        }
+        if (dy != nullptr) *reinterpret_cast<uint4*>(dy + row * lddy + col) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (dz != nullptr && (dmask != nullptr || dz != dy))
+          *reinterpret_cast<uint4*>(dz + row * lddz + col) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
       }
     }
   }
@@ -303,7 +347,12 @@ ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
       if (i * 256 >= H) break;
       __syncthreads();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = which == 0 ? ag[i][e] : (which == 1 ? ab[i][e] : az[i][e]);
+      for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        upk2(which == 0 ? ag[i][k] : (which == 1 ? ab[i][k] : az[i][k]), lo, hi);
+        red[warp][lane * 8 + 2 * k] = lo;
+        red[warp][lane * 8 + 2 * k + 1] = hi;
+      }
       __syncthreads();
       const int c = threadIdx.x;  // 256 threads <-> 256 columns
       float t = 0.0f;
@@ -896,11 +945,15 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
     const int cap = num_sms() * 2;      // two resident blocks per SM, rows strided over them
     if (grid > cap) grid = cap;
 #define LN_LEAN(NV)                                                                                                  \
-  MMFB_LAUNCH(ln_bwd_lean_kernel<NV>, grid, ROW_WARPS * 32, 0, s, (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
+  MMFB_LAUNCH((ln_bwd_lean_kernel<NV, DX2>), grid, ROW_WARPS * 32, 0, s, (const bf16*)a.dx, a.lddx, (const bf16*)a.dx2, a.lddx2,       \
                                                          (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma, \
                                                          (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask,         \
                                                          a.ldmask, a.drop_scale, a.dgamma, a.dbeta, a.dbias, a.M, a.H)
-    if (nv_ <= 1) LN_LEAN(1); else if (nv_ == 2) LN_LEAN(2); else if (nv_ == 3) LN_LEAN(3); else LN_LEAN(4);
+#define LN_LEAN2(DX2_)                                                                                              \
+  { constexpr bool DX2 = DX2_;                                                                                       \
+    if (nv_ <= 1) LN_LEAN(1); else if (nv_ == 2) LN_LEAN(2); else if (nv_ == 3) LN_LEAN(3); else LN_LEAN(4); }
+    if (a.dx2 != nullptr) LN_LEAN2(true) else LN_LEAN2(false)
+#undef LN_LEAN2
 #undef LN_LEAN
     return launch_ok("layernorm_bwd(lean)");
   }

@@ -24,8 +24,8 @@ b3, b1, bh = (torch.zeros(n, device=dev, dtype=bf) for n in (3 * H, I, H))
 bits_h = F.dropout_bits((M,), H, 0.1, 1, 0, dev)
 qkv = torch.randn(M, 3 * H, device=dev).to(bf)
 q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
-mask = torch.zeros(B, S, device=dev)
-mask[:, 200:] = -10000.0
+lens = torch.randint(S // 2, S + 1, (B,), device=dev)          # ragged key padding, as in tools/kbench.py
+mask = ((torch.arange(S, device=dev)[None] >= lens[:, None]).float() * -10000.0).contiguous()
 bits_a = F.dropout_bits((B, heads, S), S, 0.1, 7, 0, dev)
 dctx = torch.randn(M, H, device=dev).to(bf)
 ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_fp32=True)
@@ -51,19 +51,31 @@ def ln_bwd(variant):
     os.environ.pop("MMFB_LN_BWD", None)
 
 
+def attn_fwd(env):
+    for k_, v_ in env.items():
+        os.environ[k_] = v_
+    F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_fp32=True)
+    for k_ in env:
+        os.environ.pop(k_, None)
+
+
 work = [
     lambda: F.gemm(x, w_qkv, epi=lib.EPI_BIAS, bias=b3),
     lambda: F.gemm(x, w_o, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9),
     lambda: F.gemm(x, w_1, epi=lib.EPI_BIAS_GELU, bias=b1),
     lambda: F.gemm(x, w_2, b_mn=True, epi=lib.EPI_GELU_BWD, aux=xi),
     lambda: F.gemm(xi, w_2, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9),
-    lambda: F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_fp32=True),
+    lambda: attn_fwd({}),
+    lambda: attn_fwd({"MMFB_ATTN_FWD": "1"}),
     lambda: attn_bwd({"MMFB_ATTN_BWD": "8"}),
     lambda: attn_bwd({"MMFB_ATTN_BWD": "16"}),
     lambda: ln_bwd("pair"),
     lambda: ln_bwd("lean"),
     lambda: F.dropout_bits((B, heads, S), S, 0.1, 7, 0, dev),
 ]
+if os.environ.get("PROF_ONLY"):          # e.g. PROF_ONLY=attn,ln : skip the GEMMs
+    keep = os.environ["PROF_ONLY"].split(",")
+    work = [w for i, w in enumerate(work) if ("attn" in keep and 5 <= i <= 8) or ("ln" in keep and 9 <= i <= 10)]
 for fn in work:
     fn()
 torch.cuda.synchronize()
