@@ -339,7 +339,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   * P never touches shared memory: it is written over the score columns that have already been consumed
 //     (tcgen05.st, bf16 pairs in K order) and O = P V reads its A operand from tensor memory;
 //     region map per tile:  S [0,256)  ->  P(keys 0..127) [0,64) | O [64,128) | P(keys 128..255) [128,192).
-// 544 threads: warps 0..7 = softmax group of tile 0, warps 8..15 = tile 1, warp 16 = TMA + MMA issue (+ mask rows).
+// 576 threads: warps 0..7 = softmax group of tile 0, warps 8..15 = tile 1, warp 16 = MMA issue, warp 17 = TMA + mask rows.
 // Barriers (phase = pair parity unless noted): qk_full / v_full / mask_full / stage_free per ring stage, and per tile
 // s_ready (S committed), p_ready (256 arrivals: P complete), o_ready (O committed), o_read (256 arrivals: O copied out).
 // ----------------------------------------------------------------------------------------------
@@ -401,7 +401,8 @@ __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const flo
 #endif
 }
 
-__global__ void __launch_bounds__(544, 1)
+constexpr int FWD_PAIR_THREADS = 576;       // 16 softmax warps + 1 MMA-issue warp + 1 loader warp
+__global__ void __maxnreg__(112)
 attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnFwdDev p, int n_pairs) {
   griddep_launch();
@@ -409,7 +410,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int D = 64;
   constexpr int TILE = 16384;                        // [128 x 128 B]
   constexpr int STAGE = 6 * TILE;                    // Q0 | Q1 | K0 K1 | V0 V1
-  constexpr uint32_t REG = 256, COL_PLO = 0, COL_O = 64, COL_PHI = 128;
+  // region map per tile (256 columns): S [0,256) -> O [0,64) | P(keys 0..127) [64,128) | - | P(keys 128..255) [192,256):
+  // pass 2 walks a thread's chunks from the last to the first, so chunk k's probabilities (16 columns) land on score
+  // columns of chunks >= k that have been consumed, and the two chunks pass 1 read last are still in registers.
+  constexpr uint32_t REG = 256, COL_O = 0, COL_PLO = 64, COL_PHI = 192;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   float* sMask = reinterpret_cast<float*>(smem + 2 * STAGE);      // [2 stages][256]
@@ -419,7 +423,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* qk_full = bars;          // [2]
   uint64_t* v_full = bars + 2;       // [2]
   uint64_t* mask_full = bars + 4;    // [2]
-  uint64_t* stage_free = bars + 6;   // [2]
+  uint64_t* stage_free = bars + 6;   // [2]  one commit per tile
   uint64_t* s_ready = bars + 8;      // [2 tiles]
   uint64_t* p_ready = bars + 10;     // [2 tiles]
   uint64_t* o_ready = bars + 12;     // [2 tiles]
@@ -433,7 +437,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int SKP = nkt * 128;                         // padded key count: N of the score MMA
   const int N = (n_pairs - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-  if (warp == 16) {
+  if (warp == 17) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -442,7 +446,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_init(&qk_full[s], 1);
         mbar_init(&v_full[s], 1);
         mbar_init(&mask_full[s], 32);
-        mbar_init(&stage_free[s], 1);
+        mbar_init(&stage_free[s], nt);
         mbar_init(&s_ready[s], 1);
         mbar_init(&p_ready[s], 256);
         mbar_init(&o_ready[s], 1);
@@ -459,16 +463,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 16) {
-    // ------------------------------------ TMA + MMA issue (+ mask rows) ------------------------------------
-    auto pair_of = [&](int n, int& h, int& b) {
-      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-      h = it % p.H;
-      b = it / p.H;
-    };
+  if (warp == 17) {
+    // ------------------------------------ loader: TMA tiles + mask rows, two pairs ahead ------------------------------------
     auto load_pair = [&](int n) {          // lane 0: Q tiles + K into qk_full, V into v_full of ring stage n & 1
-      int h, b;
-      pair_of(n, h, b);
+      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+      const int h = it % p.H, b = it / p.H;
       const int s = n & 1;
       uint8_t* st = smem + s * STAGE;
       mbar_expect_tx(&qk_full[s], (nt + nkt) * TILE);
@@ -478,90 +477,110 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < nkt; ++j) tma_load_3d(st + (4 + j) * TILE, &tmV, &v_full[s], h * D, j * 128, b);
     };
     auto load_mask = [&](int n) {          // whole warp: log2-domain additive mask, -inf on the padded key columns
-      int h, b;
-      pair_of(n, h, b);
+      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+      const int b = it / p.H;
       float* dst = sMask + (n & 1) * 256;
       // Chunks whose 32 keys are ALL masked out (additive -10000, or beyond Skv) contribute exp2(-14427 + ...) = 0 exactly:
       // they are skipped in both softmax passes and in the P V contraction (identical results; a quarter of the chunks at
       // the padding rates of the reference's text / region batches).  A sample without any attendable key keeps them all:
       // its softmax is uniform over the masked keys (hf_layers.py:191-196 semantics).
-      uint32_t act = 0;
+      float mv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = lane + 32 * j;
-        const float mv = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
-        dst[i] = mv;
-        if (__any_sync(0xffffffffu, mv > -5000.0f)) act |= 1u << j;
+        mv[j] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+      }
+      uint32_t act = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dst[lane + 32 * j] = mv[j];
+        if (__any_sync(0xffffffffu, mv[j] > -5000.0f)) act |= 1u << j;
       }
       if (act == 0) act = (1u << ((p.Skv + 31) / 32)) - 1u;
       if (lane == 0) sAct[n & 1] = act;
       __syncwarp();
       mbar_arrive(&mask_full[n & 1]);
     };
-    auto issue_s = [&](int n, int t) {     // lane 0: S_t = Q_t K^T over all (padded) keys
-      const uint32_t st = smem_u32(smem + (n & 1) * STAGE);
-      const uint32_t aQ = st + t * TILE, aK = st + 2 * TILE;
-      const uint32_t idesc = umma_idesc_bf16(128, SKP, false, false);
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_bf16(tmem_base + t * REG, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc,
-                  kk > 0 ? 1u : 0u);
-      umma_commit(&s_ready[t]);
-    };
-    auto issue_o = [&](int n, int t) {     // lane 0: O_t = P V, A = P from tensor memory (8 columns per 16 keys)
-      const uint32_t aV = smem_u32(smem + (n & 1) * STAGE + 4 * TILE);
-      const uint32_t idesc = umma_idesc_bf16(128, D, false, true);
-      const int ksteps = (p.Skv + 15) / 16;
-      const uint32_t act = sAct[n & 1];
-      bool first = true;
-      for (int kk = 0; kk < ksteps; ++kk) {
-        if (!((act >> (kk >> 1)) & 1u)) continue;            // P is exactly zero over this chunk
-        const uint32_t a_tm = tmem_base + t * REG + (kk < 8 ? COL_PLO + kk * 8 : COL_PHI + (kk - 8) * 8);
-        // V tile j = kk / 8 (128 keys each), 16 keys per step: 2048 B per step inside the tile, MN-major (LBO = tile pitch unused: D = 64)
-        umma_bf16_ts(tmem_base + t * REG + COL_O, a_tm, umma_desc_sw128(aV + (kk >> 3) * TILE + (kk & 7) * 2048, TILE, 1024), idesc,
-                     first ? 0u : 1u);
-        first = false;
-      }
-      umma_commit(&o_ready[t]);
-    };
     for (int n = 0; n < 2 && n < N; ++n) {
       if (lane == 0) load_pair(n);
       load_mask(n);
     }
+    for (int n = 0; n + 2 < N; ++n) {
+      // ring stage n & 1 (tiles, mask row, chunk bits) is refilled once every MMA of pair n has completed
+      mbar_wait(&stage_free[n & 1], (n >> 1) & 1);
+      if (lane == 0) load_pair(n + 2);
+      load_mask(n + 2);
+    }
+  } else if (warp == 16) {
+    // ------------------------------------ MMA issue: one thread, both tiles, never blocked on one of them ------------------------------------
     if (lane == 0 && N > 0) {
+      auto issue_s = [&](int n, int t) {   // S_t = Q_t K^T over all (padded) keys
+        const uint32_t st = smem_u32(smem + (n & 1) * STAGE);
+        const uint32_t aQ = st + t * TILE, aK = st + 2 * TILE;
+        const uint32_t idesc = umma_idesc_bf16(128, SKP, false, false);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16(tmem_base + t * REG, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc,
+                    kk > 0 ? 1u : 0u);
+        umma_commit(&s_ready[t]);
+      };
+      auto issue_o = [&](int n, int t) {   // O_t = P V, A = P from tensor memory (8 columns per 16 keys)
+        const uint32_t aV = smem_u32(smem + (n & 1) * STAGE + 4 * TILE);
+        const uint32_t idesc = umma_idesc_bf16(128, D, false, true);
+        const int ksteps = (p.Skv + 15) / 16;
+        const uint32_t act = sAct[n & 1];
+        bool first = true;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          if (!((act >> (kk >> 1)) & 1u)) continue;            // P is exactly zero over this chunk
+          const uint32_t a_tm = tmem_base + t * REG + (kk < 8 ? COL_PLO + kk * 8 : COL_PHI + (kk - 8) * 8);
+          // V tile j = kk / 8 (128 keys each), 16 keys per step: 2048 B per step inside the tile, MN-major
+          umma_bf16_ts(tmem_base + t * REG + COL_O, a_tm, umma_desc_sw128(aV + (kk >> 3) * TILE + (kk & 7) * 2048, TILE, 1024), idesc,
+                       first ? 0u : 1u);
+          first = false;
+        }
+        umma_commit(&o_ready[t]);
+      };
       mbar_wait(&qk_full[0], 0);
       tc_fence_after();
       for (int t = 0; t < nt; ++t) issue_s(0, t);
-    }
-    // Software-pipelined issue order (ping-pong): O_t(n) as soon as group t has finished P_t(n); then, as soon as group t
-    // has copied O_t(n) out, S_t(n+1) - while the OTHER group is still in its softmax.  The two groups settle half a period
-    // apart, so the tensor core work of one hides behind the arithmetic of the other.
-    for (int n = 0; n < N; ++n) {
-      const int s = n & 1;
-      if (lane == 0) {
-        mbar_wait(&v_full[s], (n >> 1) & 1);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(&p_ready[t], n & 1);
-          tc_fence_after();
-          issue_o(n, t);
-          if (t == nt - 1) umma_commit(&stage_free[s]);       // every MMA that reads ring stage s has been issued
-          if (n + 1 < N) {
-            mbar_wait(&o_read[t], n & 1);                     // O_t(n) has been copied out: region t is free
-            if (t == 0) mbar_wait(&qk_full[s ^ 1], ((n + 1) >> 1) & 1);
-            tc_fence_after();
-            issue_s(n + 1, t);
+      // Per tile: [wait P_t(n)] -> O_t(n) -> [wait O_t(n) copied out] -> S_t(n+1) -> ...  The two chains are independent;
+      // the barriers are PROBED (mbarrier.test_wait) in turn, so whichever softmax group gets there first is served first
+      // and the groups settle half a period apart: the tensor core work of one hides behind the arithmetic of the other.
+      int pn[2] = {0, 0};                  // pair index the tile is in
+      int ph[2] = {0, 0};                  // 0: O_t(pn) is next, 1: S_t(pn + 1) is next
+      int live = nt;
+      if (nt < 2) ph[1] = 2;
+      uint32_t spins = 0;
+      long long t0 = 0;
+      while (live > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int n = pn[t];
+          if (ph[t] == 0) {
+            if (mbar_test(&p_ready[t], n & 1) && mbar_test(&v_full[n & 1], (n >> 1) & 1)) {
+              tc_fence_after();
+              issue_o(n, t);
+              umma_commit(&stage_free[n & 1]);                 // every MMA of this tile that reads the ring stage has been issued
+              if (n + 1 < N) ph[t] = 1; else { ph[t] = 2; --live; }
+              progressed = true;
+            }
+          } else if (ph[t] == 1) {
+            if (mbar_test(&o_read[t], n & 1) && mbar_test(&qk_full[(n + 1) & 1], ((n + 1) >> 1) & 1)) {
+              tc_fence_after();
+              issue_s(n + 1, t);
+              pn[t] = n + 1;
+              ph[t] = 0;
+              progressed = true;
+            }
           }
         }
-      }
-      __syncwarp();
-      if (n + 2 < N) {
-        // ring stage s is reloaded for pair n+2 once its MMAs have completed; its mask row is not read after p_ready(n)
-        if (lane == 0) {
-          mbar_wait(&stage_free[s], (n >> 1) & 1);
-          load_pair(n + 2);
+        if (progressed) { spins = 0; t0 = 0; }
+        else if (((++spins) & 0xFFFFu) == 0) {                 // watchdog: a protocol bug traps instead of hanging the GPU
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 8000000000LL) { printf("mmfb: attention forward issue loop timeout (block %d)\n", (int)blockIdx.x); __trap(); }
         }
-        __syncwarp();
-        load_mask(n + 2);
       }
     }
   } else {
@@ -573,16 +592,17 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t treg = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * REG;
       const int nch = (p.Skv + 31) / 32;
       const int c0 = half * 4;                                // this thread's chunks: c0 .. c0+3 (keys 128*half ..)
-      const int my_chunks = min(4, max(0, (SKP / 32) - c0));  // chunks inside the padded key range
+      const bool have = half < nkt;                           // this half of the key range exists
       float* gMax = sMax + t * 256;
       float* gSum = sSum + t * 256;
       const int bar_id = 1 + t;
+      const uint32_t pcol = half == 0 ? COL_PLO : COL_PHI;
       for (int n = 0; n < N; ++n) {
         const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
         const int h = it % p.H, b = it / p.H;
         const int q = t * 128 + row;
         const bool valid = q < p.Sq;
-        const float4* m4 = reinterpret_cast<const float4*>(sMask + (n & 1) * 256);
+        const float4* m4 = reinterpret_cast<const float4*>(sMask + (n & 1) * 256) + c0 * 8;
         // keep-bit words of this thread's chunks: fetched before the score barrier
         uint32_t bits[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         if (p.dmask != nullptr && valid) {
@@ -592,38 +612,50 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (c0 + k < nch) bits[k] = __ldg(dm + c0 + k);
         }
         mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
-        const uint32_t act = sAct[n & 1] >> c0;                // bit k: this thread's chunk k has an attendable key
+        const uint32_t act = have ? (sAct[n & 1] >> c0) & 0xFu : 0u;   // bit k: chunk k of this thread has an attendable key
+        const bool on0 = act & 1u, on1 = act & 2u, on2 = act & 4u, on3 = act & 8u;
         mbar_wait(&s_ready[t], n & 1);
         tc_fence_after();
-        // ---- pass 1: row maximum over this thread's columns ----
+        // ---- pass 1: row maximum; the load of the next chunk is in flight while this one is reduced ----
+        uint32_t ra[32], rb[32];
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int k = 0; k < my_chunks; ++k) {
-          if (!((act >> k) & 1u)) continue;
-          uint32_t r[32];
-          tmem_ld32(treg + (c0 + k) * 32, r);
-          tmem_ld_wait();
-          fwd_chunk_max(r, m4 + (c0 + k) * 8, p.scale2, mx);
-        }
+        if (on0) tmem_ld32(treg + (c0 + 0) * 32, ra);
+        tmem_ld_wait();
+        if (on1) tmem_ld32(treg + (c0 + 1) * 32, rb);
+        if (on0) fwd_chunk_max(ra, m4 + 0, p.scale2, mx);
+        tmem_ld_wait();
+        if (on2) tmem_ld32(treg + (c0 + 2) * 32, ra);
+        if (on1) fwd_chunk_max(rb, m4 + 8, p.scale2, mx);
+        tmem_ld_wait();
+        if (on3) tmem_ld32(treg + (c0 + 3) * 32, rb);
+        if (on2) fwd_chunk_max(ra, m4 + 16, p.scale2, mx);
+        tmem_ld_wait();
+        if (on3) fwd_chunk_max(rb, m4 + 24, p.scale2, mx);
         gMax[half * 128 + row] = mx;
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
         mx = fmaxf(gMax[row], gMax[128 + row]);
-        // ---- pass 2: probabilities -> tensor memory, over score columns this thread has already consumed ----
+        // ---- pass 2, last chunk first (chunks 3 and 2 are still in rb / ra): probabilities -> tensor memory ----
         float sum = 0.0f;
-        const uint32_t pcol = half == 0 ? COL_PLO : COL_PHI;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          uint32_t pk[16];
-          if (k < my_chunks && ((act >> k) & 1u)) {
-            uint32_t r[32];
-            tmem_ld32(treg + (c0 + k) * 32, r);
-            tmem_ld_wait();
-            fwd_chunk_exp(r, m4 + (c0 + k) * 8, p.scale2, mx, bits[k], sum, pk);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          }
-          if (c0 + k < nkt * 4 && ((act >> k) & 1u)) tmem_st16(treg + pcol + k * 16, pk);
+        uint32_t pk[16];
+        if (on3) {
+          fwd_chunk_exp(rb, m4 + 24, p.scale2, mx, bits[3], sum, pk);
+          tmem_st16(treg + pcol + 48, pk);
+        }
+        if (on1) tmem_ld32(treg + (c0 + 1) * 32, rb);
+        if (on2) {
+          fwd_chunk_exp(ra, m4 + 16, p.scale2, mx, bits[2], sum, pk);
+          tmem_st16(treg + pcol + 32, pk);
+        }
+        tmem_ld_wait();
+        if (on0) tmem_ld32(treg + (c0 + 0) * 32, ra);
+        if (on1) {
+          fwd_chunk_exp(rb, m4 + 8, p.scale2, mx, bits[1], sum, pk);
+          tmem_st16(treg + pcol + 16, pk);
+        }
+        tmem_ld_wait();
+        if (on0) {
+          fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk);
+          tmem_st16(treg + pcol + 0, pk);
         }
         gSum[half * 128 + row] = sum;
         tmem_st_wait();
@@ -634,8 +666,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // ---- O_t: 32 of the 64 columns per thread ----
         mbar_wait(&o_ready[t], n & 1);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld32(treg + COL_O + half * 32, r);
+        tmem_ld32(treg + COL_O + half * 32, ra);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&o_read[t]);
@@ -647,18 +678,18 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[qd * 8 + 0]) * inv, __uint_as_float(r[qd * 8 + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(r[qd * 8 + 2]) * inv, __uint_as_float(r[qd * 8 + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(r[qd * 8 + 4]) * inv, __uint_as_float(r[qd * 8 + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * inv, __uint_as_float(r[qd * 8 + 7]) * inv);
+            o.x = pack_bf16x2(__uint_as_float(ra[qd * 8 + 0]) * inv, __uint_as_float(ra[qd * 8 + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(ra[qd * 8 + 2]) * inv, __uint_as_float(ra[qd * 8 + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(ra[qd * 8 + 4]) * inv, __uint_as_float(ra[qd * 8 + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(ra[qd * 8 + 6]) * inv, __uint_as_float(ra[qd * 8 + 7]) * inv);
             dst[qd] = o;
           }
           if (p.ctx32 != nullptr) {
             float4* d32 = reinterpret_cast<float4*>(p.ctx32 + tok * (p.H * D) + h * D + half * 32);
 #pragma unroll
             for (int qd = 0; qd < 8; ++qd)
-              d32[qd] = make_float4(__uint_as_float(r[qd * 4 + 0]) * inv, __uint_as_float(r[qd * 4 + 1]) * inv,
-                                    __uint_as_float(r[qd * 4 + 2]) * inv, __uint_as_float(r[qd * 4 + 3]) * inv);
+              d32[qd] = make_float4(__uint_as_float(ra[qd * 4 + 0]) * inv, __uint_as_float(ra[qd * 4 + 1]) * inv,
+                                    __uint_as_float(ra[qd * 4 + 2]) * inv, __uint_as_float(ra[qd * 4 + 3]) * inv);
           }
         }
       }
@@ -666,7 +697,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1679,7 +1710,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       }
       const int n_pairs = a.heads * a.B;
       const int grid_p = n_pairs < num_sms() ? n_pairs : num_sms();
-      MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, 544, smem_p, stream, tmQ, tmK128, tmV128, p, n_pairs);
+      MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, FWD_PAIR_THREADS, smem_p, stream, tmQ, tmK128, tmV128, p, n_pairs);
       cudaError_t e2 = cudaGetLastError();
       if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd_pair launch: %s", cudaGetErrorString(e2));
       count_launch();

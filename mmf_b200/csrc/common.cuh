@@ -82,6 +82,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (mbarrier.test_wait returns at once; try_wait may suspend the thread for a hardware time slice)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Wait with a watchdog: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
 // The spin loop is kept to three instructions per failed probe (try_wait itself suspends the warp in hardware for a
 // while before it returns false): the clock is read only every 2^16 probes.  The round-1 loop read the clock on every
