@@ -402,7 +402,8 @@ __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const flo
 }
 
 constexpr int FWD_PAIR_THREADS = 576;       // 16 softmax warps + 1 MMA-issue warp + 1 loader warp
-__global__ void __maxnreg__(112)
+// 18 warps put 5 on one scheduler partition (16 K registers each): at most 96 registers per thread can launch
+__global__ void __launch_bounds__(FWD_PAIR_THREADS, 1)
 attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnFwdDev p, int n_pairs) {
   griddep_launch();
@@ -1613,6 +1614,365 @@ attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// fused backward, persistent (d = 64, Sq, Skv <= 256) - the default
+//
+// attn_bwd_fused16_kernel is launched once per (batch, head): 13.5 waves of CTAs that each pay the tensor-memory
+// allocation, barrier set-up, the (exposed) loads of the row statistics, the first 64 KB of operand tiles and, at the end,
+// the drain of dK / dV / dQ - about a third of the ~18 us a CTA lives (ncu round 2: 50 % of the stall samples on loads and
+// barriers, tensor pipe 15 % active).  This kernel keeps ONE CTA per SM alive over its share of the (batch, head) items:
+//   * same arithmetic, tensor-memory map, MMAs and accumulation order as the 16-warp kernel (bit-identical results);
+//   * warp 17 is a loader: the four operand slot groups (K_0 V_0 | Q_0 dO_0 | Q_1 dO_1 | K_1 V_1) are refilled for the NEXT
+//     item as soon as the last accumulation that reads them has completed (tile_free barriers committed by the MMA
+//     thread), and the row statistics / mask row / active-chunk bits of the next item are staged in a second buffer;
+//   * the score MMAs of the next item's first block pair are issued right after the last pair's probabilities have been
+//     read, so the tensor core and the TMA engine work through the epilogue stores of the previous item.
+// 576 threads: warps 0..15 compute (thread = query row x 32-column chunk), warp 16 = MMA issue, warp 17 = loader.
+// ----------------------------------------------------------------------------------------------
+constexpr int BWD_PERS_THREADS = 576;
+template <bool DROP>
+__global__ void __launch_bounds__(BWD_PERS_THREADS, 1)
+attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     AttnBwdFusedDev p, int n_items) {
+  griddep_launch();
+  griddep_wait();
+  constexpr int D = 64;
+  constexpr int TILE = 16384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sQ = smem;                 // [2][128 x 128B]
+  uint8_t* sdO = sQ + 2 * TILE;
+  uint8_t* sK = sdO + 2 * TILE;
+  uint8_t* sV = sK + 2 * TILE;
+  uint8_t* sP = sV + 2 * TILE;        // [128 q x 128 kv] bf16 = 2 chunks of [128 x 128B]
+  uint8_t* sDS = sP + 2 * TILE;
+  float* sStat = reinterpret_cast<float*>(sDS + 2 * TILE);   // [2 buffers][lse 256 | delta 256 | mask 256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 768);
+  uint64_t* q_full = bars;            // [2]  Q_i + dO_i          (phase = item parity)
+  uint64_t* kv_full = bars + 2;       // [2]  K_j + V_j           (phase = item parity)
+  uint64_t* tile_free = bars + 4;     // [4]  K0V0 | Q0dO0 | Q1dO1 | K1V1: last reader of this item has completed
+  uint64_t* stat_full = bars + 8;     // [2 buffers] 32 arrivals
+  uint64_t* s_ready = bars + 10;      // phase = pair counter parity
+  uint64_t* p_ready = bars + 11;      // 512 arrivals
+  uint64_t* acc_done = bars + 12;
+  uint64_t* kv_read = bars + 13;      // 512 arrivals, phase = key-block counter parity
+  uint64_t* dq_read = bars + 14;      // 512 arrivals, phase = item parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* sAct = tmem_slot + 1;     // [2 buffers] bit c: 32-key chunk c has an attendable key
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ni = (p.Sq + 127) / 128, nj = (p.Skv + 127) / 128;
+  const int np = ni * nj;
+  const int N = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto item_hb = [&](int n, int& h, int& b) {
+    const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+    h = it % p.H;
+    b = it / p.H;
+  };
+
+  if (warp == 17) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      for (int x = 0; x < 2; ++x) { mbar_init(&q_full[x], 1); mbar_init(&kv_full[x], 1); mbar_init(&stat_full[x], 32); }
+      for (int x = 0; x < 4; ++x) mbar_init(&tile_free[x], 1);
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, 512);
+      mbar_init(acc_done, 1);
+      mbar_init(kv_read, 512);
+      mbar_init(dq_read, 512);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 17) {
+    // ------------------------------------ loader ------------------------------------
+    auto load_kv = [&](int n, int j) {     // lane 0
+      int h, b;
+      item_hb(n, h, b);
+      mbar_expect_tx(&kv_full[j], 2 * TILE);
+      tma_load_3d(sK + j * TILE, &tmK, &kv_full[j], h * D, j * 128, b);
+      tma_load_3d(sV + j * TILE, &tmV, &kv_full[j], h * D, j * 128, b);
+    };
+    auto load_q = [&](int n, int i) {      // lane 0
+      int h, b;
+      item_hb(n, h, b);
+      mbar_expect_tx(&q_full[i], 2 * TILE);
+      tma_load_3d(sQ + i * TILE, &tmQ, &q_full[i], h * D, i * 128, b);
+      tma_load_3d(sdO + i * TILE, &tmdO, &q_full[i], h * D, i * 128, b);
+    };
+    auto load_stats = [&](int n) {         // whole warp: lse2, delta, log2-domain mask row, active-chunk bits
+      int h, b;
+      item_hb(n, h, b);
+      const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+      float* st = sStat + (n & 1) * 768;
+      float lv[8], dv[8], mv[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const int i = lane + 32 * x;
+        const bool qv = i < p.Sq, kv = i < p.Skv;
+        lv[x] = qv ? p.lse2[bh * p.Sq + i] : INFINITY;
+        dv[x] = qv ? p.delta[bh * p.Sq + i] : 0.0f;
+        mv[x] = kv ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+      }
+      // 32-key chunks whose keys are ALL masked out (additive -10000 or beyond Skv) have P = 0 and dS = 0 exactly: their
+      // arithmetic is skipped (zeros are stored).  A sample without any attendable key keeps every chunk.
+      uint32_t act = 0;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const int i = lane + 32 * x;
+        st[i] = lv[x];
+        st[256 + i] = dv[x];
+        st[512 + i] = mv[x];
+        if (__any_sync(0xffffffffu, mv[x] > -5000.0f)) act |= 1u << x;
+      }
+      if (act == 0) act = 0xFFu;
+      if (lane == 0) sAct[n & 1] = act;
+      __syncwarp();
+      mbar_arrive(&stat_full[n & 1]);
+    };
+    if (N > 0) {
+      if (lane == 0) {
+        load_kv(0, 0);
+        for (int i = 0; i < ni; ++i) load_q(0, i);
+        for (int j = 1; j < nj; ++j) load_kv(0, j);
+      }
+      load_stats(0);
+    }
+    for (int n = 0; n + 1 < N; ++n) {
+      // statistics of item n+1 go to the buffer item n-1 used: every compute thread has left item n-1 (dq_read)
+      if (n >= 1) mbar_wait(dq_read, (n - 1) & 1);
+      load_stats(n + 1);
+      // operand slots in the order in which item n releases them (pair index of the last reader, j outer / i inner)
+      for (int pidx = 0; pidx < np; ++pidx) {
+        for (int j = 0; j < nj; ++j)
+          if (pidx == j * ni + ni - 1) {
+            mbar_wait(&tile_free[j == 0 ? 0 : 3], n & 1);
+            if (lane == 0) load_kv(n + 1, j);
+          }
+        for (int i = 0; i < ni; ++i)
+          if (pidx == (nj - 1) * ni + i) {
+            mbar_wait(&tile_free[1 + i], n & 1);
+            if (lane == 0) load_q(n + 1, i);
+          }
+      }
+    }
+  } else if (warp == 16) {
+    // ------------------------------------ MMA issue ------------------------------------
+    if (lane == 0 && N > 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      const uint32_t idesc_q = umma_idesc_bf16(128, D, false, true);   // A K-major,  B MN-major
+      const uint32_t idesc_t = umma_idesc_bf16(128, D, true, true);    // A MN-major, B MN-major
+      auto issue_scores = [&](int n, int i, int j) {      // S = Q_i K_j^T, dP = dO_i V_j^T of item n
+        mbar_wait(&q_full[i], n & 1);
+        mbar_wait(&kv_full[j], n & 1);
+        tc_fence_after();
+        const uint32_t aQ_ = smem_u32(sQ + i * TILE), adO_ = smem_u32(sdO + i * TILE);
+        const uint32_t aK_ = smem_u32(sK + j * TILE), aV_ = smem_u32(sV + j * TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + COL_S, umma_desc_sw128(aQ_ + kk * 32, 16, 1024), umma_desc_sw128(aK_ + kk * 32, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + COL_DP, umma_desc_sw128(adO_ + kk * 32, 16, 1024), umma_desc_sw128(aV_ + kk * 32, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(s_ready);
+      };
+      uint32_t g = 0;                    // pair counter over all items
+      uint32_t kb = 0;                   // key-block counter over all items
+      issue_scores(0, 0, 0);
+      for (int n = 0; n < N; ++n) {
+        for (int j = 0; j < nj; ++j, ++kb) {
+          for (int i = 0; i < ni; ++i, ++g) {
+            const int pidx = j * ni + i;
+            const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
+            const uint32_t aK = smem_u32(sK + j * TILE);
+            mbar_wait(p_ready, g & 1);               // S/dP of this pair have been read, P'/dS' are in shared memory
+            const bool last_pair = pidx == np - 1;
+            if (!last_pair) {
+              const int i2 = (i + 1 < ni) ? i + 1 : 0, j2 = (i + 1 < ni) ? j : j + 1;
+              issue_scores(n, i2, j2);               // next pair of this item: its tiles are resident
+            }
+            // accumulators that are overwritten (not accumulated) must have been read out by the compute threads
+            if (i == 0 && kb > 0) mbar_wait(kv_read, (kb - 1) & 1);
+            if (pidx == 0 && n > 0) mbar_wait(dq_read, (n - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {   // K dimension = the 128 keys of block j
+              const uint32_t aoff = (kk >> 2) * TILE + (kk & 3) * 32;
+              umma_bf16(tmem_base + COL_DQ + i * D, umma_desc_sw128(smem_u32(sDS) + aoff, 16, 1024),
+                        umma_desc_sw128(aK + kk * 2048, TILE, 1024), idesc_q, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {   // K dimension = the 128 queries of block i; A = transposed views
+              umma_bf16(tmem_base + COL_DK, umma_desc_sw128(smem_u32(sDS) + kk * 2048, TILE, 1024),
+                        umma_desc_sw128(aQ + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + COL_DV, umma_desc_sw128(smem_u32(sP) + kk * 2048, TILE, 1024),
+                        umma_desc_sw128(adO + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(acc_done);
+            // operand slots whose last reader this pair was
+            if (i == ni - 1) umma_commit(&tile_free[j == 0 ? 0 : 3]);
+            if (j == nj - 1) umma_commit(&tile_free[1 + i]);
+            // first pair of the next item AFTER the accumulations: its tiles may still be in flight
+            if (last_pair && n + 1 < N) issue_scores(n + 1, 0, 0);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------ compute ------------------------------------
+    const int quarter = warp & 3, c = warp >> 2;          // c: this thread's 32-column chunk of the key block
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t g = 0, kb = 0;
+    for (int n = 0; n < N; ++n) {
+      int h, b;
+      item_hb(n, h, b);
+      const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+      const float* sLse = sStat + (n & 1) * 768;
+      const float* sDel = sLse + 256;
+      const float* sMsk = sLse + 512;
+      mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      const uint32_t act = sAct[n & 1];
+      for (int j = 0; j < nj; ++j, ++kb) {
+        for (int i = 0; i < ni; ++i, ++g) {
+          const int q = i * 128 + row;
+          const float l2 = sLse[q], dl = sDel[q];
+          uint32_t bits = 0xFFFFFFFFu;
+          if (DROP && q < p.Sq) {
+            const int w = j * 4 + c;
+            if (w < p.W) bits = __ldg(p.dmask + (bh * p.Sq + q) * p.W + w);
+          }
+          const float4* m4 = reinterpret_cast<const float4*>(sMsk + j * 128 + c * 32);
+          uint32_t wds[16], wp[16];                           // packed bf16 pairs of dS' and P' for this thread's 32 columns
+          mbar_wait(s_ready, g & 1);
+          tc_fence_after();
+          const bool chunk_on = (act >> (j * 4 + c)) & 1u;
+          if (!chunk_on) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { wds[e] = 0u; wp[e] = 0u; }
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2 && chunk_on; ++hh) {
+            uint32_t rs[16], rd[16];
+            tmem_ld16(trow + COL_S + c * 32 + hh * 16, rs);
+            tmem_ld16(trow + COL_DP + c * 32 + hh * 16, rd);
+            tmem_ld_wait();
+            const uint64_t sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-l2, -l2), ndl2 = pk2(-dl, -dl);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 m = m4[hh * 4 + q4];
+              const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int k = 0; k < 4; k += 2) {
+                const int jx = q4 * 4 + k;                    // column inside the 16-column half
+                const int bx = hh * 16 + jx;                  // bit index inside the 32-column chunk
+                float ds0, ds1, pv0, pv1, a0, a1;
+                upk2(add2(fma2(pk2(__uint_as_float(rs[jx]), __uint_as_float(rs[jx + 1])), sc2, pk2(mm[k], mm[k + 1])), nl2), a0, a1);
+                const uint64_t pr = pk2(ex2_approx(a0), ex2_approx(a1));
+                const uint64_t dp = pk2(__uint_as_float(rd[jx]), __uint_as_float(rd[jx + 1]));
+                if (DROP) {
+                  const uint64_t kf = pk2(((bits >> bx) & 1u) ? p.dscale : 0.0f, ((bits >> (bx + 1)) & 1u) ? p.dscale : 0.0f);
+                  upk2(mul2(pr, fma2(dp, kf, ndl2)), ds0, ds1);
+                  upk2(mul2(pr, kf), pv0, pv1);
+                } else {
+                  upk2(mul2(pr, add2(dp, ndl2)), ds0, ds1);
+                  upk2(pr, pv0, pv1);
+                }
+                wds[hh * 8 + (jx >> 1)] = pack_bf16x2(ds0, ds1);
+                wp[hh * 8 + (jx >> 1)] = pack_bf16x2(pv0, pv1);
+              }
+            }
+          }
+          // the accumulations of the previous pair still read P'/dS' while the arithmetic above ran
+          if (g > 0) mbar_wait(acc_done, (g - 1) & 1);
+          uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
+          uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const int chunk = ((c & 1) * 4 + qd) ^ (row & 7);
+            *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(wds[qd * 4], wds[qd * 4 + 1], wds[qd * 4 + 2], wds[qd * 4 + 3]);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(wp[qd * 4], wp[qd * 4 + 1], wp[qd * 4 + 2], wp[qd * 4 + 3]);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(p_ready);
+        }
+        // ---- dK_j, dV_j are complete: rows = keys of block j; this thread stores 16 of the 64 columns of each ----
+        mbar_wait(acc_done, (g - 1) & 1);
+        tc_fence_after();
+        {
+          const int kvr = j * 128 + row;
+          uint32_t rk[16], rv[16];
+          tmem_ld16(trow + COL_DK + c * 16, rk);
+          tmem_ld16(trow + COL_DV + c * 16, rv);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(kv_read);
+          if (kvr < p.Skv) {
+            uint4* dk4 = reinterpret_cast<uint4*>(p.dk + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dk + h * D + c * 16);
+            uint4* dv4 = reinterpret_cast<uint4*>(p.dv + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dv + h * D + c * 16);
+#pragma unroll
+            for (int qd = 0; qd < 2; ++qd) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(rk[qd * 8 + 0]) * p.scale, __uint_as_float(rk[qd * 8 + 1]) * p.scale);
+              o.y = pack_bf16x2(__uint_as_float(rk[qd * 8 + 2]) * p.scale, __uint_as_float(rk[qd * 8 + 3]) * p.scale);
+              o.z = pack_bf16x2(__uint_as_float(rk[qd * 8 + 4]) * p.scale, __uint_as_float(rk[qd * 8 + 5]) * p.scale);
+              o.w = pack_bf16x2(__uint_as_float(rk[qd * 8 + 6]) * p.scale, __uint_as_float(rk[qd * 8 + 7]) * p.scale);
+              dk4[qd] = o;
+              o.x = pack_bf16x2(__uint_as_float(rv[qd * 8 + 0]), __uint_as_float(rv[qd * 8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(rv[qd * 8 + 2]), __uint_as_float(rv[qd * 8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(rv[qd * 8 + 4]), __uint_as_float(rv[qd * 8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(rv[qd * 8 + 6]), __uint_as_float(rv[qd * 8 + 7]));
+              dv4[qd] = o;
+            }
+          }
+        }
+      }
+      // ---- dQ_i: rows = queries (every accumulation of the item is complete: acc_done of its last pair was waited for) ----
+      uint32_t rq[2][16];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (i < ni) tmem_ld16(trow + COL_DQ + i * D + c * 16, rq[i]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_read);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = i * 128 + row;
+        if (i < ni && q < p.Sq) {
+          uint4* dq4 = reinterpret_cast<uint4*>(p.dq + (static_cast<int64_t>(b) * p.Sq + q) * p.ld_dq + h * D + c * 16);
+#pragma unroll
+          for (int qd = 0; qd < 2; ++qd) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 0]) * p.scale, __uint_as_float(rq[i][qd * 8 + 1]) * p.scale);
+            o.y = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 2]) * p.scale, __uint_as_float(rq[i][qd * 8 + 3]) * p.scale);
+            o.z = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 4]) * p.scale, __uint_as_float(rq[i][qd * 8 + 5]) * p.scale);
+            o.w = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 6]) * p.scale, __uint_as_float(rq[i][qd * 8 + 7]) * p.scale);
+            dq4[qd] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d].  One warp per token row, 16-byte vector loads; a head of D
 // elements is owned by D/8 consecutive lanes and reduced with shuffles (coalesced 512 B / 1 KB per warp access).
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
@@ -1795,7 +2155,22 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     // default: the 16-warp kernel (measured 307 us against 336 us per layer at the bench shape, profiles/r2_kbench_before.json);
     // MMFB_ATTN_BWD=8 (read per call) selects the 8-warp kernel for A/B runs
     const char* w_env = getenv("MMFB_ATTN_BWD");
-    if (w_env == nullptr || w_env[0] != '8') {
+    if (w_env == nullptr || w_env[0] == 'p') {
+      // default: the persistent kernel (one CTA per SM over its share of the (batch, head) items); MMFB_ATTN_BWD=16 / 8
+      // (read per call) select the one-CTA-per-item kernels for A/B runs
+      const int smem_p = 12 * 16384 + 2 * 768 * 4 + 256 + 1024;
+      static bool pers_attr = false;
+      if (!pers_attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_pers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+        if (e != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_bwd(persistent) smem attr: %s", cudaGetErrorString(e));
+        pers_attr = true;
+      }
+      const int n_items = a.heads * a.B;
+      const int grid_p = n_items < num_sms() ? n_items : num_sms();
+      if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_pers_kernel<true>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items);
+      else MMFB_LAUNCH(attn_bwd_pers_kernel<false>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items);
+    } else if (w_env[0] != '8') {
       static bool w16_attr = false;
       if (!w16_attr) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -363,6 +363,196 @@ ln_bwd_lean_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __rest
   }
 }
 
+// Single-pass LayerNorm backward, streaming variant (MMFB_LN_BWD=stream).  ncu of the kernel above (round 2, call 6): issue
+// slots 39 % used, 49 % of the stall samples on the global loads of the row a warp is about to process - a warp loads,
+// computes, stores, and only the other 15 warps of the SM cover its load latency.  Here every warp owns a private ring of
+// ST row slots in shared memory that its lane 0 fills with bulk async copies (cp.async.bulk, one per tensor row,
+// completion on a per-slot mbarrier) ST rows ahead, so ST x 16 warps x 3 KB are in flight per SM whatever the warps are
+// doing, the row lives in shared memory across the two phases (no row registers), and the arithmetic is the packed-fp32
+// form of the lean kernel.  Rows are read from HBM once; dy / dz are stored straight from registers.
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+template <int NV, bool HAS_DX2, int ST>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
+ln_bwd_stream_kernel(const bf16* __restrict__ dx, int64_t lddx, const bf16* __restrict__ dx2, int64_t lddx2,
+                     const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const bf16* __restrict__ gamma, bf16* __restrict__ dy, int64_t lddy,
+                     bf16* __restrict__ dz, int64_t lddz, const uint32_t* __restrict__ dmask, int64_t ldmask, float dscale,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  griddep_launch();
+  griddep_wait();
+  constexpr int NT = HAS_DX2 ? 3 : 2;                 // tensors per slot: dx, y (, dx2)
+  constexpr int ROWB = NV * 512;                      // bytes reserved per tensor row in a slot
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  uint8_t* ring = ln_smem;                                                        // [ROW_WARPS][ST][NT][ROWB]
+  float* red = reinterpret_cast<float*>(ring + ROW_WARPS * ST * NT * ROWB);       // [ROW_WARPS][256]
+  float* sG = red + ROW_WARPS * 256;                                              // [NV * 256]
+  uint32_t* sKeep = reinterpret_cast<uint32_t*>(sG + NV * 256);                   // [256][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sKeep + 1024);                     // [ROW_WARPS][ST]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < NV * 256; c += ROW_WARPS * 32) sG[c] = c < H ? __bfloat162float(gamma[c]) : 0.0f;
+  {
+    const uint32_t b = threadIdx.x;          // 256 threads <-> the 256 patterns of 8 keep-bits
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      sKeep[b * 4 + k] = (((b >> (2 * k)) & 1u) ? 0x0000ffffu : 0u) | (((b >> (2 * k + 1)) & 1u) ? 0xffff0000u : 0u);
+  }
+  if (threadIdx.x < ROW_WARPS * ST) mbar_init(&full[threadIdx.x], 1);
+  fence_barrier_init();
+  __syncthreads();
+  uint8_t* my = ring + warp * (ST * NT * ROWB);
+  uint64_t* my_full = full + warp * ST;
+  const uint32_t row_bytes = static_cast<uint32_t>(H) * 2u;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * ROW_WARPS;
+  const int64_t row_first = static_cast<int64_t>(blockIdx.x) * ROW_WARPS + warp;
+  auto fill = [&](int slot, int64_t row) {            // lane 0
+    uint8_t* d = my + slot * (NT * ROWB);
+    mbar_expect_tx(&my_full[slot], NT * row_bytes);
+    bulk_load_1d(d, dx + row * lddx, row_bytes, &my_full[slot]);
+    bulk_load_1d(d + ROWB, y + row * ldy, row_bytes, &my_full[slot]);
+    if (HAS_DX2) bulk_load_1d(d + 2 * ROWB, dx2 + row * lddx2, row_bytes, &my_full[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s0 = 0; s0 < ST; ++s0)
+      if (row_first + s0 * stride < M) fill(s0, row_first + s0 * stride);
+  }
+  uint64_t ag[NV][4], ab[NV][4], az[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ag[i][k] = 0ull; ab[i][k] = 0ull; az[i][k] = 0ull; }
+  const float invH = 1.0f / static_cast<float>(H);
+  const uint64_t ds2 = pk2(dscale, dscale);
+  float mu_n = 0.0f, rs_n = 0.0f;
+  if (row_first < M) { mu_n = mean[row_first]; rs_n = rstd[row_first]; }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t row = row_first; row < M; row += stride) {
+    const float mu = mu_n, rs = rs_n;
+    if (row + stride < M) { mu_n = mean[row + stride]; rs_n = rstd[row + stride]; }   // one row ahead
+    uint32_t keepw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      keepw[i] = 0xFFu;
+      if (dmask != nullptr && col < H) keepw[i] = (__ldg(dmask + row * ldmask + (col >> 5)) >> (col & 31)) & 0xFFu;
+    }
+    const float nmr = -mu * rs;
+    const uint64_t rs2 = pk2(rs, rs), nmr2 = pk2(nmr, nmr);
+    const uint8_t* sl = my + slot * (NT * ROWB);
+    mbar_wait(&my_full[slot], phase);
+    uint64_t s1 = 0ull, s2 = 0ull;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        const uint4 dwv = *reinterpret_cast<const uint4*>(sl + col * 2);
+        const uint4 ywv = *reinterpret_cast<const uint4*>(sl + ROWB + col * 2);
+        const uint32_t da[4] = {dwv.x, dwv.y, dwv.z, dwv.w};
+        const uint32_t ya[4] = {ywv.x, ywv.y, ywv.z, ywv.w};
+        uint32_t xa[4] = {0u, 0u, 0u, 0u};
+        if (HAS_DX2) {
+          const uint4 t = *reinterpret_cast<const uint4*>(sl + 2 * ROWB + col * 2);
+          xa[0] = t.x; xa[1] = t.y; xa[2] = t.z; xa[3] = t.w;
+        }
+        const float4 ga = *reinterpret_cast<const float4*>(sG + col), gb = *reinterpret_cast<const float4*>(sG + col + 4);
+        const uint64_t g2[4] = {pk2(ga.x, ga.y), pk2(ga.z, ga.w), pk2(gb.x, gb.y), pk2(gb.z, gb.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t d2 = unpack2(da[k]);
+          if (HAS_DX2) d2 = add2(d2, unpack2(xa[k]));
+          const uint64_t xh2 = fma2(unpack2(ya[k]), rs2, nmr2);
+          const uint64_t dg2 = mul2(d2, g2[k]);
+          s1 = add2(s1, dg2);
+          s2 = fma2(dg2, xh2, s2);
+          ag[i][k] = fma2(d2, xh2, ag[i][k]);
+          ab[i][k] = add2(ab[i][k], d2);
+        }
+      }
+    }
+    float s1a, s1b, s2a, s2b;
+    upk2(s1, s1a, s1b);
+    upk2(s2, s2a, s2b);
+    const float m1 = warp_sum(s1a + s1b) * invH, m2 = warp_sum(s2a + s2b) * invH;
+    const uint64_t nA2 = pk2(-rs * m1, -rs * m1), nB2 = pk2(-rs * m2, -rs * m2);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (col < H) {
+        const uint4 dwv = *reinterpret_cast<const uint4*>(sl + col * 2);
+        const uint4 ywv = *reinterpret_cast<const uint4*>(sl + ROWB + col * 2);
+        const uint32_t da[4] = {dwv.x, dwv.y, dwv.z, dwv.w};
+        const uint32_t ya[4] = {ywv.x, ywv.y, ywv.z, ywv.w};
+        uint32_t xa[4] = {0u, 0u, 0u, 0u};
+        if (HAS_DX2) {
+          const uint4 t = *reinterpret_cast<const uint4*>(sl + 2 * ROWB + col * 2);
+          xa[0] = t.x; xa[1] = t.y; xa[2] = t.z; xa[3] = t.w;
+        }
+        const float4 ga = *reinterpret_cast<const float4*>(sG + col), gb = *reinterpret_cast<const float4*>(sG + col + 4);
+        const uint64_t g2[4] = {pk2(ga.x, ga.y), pk2(ga.z, ga.w), pk2(gb.x, gb.y), pk2(gb.z, gb.w)};
+        uint32_t keep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (dmask != nullptr) {
+          const uint4 kk = *reinterpret_cast<const uint4*>(sKeep + keepw[i] * 4);
+          keep[0] = kk.x; keep[1] = kk.y; keep[2] = kk.z; keep[3] = kk.w;
+        }
+        uint32_t ow[4], zw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint64_t d2 = unpack2(da[k]);
+          if (HAS_DX2) d2 = add2(d2, unpack2(xa[k]));
+          const uint64_t xh2 = fma2(unpack2(ya[k]), rs2, nmr2);
+          const uint64_t o2 = fma2(nB2, xh2, fma2(d2, mul2(g2[k], rs2), nA2));
+          ow[k] = pack2(o2);
+          if (dmask != nullptr) {
+            zw[k] = pack2(mul2(o2, ds2)) & keep[k];
+            az[i][k] = add2(az[i][k], unpack2(zw[k]));
+          } else {
+            zw[k] = ow[k];
+            az[i][k] = add2(az[i][k], o2);
+          }
+        }
+        if (dy != nullptr) *reinterpret_cast<uint4*>(dy + row * lddy + col) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (dz != nullptr && (dmask != nullptr || dz != dy))
+          *reinterpret_cast<uint4*>(dz + row * lddz + col) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+      }
+    }
+    // the slot has been read by every lane: refill it with the row ST steps ahead
+    __syncwarp();
+    if (lane == 0 && row + ST * stride < M) {
+      fence_proxy_async();
+      fill(slot, row + ST * stride);
+    }
+    if (++slot == ST) { slot = 0; phase ^= 1u; }
+  }
+  // block reduction of the three column-sum sets, 256 columns at a time, then one atomic per column
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 256 >= H) break;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        upk2(which == 0 ? ag[i][k] : (which == 1 ? ab[i][k] : az[i][k]), lo, hi);
+        red[warp * 256 + lane * 8 + 2 * k] = lo;
+        red[warp * 256 + lane * 8 + 2 * k + 1] = hi;
+      }
+      __syncthreads();
+      const int c = threadIdx.x;  // 256 threads <-> 256 columns
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < ROW_WARPS; ++w) t += red[w * 256 + c];
+      if (i * 256 + c < H) atomicAdd(dst + i * 256 + c, t);
+    }
+  }
+}
+
 // Single-pass LayerNorm backward, tile variant (staged: MMFB_LN_BWD=tile).  A row is spread over WPR warps (each lane
 // owns ONE 8-column slab for all rows it visits), so the three column-sum sets cost 24 registers per thread instead of
 // 24 x (H / 256), gamma is loop-invariant, and a group of WPR warps processes RB rows per step: 2 x RB 16-byte loads in
@@ -940,7 +1130,35 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
 #undef LN_TILE
     return launch_ok("layernorm_bwd(tile)");
   }
-  if (lean && nv_ <= 4) {
+  const bool stream = lean_env != nullptr && lean_env[0] == 's';
+  // bulk copies need 16-byte aligned rows (H % 8 == 0 is already required; leading dimensions in elements % 8 too)
+  if (stream && nv_ <= 4 && a.lddx % 8 == 0 && a.ldy % 8 == 0 && (a.dx2 == nullptr || a.lddx2 % 8 == 0)) {
+    int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
+    const int cap = num_sms() * 2;
+    if (grid > cap) grid = cap;
+#define LN_STREAM(NV, DX2_, ST_)                                                                                      \
+  {                                                                                                                    \
+    constexpr size_t smem_ = static_cast<size_t>(ROW_WARPS) * (ST_) * ((DX2_) ? 3 : 2) * (NV) * 512 +                  \
+                             ROW_WARPS * 256 * 4 + (NV) * 256 * 4 + 4096 + ROW_WARPS * (ST_) * 8;                      \
+    static bool attr_done = false;                                                                                     \
+    if (!attr_done) {                                                                                                  \
+      cudaFuncSetAttribute(ln_bwd_stream_kernel<NV, DX2_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
+      attr_done = true;                                                                                                \
+    }                                                                                                                  \
+    MMFB_LAUNCH((ln_bwd_stream_kernel<NV, DX2_, ST_>), grid, ROW_WARPS * 32, smem_, s, (const bf16*)a.dx, a.lddx,      \
+                (const bf16*)a.dx2, a.lddx2, (const bf16*)a.y, a.ldy, a.mean, a.rstd, (const bf16*)a.gamma,            \
+                (bf16*)a.dy, a.lddy, (bf16*)a.dz, a.lddz, a.drop_mask, a.ldmask, a.drop_scale, a.dgamma, a.dbeta,      \
+                a.dbias, a.M, a.H);                                                                                    \
+  }
+    if (a.dx2 != nullptr) {
+      if (nv_ <= 1) LN_STREAM(1, true, 3) else if (nv_ == 2) LN_STREAM(2, true, 3) else if (nv_ == 3) LN_STREAM(3, true, 2) else LN_STREAM(4, true, 2)
+    } else {
+      if (nv_ <= 1) LN_STREAM(1, false, 4) else if (nv_ == 2) LN_STREAM(2, false, 4) else if (nv_ == 3) LN_STREAM(3, false, 3) else LN_STREAM(4, false, 2)
+    }
+#undef LN_STREAM
+    return launch_ok("layernorm_bwd(stream)");
+  }
+  if ((lean || stream) && nv_ <= 4) {
     int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
     const int cap = num_sms() * 2;      // two resident blocks per SM, rows strided over them
     if (grid > cap) grid = cap;

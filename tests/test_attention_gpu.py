@@ -88,6 +88,16 @@ def test_attention_dropout_explicit_mask(S, d):
     assert max(errs.values()) < 1e-2
 
 
+@pytest.mark.parametrize("B,heads,Sq,Skv,p_drop", [(40, 12, 228, 228, 0.1), (70, 8, 100, 256, 0.0), (64, 6, 256, 36, 0.1),
+                                                   (13, 12, 128, 128, 0.0)])
+def test_attention_many_items_per_cta(B, heads, Sq, Skv, p_drop):
+    """d = 64, both sequences <= 256: the persistent kernels (one CTA per SM) walk several (batch, head) items each - ring
+    stages, statistics buffers, barrier phases and accumulator hand-over across items (1, 2 and 3+ items per CTA, one and
+    two 128-row blocks per side), with ragged key padding and one sample without any attendable key"""
+    errs = _case(B, heads, Sq, Skv, 64, p_drop=p_drop, seed=11, full_mask_row=True)
+    assert max(errs.values()) < 1e-2
+
+
 def test_attention_limits_raise():
     from mmf_b200 import functional as F
     q = torch.zeros(500, 64, device="cuda", dtype=torch.bfloat16)

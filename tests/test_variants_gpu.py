@@ -10,7 +10,9 @@ pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("variant,M,H", [("pair", 1000, 768), ("tile", 1000, 768), ("tile", 37848, 768), ("pair", 333, 1024),
-                                         ("tile", 50, 128), ("pair", 7, 512)])
+                                         ("tile", 50, 128), ("pair", 7, 512), ("stream", 1000, 768), ("stream", 37848, 768),
+                                         ("stream", 333, 1024), ("stream", 50, 128), ("stream", 7, 512), ("stream", 5000, 256),
+                                         ("lean", 1000, 768)])
 def test_layernorm_backward_variants_match_the_default(variant, M, H):
     from mmf_b200 import functional as F
     torch.manual_seed(0)
@@ -45,10 +47,13 @@ def test_layernorm_backward_variants_match_the_default(variant, M, H):
         os.environ.pop("MMFB_LN_BWD", None)
 
 
+@pytest.mark.parametrize("variant", ["8", "16"])
 @pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (256, 130, False), (100, 256, True), (36, 36, True), (128, 128, False)])
-def test_8_warp_fused_attention_backward_matches_the_default(Sq, Skv, drop):
-    """MMFB_ATTN_BWD=8 (two threads per query row, serial issue order) against the default 16-warp kernel (four threads per
-    row, overlapped issue order, tiles on four barriers): same MMAs in the same accumulation order, same arithmetic"""
+def test_one_cta_per_item_attention_backward_matches_the_default(Sq, Skv, drop, variant):
+    """MMFB_ATTN_BWD=8 (two threads per query row, serial issue order) and =16 (four threads per row, overlapped issue order,
+    one CTA per (batch, head)) against the default persistent kernel: same MMAs in the same accumulation order, same
+    arithmetic.  B * heads = 12 items are fewer than the SMs; the many-items-per-CTA case is the 37848-token encoder test
+    and tests/test_attention_gpu.py::test_attention_many_items_per_cta."""
     from mmf_b200 import functional as F
     torch.manual_seed(Sq * 5 + Skv)
     B, heads, d = 4, 3, 64
@@ -66,7 +71,7 @@ def test_8_warp_fused_attention_backward_matches_the_default(Sq, Skv, drop):
 
     def run(flag):
         if flag:
-            os.environ["MMFB_ATTN_BWD"] = "8"
+            os.environ["MMFB_ATTN_BWD"] = variant
         else:
             os.environ.pop("MMFB_ATTN_BWD", None)
         out = F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask, bits, scale, ctx32=c32)

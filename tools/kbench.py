@@ -110,7 +110,7 @@ def main():
                    f_fwd, b_fwd, env)
         ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, S, S, mask, bits, 1 / 0.9, save_fp32=True)
         dq = torch.empty_like(qkv)
-        for tag, env in (("default fused, 16 warps", {}), ("MMFB_ATTN_BWD=8", {"MMFB_ATTN_BWD": "8"})):
+        for tag, env in (("default persistent", {}), ("MMFB_ATTN_BWD=16", {"MMFB_ATTN_BWD": "16"}), ("MMFB_ATTN_BWD=8", {"MMFB_ATTN_BWD": "8"})):
             timeit("attention_bwd (+delta) [%s]" % tag,
                    lambda: F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, S, S, mask, bits, 1 / 0.9, dq=dq[:, :H],
                                            dk=dq[:, H:2 * H], dv=dq[:, 2 * H:], ctx32=c32), f_bwd, b_bwd, env)
@@ -125,7 +125,8 @@ def main():
         bits = F.dropout_bits((M,), H, 0.1, 1, 0, dev)
         dg, db_, dbias = (torch.zeros(H, device=dev) for _ in range(3))
         nb = M * (8.0 * H + H / 8.0 + 8.0)
-        for tag, env in (("default single pass", {}), ("MMFB_LN_BWD=pair", {"MMFB_LN_BWD": "pair"}), ("MMFB_LN_BWD=tile", {"MMFB_LN_BWD": "tile"})):
+        for tag, env in (("default single pass", {}), ("MMFB_LN_BWD=pair", {"MMFB_LN_BWD": "pair"}), ("MMFB_LN_BWD=tile", {"MMFB_LN_BWD": "tile"}),
+                         ("MMFB_LN_BWD=stream", {"MMFB_LN_BWD": "stream"}), ("MMFB_LN_BWD=lean", {"MMFB_LN_BWD": "lean"})):
             timeit("layernorm_bwd +dropout +dgamma/dbeta/dbias [%s]" % tag,
                    lambda: F.layernorm_bwd(dx, y, mean, rstd, g, dg, db_, dbias=dbias, drop_mask=bits, drop_scale=1 / 0.9), None, nb, env)
         timeit("layernorm_fwd", lambda: F.layernorm_fwd(y, g, torch.zeros_like(g)), None, M * (4.0 * H + 8))
