@@ -84,7 +84,8 @@ typedef struct {
   void* ctx; int64_t ldo;            /* bf16 [B*Sq, ldo]: output of fwd, input of bwd */
   float* lse2;
   const uint32_t* drop_mask; float drop_scale;
-  float* ctx32;                      /* optional fp32 copy of ctx, contiguous [B*Sq, heads*head_dim]: written by fwd, read by bwd */
+  void* ctx_lo;                      /* optional bf16 [B*Sq, heads*head_dim], contiguous: bf16(O - float(ctx)), the part of the
+                                        fp32 output the bf16 ctx drops; written by fwd, read by bwd (delta = rowsum(dO*(ctx+ctx_lo))) */
   /* backward only */
   const void* dctx; int64_t ld_dctx; /* bf16 [B*Sq, ld_dctx] */
   float* delta;                      /* fp32 scratch [B, heads, Sq] */

@@ -38,8 +38,9 @@ struct AttnFwdDev {
   const float* mask;      // [B, Skv] additive, or null
   bf16* ctx;              // [B*Sq, ldo]
   int64_t ldo;
-  float* ctx32;           // optional fp32 copy of ctx [B*Sq, H*D] (training): the backward's delta = rowsum(dO*O)
-                          // is taken from it, so bf16 rounding of O does not bias every dS of a row the same way
+  bf16* ctx_lo;           // optional [B*Sq, H*D] (training): bf16(O - float(ctx)), the part of O the bf16 output drops.
+                          // The backward's delta = rowsum(dO * (ctx + ctx_lo)): with the bf16 O alone every dS of a row
+                          // inherits the same rounding error (round 1: 4.5e-2 on q/k weight gradients of a 10-token case)
   float* lse2;            // [B, H, Sq]  log2-domain log-sum-exp of the scaled+masked scores
   const uint32_t* dmask;  // keep bits [B, H, Sq, W] (bit kv%32 of word kv/32) or null
   int W;
@@ -307,12 +308,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           o.w = pack_bf16x2(__uint_as_float(r[qd * 8 + 6]) * inv, __uint_as_float(r[qd * 8 + 7]) * inv);
           dst[qd] = o;
         }
-        if (p.ctx32 != nullptr) {
-          float4* d32 = reinterpret_cast<float4*>(p.ctx32 + (static_cast<int64_t>(b) * p.Sq + q) * (p.H * D) + h * D + c * 32);
+        if (p.ctx_lo != nullptr) {
+          uint4* dlo = reinterpret_cast<uint4*>(p.ctx_lo + (static_cast<int64_t>(b) * p.Sq + q) * (p.H * D) + h * D + c * 32);
 #pragma unroll
-          for (int qd = 0; qd < 8; ++qd)
-            d32[qd] = make_float4(__uint_as_float(r[qd * 4 + 0]) * inv, __uint_as_float(r[qd * 4 + 1]) * inv,
-                                  __uint_as_float(r[qd * 4 + 2]) * inv, __uint_as_float(r[qd * 4 + 3]) * inv);
+          for (int qd = 0; qd < 4; ++qd) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float o0 = __uint_as_float(r[qd * 8 + 2 * e]) * inv, o1 = __uint_as_float(r[qd * 8 + 2 * e + 1]) * inv;
+              const float2 hi = unpack_bf16x2(pack_bf16x2(o0, o1));
+              w[e] = pack_bf16x2(o0 - hi.x, o1 - hi.y);
+            }
+            dlo[qd] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
     }
@@ -339,10 +347,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   * P never touches shared memory: it is written over the score columns that have already been consumed
 //     (tcgen05.st, bf16 pairs in K order) and O = P V reads its A operand from tensor memory;
 //     region map per tile:  S [0,256)  ->  P(keys 0..127) [0,64) | O [64,128) | P(keys 128..255) [128,192).
-// 576 threads: warps 0..7 = softmax group of tile 0, warps 8..15 = tile 1, warp 16 = MMA issue, warp 17 = TMA + mask rows.
+// 608 threads: warps 0..7 = softmax group of tile 0, warps 8..15 = tile 1, warp 16 = MMA issue, warp 17 = TMA loads + mask
+// rows + item counter, warp 18 = bulk tensor stores of the output tiles.
 // Barriers (phase = pair parity unless noted): qk_full / v_full / mask_full / stage_free per ring stage, and per tile
 // s_ready (S committed), p_ready (256 arrivals: P complete), o_ready (O committed), o_read (256 arrivals: O copied out).
 // ----------------------------------------------------------------------------------------------
+// Timeline tracing for kernel development (-DMMFB_TRACE=1 builds only, python tools/ab.py build trace -DMMFB_TRACE=1):
+// CTA 0 stamps clock64() at fixed points of its first 64 items; tools/trace_attn.py prints the phase durations.
+#ifdef MMFB_TRACE
+__device__ long long mmfb_trace_buf[4 * 64 * 16];
+#define MMFB_TR(role, n, slot)                                                                                        \
+  do {                                                                                                                \
+    if (blockIdx.x == 0 && (n) < 64) mmfb_trace_buf[((role) * 64 + (n)) * 16 + (slot)] = clock64();                   \
+  } while (0)
+#else
+#define MMFB_TR(role, n, slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ void fwd_chunk_max(const uint32_t (&r)[32], const float4* m4, float scale2, float& mx) {
 #if MMFB_F32X2
   const uint64_t sc2 = pk2(scale2, scale2);
@@ -401,11 +422,18 @@ __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const flo
 #endif
 }
 
-constexpr int FWD_PAIR_THREADS = 576;       // 16 softmax warps + 1 MMA-issue warp + 1 loader warp
+constexpr int FWD_PAIR_THREADS = 608;       // 16 softmax warps + MMA-issue warp + loader warp + store warp
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 18 warps put 5 on one scheduler partition (16 K registers each): at most 96 registers per thread can launch
 __global__ void __launch_bounds__(FWD_PAIR_THREADS, 1)
 attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, AttnFwdDev p, int n_pairs) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                     const __grid_constant__ CUtensorMap tmOlo, AttnFwdDev p, int n_pairs, int* sched) {
   griddep_launch();
   griddep_wait();
   constexpr int D = 64;
@@ -424,19 +452,21 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* qk_full = bars;          // [2]
   uint64_t* v_full = bars + 2;       // [2]
   uint64_t* mask_full = bars + 4;    // [2]
-  uint64_t* stage_free = bars + 6;   // [2]  one commit per tile
+  uint64_t* stage_free = bars + 6;   // [2]  per tile: one commit of the MMA thread + one arrival of the store warp
   uint64_t* s_ready = bars + 8;      // [2 tiles]
   uint64_t* p_ready = bars + 10;     // [2 tiles]
   uint64_t* o_ready = bars + 12;     // [2 tiles]
   uint64_t* o_read = bars + 14;      // [2 tiles]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* o_staged = bars + 16;    // [2 tiles] 256 arrivals: the output tile is in shared memory
+  uint64_t* k_free = bars + 18;      // [2 stages] both tiles' score MMAs of the stage have completed: the K slots are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   uint32_t* sAct = tmem_slot + 1;    // [2 stages] bit c: 32-key chunk c has at least one key that is not masked out
+  int* sItem = reinterpret_cast<int*>(sAct + 2);   // [2 stages] (batch, head) item of the stage, -1 = no more work
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.Sq + 127) / 128;                 // query tiles per pair (1 or 2)
   const int nkt = (p.Skv + 127) / 128;               // key tiles (1 or 2)
   const int SKP = nkt * 128;                         // padded key count: N of the score MMA
-  const int N = (n_pairs - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 17) {
     if (lane == 0) {
@@ -447,7 +477,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_init(&qk_full[s], 1);
         mbar_init(&v_full[s], 1);
         mbar_init(&mask_full[s], 32);
-        mbar_init(&stage_free[s], nt);
+        mbar_init(&stage_free[s], 2 * nt);
+        mbar_init(&o_staged[s], 256);
+        mbar_init(&k_free[s], nt);
         mbar_init(&s_ready[s], 1);
         mbar_init(&p_ready[s], 256);
         mbar_init(&o_ready[s], 1);
@@ -466,8 +498,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 17) {
     // ------------------------------------ loader: TMA tiles + mask rows, two pairs ahead ------------------------------------
-    auto load_pair = [&](int n) {          // lane 0: Q tiles + K into qk_full, V into v_full of ring stage n & 1
-      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+    // Items are handed out by an atomic counter (sched[0]), not by a fixed stride: their cost varies with the padding of the
+    // sample (masked chunks are skipped), and with 13.5 items per CTA a static split leaves the slowest CTA ~10 % behind.
+    // The item of ring stage s travels with its mask row: sItem[s], sAct[s], sMask[s] are published by mask_full[s].
+    auto load_pair = [&](int n, int it) {  // lane 0: Q tiles + K into qk_full, V into v_full of ring stage n & 1
       const int h = it % p.H, b = it / p.H;
       const int s = n & 1;
       uint8_t* st = smem + s * STAGE;
@@ -477,44 +511,48 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_expect_tx(&v_full[s], nkt * TILE);
       for (int j = 0; j < nkt; ++j) tma_load_3d(st + (4 + j) * TILE, &tmV, &v_full[s], h * D, j * 128, b);
     };
-    auto load_mask = [&](int n) {          // whole warp: log2-domain additive mask, -inf on the padded key columns
-      const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-      const int b = it / p.H;
+    auto load_mask = [&](int n, int it) {  // whole warp: log2-domain additive mask, -inf on the padded key columns
       float* dst = sMask + (n & 1) * 256;
       // Chunks whose 32 keys are ALL masked out (additive -10000, or beyond Skv) contribute exp2(-14427 + ...) = 0 exactly:
       // they are skipped in both softmax passes and in the P V contraction (identical results; a quarter of the chunks at
       // the padding rates of the reference's text / region batches).  A sample without any attendable key keeps them all:
       // its softmax is uniform over the masked keys (hf_layers.py:191-196 semantics).
-      float mv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = lane + 32 * j;
-        mv[j] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
-      }
       uint32_t act = 0;
+      if (it >= 0) {
+        const int b = it / p.H;
+        float mv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dst[lane + 32 * j] = mv[j];
-        if (__any_sync(0xffffffffu, mv[j] > -5000.0f)) act |= 1u << j;
+        for (int j = 0; j < 8; ++j) {
+          const int i = lane + 32 * j;
+          mv[j] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dst[lane + 32 * j] = mv[j];
+          if (__any_sync(0xffffffffu, mv[j] > -5000.0f)) act |= 1u << j;
+        }
+        if (act == 0) act = (1u << ((p.Skv + 31) / 32)) - 1u;
       }
-      if (act == 0) act = (1u << ((p.Skv + 31) / 32)) - 1u;
-      if (lane == 0) sAct[n & 1] = act;
+      if (lane == 0) { sAct[n & 1] = act; sItem[n & 1] = it; }
       __syncwarp();
       mbar_arrive(&mask_full[n & 1]);
     };
-    for (int n = 0; n < 2 && n < N; ++n) {
-      if (lane == 0) load_pair(n);
-      load_mask(n);
-    }
-    for (int n = 0; n + 2 < N; ++n) {
-      // ring stage n & 1 (tiles, mask row, chunk bits) is refilled once every MMA of pair n has completed
-      mbar_wait(&stage_free[n & 1], (n >> 1) & 1);
-      if (lane == 0) load_pair(n + 2);
-      load_mask(n + 2);
+    for (int n = 0;; ++n) {
+      // ring stage n & 1 (tiles, mask row, item) is refilled once every MMA of the item that used it has completed
+      if (n >= 2) mbar_wait(&stage_free[n & 1], ((n - 2) >> 1) & 1);
+      int it = 0;
+      if (lane == 0) it = atomicAdd(sched, 1);
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (it >= n_pairs) it = -1;
+      if (lane == 0) MMFB_TR(3, n, 0);
+      if (lane == 0 && it >= 0) load_pair(n, it);
+      load_mask(n, it);
+      if (lane == 0) MMFB_TR(3, n, 1);
+      if (it < 0) break;
     }
   } else if (warp == 16) {
     // ------------------------------------ MMA issue: one thread, both tiles, never blocked on one of them ------------------------------------
-    if (lane == 0 && N > 0) {
+    if (lane == 0) {
       auto issue_s = [&](int n, int t) {   // S_t = Q_t K^T over all (padded) keys
         const uint32_t st = smem_u32(smem + (n & 1) * STAGE);
         const uint32_t aQ = st + t * TILE, aK = st + 2 * TILE;
@@ -524,6 +562,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_bf16(tmem_base + t * REG, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024), idesc,
                     kk > 0 ? 1u : 0u);
         umma_commit(&s_ready[t]);
+        umma_commit(&k_free[n & 1]);
       };
       auto issue_o = [&](int n, int t) {   // O_t = P V, A = P from tensor memory (8 columns per 16 keys)
         const uint32_t aV = smem_u32(smem + (n & 1) * STAGE + 4 * TILE);
@@ -541,16 +580,22 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         umma_commit(&o_ready[t]);
       };
-      mbar_wait(&qk_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < nt; ++t) issue_s(0, t);
-      // Per tile: [wait P_t(n)] -> O_t(n) -> [wait O_t(n) copied out] -> S_t(n+1) -> ...  The two chains are independent;
-      // the barriers are PROBED (mbarrier.test_wait) in turn, so whichever softmax group gets there first is served first
-      // and the groups settle half a period apart: the tensor core work of one hides behind the arithmetic of the other.
-      int pn[2] = {0, 0};                  // pair index the tile is in
-      int ph[2] = {0, 0};                  // 0: O_t(pn) is next, 1: S_t(pn + 1) is next
+      // Per tile: [wait P_t(n)] -> O_t(n) -> [wait O_t(n) copied out, item n+1 published] -> S_t(n+1) -> ...  The two chains
+      // are independent; the barriers are PROBED (mbarrier.test_wait) in turn, so whichever softmax group gets there first is
+      // served first and the groups settle half a period apart: the tensor core work of one hides behind the arithmetic of
+      // the other.  An idle probe round sleeps ~50 ns: a spinning warp would take issue slots from the softmax warps of
+      // its scheduler partition.
+      int pn[2] = {0, 0};                  // item index (per CTA) the tile is in
+      int ph[2] = {0, 0};                  // 0: O_t(pn) is next, 1: S_t(pn + 1) is next, 2: done
       int live = nt;
       if (nt < 2) ph[1] = 2;
+      mbar_wait(&mask_full[0], 0);
+      if (sItem[0] < 0) live = 0;
+      else {
+        mbar_wait(&qk_full[0], 0);
+        tc_fence_after();
+        for (int t = 0; t < nt; ++t) issue_s(0, t);
+      }
       uint32_t spins = 0;
       long long t0 = 0;
       while (live > 0) {
@@ -561,29 +606,63 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (ph[t] == 0) {
             if (mbar_test(&p_ready[t], n & 1) && mbar_test(&v_full[n & 1], (n >> 1) & 1)) {
               tc_fence_after();
+              MMFB_TR(2, n, 2 * t);
               issue_o(n, t);
               umma_commit(&stage_free[n & 1]);                 // every MMA of this tile that reads the ring stage has been issued
-              if (n + 1 < N) ph[t] = 1; else { ph[t] = 2; --live; }
+              ph[t] = 1;
               progressed = true;
             }
           } else if (ph[t] == 1) {
-            if (mbar_test(&o_read[t], n & 1) && mbar_test(&qk_full[(n + 1) & 1], ((n + 1) >> 1) & 1)) {
-              tc_fence_after();
-              issue_s(n + 1, t);
-              pn[t] = n + 1;
-              ph[t] = 0;
-              progressed = true;
+            if (mbar_test(&o_read[t], n & 1) && mbar_test(&mask_full[(n + 1) & 1], ((n + 1) >> 1) & 1)) {
+              if (sItem[(n + 1) & 1] < 0) {                    // no further item
+                ph[t] = 2;
+                --live;
+                progressed = true;
+              } else if (mbar_test(&qk_full[(n + 1) & 1], ((n + 1) >> 1) & 1)) {
+                tc_fence_after();
+                MMFB_TR(2, n, 2 * t + 1);
+                issue_s(n + 1, t);
+                pn[t] = n + 1;
+                ph[t] = 0;
+                progressed = true;
+              }
             }
           }
         }
         if (progressed) { spins = 0; t0 = 0; }
-        else if (((++spins) & 0xFFFFu) == 0) {                 // watchdog: a protocol bug traps instead of hanging the GPU
-          const long long now = clock64();
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 8000000000LL) { printf("mmfb: attention forward issue loop timeout (block %d)\n", (int)blockIdx.x); __trap(); }
+        else {
+          __nanosleep(40);
+          if (((++spins) & 0xFFFFu) == 0) {                    // watchdog: a protocol bug traps instead of hanging the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) { printf("mmfb: attention forward issue loop timeout (block %d)\n", (int)blockIdx.x); __trap(); }
+          }
         }
       }
     }
+  } else if (warp == 18) {
+    // ------------------------------------ store warp: one bulk tensor store per output tile ------------------------------------
+    // rows beyond Sq are clipped by the tensor map ([B][Sq][heads * d]); the ring stage is released to the loader only after
+    // the stores have finished READING shared memory
+    for (int n = 0;; ++n) {
+      mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
+      const int it = sItem[n & 1];
+      if (it < 0) break;
+      const int h = it % p.H, b = it / p.H;
+      uint8_t* stage_base = smem + (n & 1) * STAGE;
+      for (int t = 0; t < nt; ++t) {
+        mbar_wait(&o_staged[t], n & 1);
+        if (lane == 0) {
+          tma_store_3d(&tmO, stage_base + t * TILE, h * D, t * 128, b);
+          if (p.ctx_lo != nullptr) tma_store_3d(&tmOlo, stage_base + (2 + t) * TILE, h * D, t * 128, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&stage_free[n & 1]);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes complete before the CTA exits
   } else {
     // ------------------------------------ softmax groups ------------------------------------
     const int t = warp >> 3;                                  // tile / group
@@ -598,8 +677,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float* gSum = sSum + t * 256;
       const int bar_id = 1 + t;
       const uint32_t pcol = half == 0 ? COL_PLO : COL_PHI;
-      for (int n = 0; n < N; ++n) {
-        const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+      for (int n = 0;; ++n) {
+        const bool tr = (threadIdx.x & 255) == 0;
+        if (tr) MMFB_TR(t, n, 0);
+        mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
+        if (tr) MMFB_TR(t, n, 1);
+        const int it = sItem[n & 1];
+        if (it < 0) break;
         const int h = it % p.H, b = it / p.H;
         const int q = t * 128 + row;
         const bool valid = q < p.Sq;
@@ -612,11 +696,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int k = 0; k < 4; ++k)
             if (c0 + k < nch) bits[k] = __ldg(dm + c0 + k);
         }
-        mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
         const uint32_t act = have ? (sAct[n & 1] >> c0) & 0xFu : 0u;   // bit k: chunk k of this thread has an attendable key
         const bool on0 = act & 1u, on1 = act & 2u, on2 = act & 4u, on3 = act & 8u;
         mbar_wait(&s_ready[t], n & 1);
         tc_fence_after();
+        if (tr) MMFB_TR(t, n, 2);
         // ---- pass 1: row maximum; the load of the next chunk is in flight while this one is reduced ----
         uint32_t ra[32], rb[32];
         float mx = -INFINITY;
@@ -633,7 +717,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
         if (on3) fwd_chunk_max(rb, m4 + 24, p.scale2, mx);
         gMax[half * 128 + row] = mx;
+        if (tr) MMFB_TR(t, n, 3);
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        if (tr) MMFB_TR(t, n, 4);
         mx = fmaxf(gMax[row], gMax[128 + row]);
         // ---- pass 2, last chunk first (chunks 3 and 2 are still in rb / ra): probabilities -> tensor memory ----
         float sum = 0.0f;
@@ -659,40 +745,51 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_st16(treg + pcol + 0, pk);
         }
         gSum[half * 128 + row] = sum;
+        if (tr) MMFB_TR(t, n, 5);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[t]);
+        if (tr) MMFB_TR(t, n, 6);
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        if (tr) MMFB_TR(t, n, 7);
         sum = gSum[row] + gSum[128 + row];
         // ---- O_t: 32 of the 64 columns per thread ----
         mbar_wait(&o_ready[t], n & 1);
         tc_fence_after();
+        if (tr) MMFB_TR(t, n, 8);
         tmem_ld32(treg + COL_O + half * 32, ra);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&o_read[t]);
-        if (valid) {
+        if (tr) MMFB_TR(t, n, 9);
+        // ---- the tile goes out through shared memory and ONE bulk tensor store per tile: 16-byte stores of a warp to 32
+        //      different rows cost 32 LSU passes each (round-2 trace: 47 % of an item's time in these stores) ----
+        {
           const float inv = p.dscale / sum;
-          if (half == 0) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = mx + log2f(sum);
-          const int64_t tok = static_cast<int64_t>(b) * p.Sq + q;
-          uint4* dst = reinterpret_cast<uint4*>(p.ctx + tok * p.ldo + h * D + half * 32);
+          if (valid && half == 0) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = mx + log2f(sum);
+          uint8_t* stage_base = smem + (n & 1) * STAGE;
+          uint8_t* orow = stage_base + t * TILE + row * 128;            // the Q_t slot: free since S_t completed
+          uint8_t* lrow = stage_base + (2 + t) * TILE + row * 128;      // the K_t slot: free once BOTH tiles' S completed
+          const bool want_lo = p.ctx_lo != nullptr;
+          if (want_lo) mbar_wait(&k_free[n & 1], (n >> 1) & 1);
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(ra[qd * 8 + 0]) * inv, __uint_as_float(ra[qd * 8 + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(ra[qd * 8 + 2]) * inv, __uint_as_float(ra[qd * 8 + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(ra[qd * 8 + 4]) * inv, __uint_as_float(ra[qd * 8 + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(ra[qd * 8 + 6]) * inv, __uint_as_float(ra[qd * 8 + 7]) * inv);
-            dst[qd] = o;
-          }
-          if (p.ctx32 != nullptr) {
-            float4* d32 = reinterpret_cast<float4*>(p.ctx32 + tok * (p.H * D) + h * D + half * 32);
+            uint32_t wh[4], wl[4];
 #pragma unroll
-            for (int qd = 0; qd < 8; ++qd)
-              d32[qd] = make_float4(__uint_as_float(ra[qd * 4 + 0]) * inv, __uint_as_float(ra[qd * 4 + 1]) * inv,
-                                    __uint_as_float(ra[qd * 4 + 2]) * inv, __uint_as_float(ra[qd * 4 + 3]) * inv);
+            for (int e = 0; e < 4; ++e) {
+              const float o0 = __uint_as_float(ra[qd * 8 + 2 * e]) * inv, o1 = __uint_as_float(ra[qd * 8 + 2 * e + 1]) * inv;
+              wh[e] = pack_bf16x2(o0, o1);
+              const float2 hi = unpack_bf16x2(wh[e]);
+              wl[e] = pack_bf16x2(o0 - hi.x, o1 - hi.y);
+            }
+            const int chunk = ((half * 4 + qd) ^ (row & 7)) * 16;
+            *reinterpret_cast<uint4*>(orow + chunk) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            if (want_lo) *reinterpret_cast<uint4*>(lrow + chunk) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
           }
+          fence_proxy_async();
+          mbar_arrive(&o_staged[t]);
         }
+        if (tr) MMFB_TR(t, n, 10);
       }
     }
   }
@@ -701,6 +798,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  // the last CTA to finish re-arms the item counter for the next launch (launches of one stream are serialised)
+  if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+    atomicExch(sched, 0);
+    atomicExch(sched + 1, 0);
   }
 }
 
@@ -1634,7 +1736,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(BWD_PERS_THREADS, 1)
 attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                     AttnBwdFusedDev p, int n_items) {
+                     AttnBwdFusedDev p, int n_items, int* sched) {
   griddep_launch();
   griddep_wait();
   constexpr int D = 64;
@@ -1660,17 +1762,12 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* dq_read = bars + 14;      // 512 arrivals, phase = item parity
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   uint32_t* sAct = tmem_slot + 1;     // [2 buffers] bit c: 32-key chunk c has an attendable key
+  int* sItem = reinterpret_cast<int*>(sAct + 2);    // [2 buffers] (batch, head) item, -1 = no more work; published by stat_full
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ni = (p.Sq + 127) / 128, nj = (p.Skv + 127) / 128;
   const int np = ni * nj;
-  const int N = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  auto item_hb = [&](int n, int& h, int& b) {
-    const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-    h = it % p.H;
-    b = it / p.H;
-  };
 
   if (warp == 17) {
     if (lane == 0) {
@@ -1695,79 +1792,89 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 17) {
     // ------------------------------------ loader ------------------------------------
-    auto load_kv = [&](int n, int j) {     // lane 0
-      int h, b;
-      item_hb(n, h, b);
+    // Items come from an atomic counter (sched[0]), not a fixed stride: their cost varies with the padding of the sample
+    // (masked chunks are skipped) and a static split leaves the slowest of 148 CTAs ~10 % behind the mean.
+    auto fetch = [&]() -> int {
+      int it = 0;
+      if (lane == 0) it = atomicAdd(sched, 1);
+      it = __shfl_sync(0xffffffffu, it, 0);
+      return it < n_items ? it : -1;
+    };
+    auto load_kv = [&](int it, int j) {    // lane 0
+      const int h = it % p.H, b = it / p.H;
       mbar_expect_tx(&kv_full[j], 2 * TILE);
       tma_load_3d(sK + j * TILE, &tmK, &kv_full[j], h * D, j * 128, b);
       tma_load_3d(sV + j * TILE, &tmV, &kv_full[j], h * D, j * 128, b);
     };
-    auto load_q = [&](int n, int i) {      // lane 0
-      int h, b;
-      item_hb(n, h, b);
+    auto load_q = [&](int it, int i) {     // lane 0
+      const int h = it % p.H, b = it / p.H;
       mbar_expect_tx(&q_full[i], 2 * TILE);
       tma_load_3d(sQ + i * TILE, &tmQ, &q_full[i], h * D, i * 128, b);
       tma_load_3d(sdO + i * TILE, &tmdO, &q_full[i], h * D, i * 128, b);
     };
-    auto load_stats = [&](int n) {         // whole warp: lse2, delta, log2-domain mask row, active-chunk bits
-      int h, b;
-      item_hb(n, h, b);
-      const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+    auto load_stats = [&](int n, int it) { // whole warp: lse2, delta, log2-domain mask row, active-chunk bits, the item itself
       float* st = sStat + (n & 1) * 768;
-      float lv[8], dv[8], mv[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const int i = lane + 32 * x;
-        const bool qv = i < p.Sq, kv = i < p.Skv;
-        lv[x] = qv ? p.lse2[bh * p.Sq + i] : INFINITY;
-        dv[x] = qv ? p.delta[bh * p.Sq + i] : 0.0f;
-        mv[x] = kv ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
-      }
-      // 32-key chunks whose keys are ALL masked out (additive -10000 or beyond Skv) have P = 0 and dS = 0 exactly: their
-      // arithmetic is skipped (zeros are stored).  A sample without any attendable key keeps every chunk.
       uint32_t act = 0;
+      if (it >= 0) {
+        const int h = it % p.H, b = it / p.H;
+        const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+        float lv[8], dv[8], mv[8];
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const int i = lane + 32 * x;
-        st[i] = lv[x];
-        st[256 + i] = dv[x];
-        st[512 + i] = mv[x];
-        if (__any_sync(0xffffffffu, mv[x] > -5000.0f)) act |= 1u << x;
+        for (int x = 0; x < 8; ++x) {
+          const int i = lane + 32 * x;
+          const bool qv = i < p.Sq, kv = i < p.Skv;
+          lv[x] = qv ? p.lse2[bh * p.Sq + i] : INFINITY;
+          dv[x] = qv ? p.delta[bh * p.Sq + i] : 0.0f;
+          mv[x] = kv ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
+        }
+        // 32-key chunks whose keys are ALL masked out (additive -10000 or beyond Skv) have P = 0 and dS = 0 exactly: their
+        // arithmetic is skipped (zeros are stored).  A sample without any attendable key keeps every chunk.
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const int i = lane + 32 * x;
+          st[i] = lv[x];
+          st[256 + i] = dv[x];
+          st[512 + i] = mv[x];
+          if (__any_sync(0xffffffffu, mv[x] > -5000.0f)) act |= 1u << x;
+        }
+        if (act == 0) act = 0xFFu;
       }
-      if (act == 0) act = 0xFFu;
-      if (lane == 0) sAct[n & 1] = act;
+      if (lane == 0) { sAct[n & 1] = act; sItem[n & 1] = it; }
       __syncwarp();
       mbar_arrive(&stat_full[n & 1]);
     };
-    if (N > 0) {
-      if (lane == 0) {
-        load_kv(0, 0);
-        for (int i = 0; i < ni; ++i) load_q(0, i);
-        for (int j = 1; j < nj; ++j) load_kv(0, j);
-      }
-      load_stats(0);
+    int it_cur = fetch();
+    if (lane == 0 && it_cur >= 0) {
+      load_kv(it_cur, 0);
+      for (int i = 0; i < ni; ++i) load_q(it_cur, i);
+      for (int j = 1; j < nj; ++j) load_kv(it_cur, j);
     }
-    for (int n = 0; n + 1 < N; ++n) {
+    load_stats(0, it_cur);
+    for (int n = 0; it_cur >= 0; ++n) {
       // statistics of item n+1 go to the buffer item n-1 used: every compute thread has left item n-1 (dq_read)
       if (n >= 1) mbar_wait(dq_read, (n - 1) & 1);
-      load_stats(n + 1);
-      // operand slots in the order in which item n releases them (pair index of the last reader, j outer / i inner)
-      for (int pidx = 0; pidx < np; ++pidx) {
-        for (int j = 0; j < nj; ++j)
-          if (pidx == j * ni + ni - 1) {
-            mbar_wait(&tile_free[j == 0 ? 0 : 3], n & 1);
-            if (lane == 0) load_kv(n + 1, j);
-          }
-        for (int i = 0; i < ni; ++i)
-          if (pidx == (nj - 1) * ni + i) {
-            mbar_wait(&tile_free[1 + i], n & 1);
-            if (lane == 0) load_q(n + 1, i);
-          }
+      const int it_next = fetch();
+      load_stats(n + 1, it_next);
+      if (it_next >= 0) {
+        // operand slots in the order in which item n releases them (pair index of the last reader, j outer / i inner)
+        for (int pidx = 0; pidx < np; ++pidx) {
+          for (int j = 0; j < nj; ++j)
+            if (pidx == j * ni + ni - 1) {
+              mbar_wait(&tile_free[j == 0 ? 0 : 3], n & 1);
+              if (lane == 0) load_kv(it_next, j);
+            }
+          for (int i = 0; i < ni; ++i)
+            if (pidx == (nj - 1) * ni + i) {
+              mbar_wait(&tile_free[1 + i], n & 1);
+              if (lane == 0) load_q(it_next, i);
+            }
+        }
       }
+      it_cur = it_next;
     }
   } else if (warp == 16) {
     // ------------------------------------ MMA issue ------------------------------------
-    if (lane == 0 && N > 0) {
+    if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
       const uint32_t idesc_q = umma_idesc_bf16(128, D, false, true);   // A K-major,  B MN-major
       const uint32_t idesc_t = umma_idesc_bf16(128, D, true, true);    // A MN-major, B MN-major
@@ -1789,14 +1896,17 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       };
       uint32_t g = 0;                    // pair counter over all items
       uint32_t kb = 0;                   // key-block counter over all items
-      issue_scores(0, 0, 0);
-      for (int n = 0; n < N; ++n) {
+      mbar_wait(&stat_full[0], 0);
+      bool more = sItem[0] >= 0;
+      if (more) issue_scores(0, 0, 0);
+      for (int n = 0; more; ++n) {
         for (int j = 0; j < nj; ++j, ++kb) {
           for (int i = 0; i < ni; ++i, ++g) {
             const int pidx = j * ni + i;
             const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
             const uint32_t aK = smem_u32(sK + j * TILE);
             mbar_wait(p_ready, g & 1);               // S/dP of this pair have been read, P'/dS' are in shared memory
+            MMFB_TR(1, n, 2 * pidx);
             const bool last_pair = pidx == np - 1;
             if (!last_pair) {
               const int i2 = (i + 1 < ni) ? i + 1 : 0, j2 = (i + 1 < ni) ? j : j + 1;
@@ -1820,11 +1930,16 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         umma_desc_sw128(adO + kk * 2048, TILE, 1024), idesc_t, (i > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(acc_done);
+            MMFB_TR(1, n, 2 * pidx + 1);
             // operand slots whose last reader this pair was
             if (i == ni - 1) umma_commit(&tile_free[j == 0 ? 0 : 3]);
             if (j == nj - 1) umma_commit(&tile_free[1 + i]);
             // first pair of the next item AFTER the accumulations: its tiles may still be in flight
-            if (last_pair && n + 1 < N) issue_scores(n + 1, 0, 0);
+            if (last_pair) {
+              mbar_wait(&stat_full[(n + 1) & 1], ((n + 1) >> 1) & 1);      // published while item n was running
+              more = sItem[(n + 1) & 1] >= 0;
+              if (more) issue_scores(n + 1, 0, 0);
+            }
           }
         }
       }
@@ -1835,14 +1950,17 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t g = 0, kb = 0;
-    for (int n = 0; n < N; ++n) {
-      int h, b;
-      item_hb(n, h, b);
+    for (int n = 0;; ++n) {
+      mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      const int it = sItem[n & 1];
+      if (it < 0) break;
+      const int h = it % p.H, b = it / p.H;
       const int64_t bh = static_cast<int64_t>(b) * p.H + h;
       const float* sLse = sStat + (n & 1) * 768;
       const float* sDel = sLse + 256;
       const float* sMsk = sLse + 512;
-      mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      const bool tr = threadIdx.x == 0;
+      if (tr) MMFB_TR(0, n, 14);
       const uint32_t act = sAct[n & 1];
       for (int j = 0; j < nj; ++j, ++kb) {
         for (int i = 0; i < ni; ++i, ++g) {
@@ -1857,6 +1975,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t wds[16], wp[16];                           // packed bf16 pairs of dS' and P' for this thread's 32 columns
           mbar_wait(s_ready, g & 1);
           tc_fence_after();
+          if (tr) MMFB_TR(0, n, 3 * (j * ni + i));
           const bool chunk_on = (act >> (j * 4 + c)) & 1u;
           if (!chunk_on) {
 #pragma unroll
@@ -1895,6 +2014,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
           }
           // the accumulations of the previous pair still read P'/dS' while the arithmetic above ran
+          if (tr) MMFB_TR(0, n, 3 * (j * ni + i) + 1);
           if (g > 0) mbar_wait(acc_done, (g - 1) & 1);
           uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
           uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
@@ -1907,6 +2027,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(p_ready);
+          if (tr) MMFB_TR(0, n, 3 * (j * ni + i) + 2);
         }
         // ---- dK_j, dV_j are complete: rows = keys of block j; this thread stores 16 of the 64 columns of each ----
         mbar_wait(acc_done, (g - 1) & 1);
@@ -1947,6 +2068,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_read);
+      if (tr) MMFB_TR(0, n, 12);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int q = i * 128 + row;
@@ -1971,12 +2093,17 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  // the last CTA to finish re-arms the item counter for the next launch
+  if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+    atomicExch(sched, 0);
+    atomicExch(sched + 1, 0);
+  }
 }
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d].  One warp per token row, 16-byte vector loads; a head of D
 // elements is owned by D/8 consecutive lanes and reduced with shuffles (coalesced 512 B / 1 KB per warp access).
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, const bf16* __restrict__ O,
-                                  int64_t ld_o, const float* __restrict__ O32, float* __restrict__ delta, int B, int H,
+                                  int64_t ld_o, const bf16* __restrict__ Olo, float* __restrict__ delta, int B, int H,
                                   int Sq, int D) {
   griddep_launch();
   griddep_wait();
@@ -1999,17 +2126,23 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t ld_do, co
       t = unpack_bf16x2(u.z); x[4] = t.x; x[5] = t.y;
       t = unpack_bf16x2(u.w); x[6] = t.x; x[7] = t.y;
     }
-    if (act && O32 != nullptr) {
-      const float4 a = *reinterpret_cast<const float4*>(O32 + tok * static_cast<int64_t>(W) + col);
-      const float4 c4 = *reinterpret_cast<const float4*>(O32 + tok * static_cast<int64_t>(W) + col + 4);
-      s = x[0] * a.x + x[1] * a.y + x[2] * a.z + x[3] * a.w + x[4] * c4.x + x[5] * c4.y + x[6] * c4.z + x[7] * c4.w;
-    } else if (act) {
+    if (act) {
       const uint4 u = *reinterpret_cast<const uint4*>(O + tok * ld_o + col);
       float2 t;
-      t = unpack_bf16x2(u.x); s += x[0] * t.x + x[1] * t.y;
-      t = unpack_bf16x2(u.y); s += x[2] * t.x + x[3] * t.y;
-      t = unpack_bf16x2(u.z); s += x[4] * t.x + x[5] * t.y;
-      t = unpack_bf16x2(u.w); s += x[6] * t.x + x[7] * t.y;
+      float o[8];
+      t = unpack_bf16x2(u.x); o[0] = t.x; o[1] = t.y;
+      t = unpack_bf16x2(u.y); o[2] = t.x; o[3] = t.y;
+      t = unpack_bf16x2(u.z); o[4] = t.x; o[5] = t.y;
+      t = unpack_bf16x2(u.w); o[6] = t.x; o[7] = t.y;
+      if (Olo != nullptr) {      // O = ctx + ctx_lo (the forward's fp32 value to ~2^-17)
+        const uint4 l = *reinterpret_cast<const uint4*>(Olo + tok * static_cast<int64_t>(W) + col);
+        t = unpack_bf16x2(l.x); o[0] += t.x; o[1] += t.y;
+        t = unpack_bf16x2(l.y); o[2] += t.x; o[3] += t.y;
+        t = unpack_bf16x2(l.z); o[4] += t.x; o[5] += t.y;
+        t = unpack_bf16x2(l.w); o[6] += t.x; o[7] += t.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += x[e] * o[e];
     }
     // reduce over the lanes of this head (lanes_per_head is a power of two dividing 32; W % 256 may leave idle lanes)
     for (int o = lanes_per_head >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -2029,6 +2162,18 @@ static int check_attn_common(const mmfb_attn_args& a, const char* who) {
     return set_error(MMFB_ERR_ARG, "%s: Skv=%d exceeds the single-pass limit %d for head_dim %d", who, a.Skv, max_kv,
                      a.head_dim);
   return MMFB_OK;
+}
+
+// Work counters of the persistent attention kernels ([0..1] forward: next item / finished CTAs, [4..5] backward): device
+// memory owned by the library, zero between launches (the last CTA of a launch re-arms them).  One set per process: the
+// kernels of ONE stream are serialised; concurrent attention launches on different streams are not supported.
+static int* sched_counters() {
+  static int* buf = nullptr;
+  if (buf == nullptr) {
+    if (cudaMalloc(&buf, 8 * sizeof(int)) != cudaSuccess) { buf = nullptr; return nullptr; }
+    if (cudaMemset(buf, 0, 8 * sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+  }
+  return buf;
 }
 
 template <int D>
@@ -2053,7 +2198,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
   p.mask = a.mask;
   p.ctx = reinterpret_cast<bf16*>(a.ctx); p.ldo = a.ldo;
   p.lse2 = a.lse2;
-  p.ctx32 = a.ctx32;
+  p.ctx_lo = reinterpret_cast<bf16*>(a.ctx_lo);
   p.dmask = a.drop_mask; p.W = (a.Skv + 31) / 32; p.dscale = a.drop_mask ? a.drop_scale : 1.0f;
   p.scale2 = LOG2E / sqrtf(static_cast<float>(D));
   if (D == 64 && a.Sq <= 256 && a.Skv <= 256) {
@@ -2070,7 +2215,13 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       }
       const int n_pairs = a.heads * a.B;
       const int grid_p = n_pairs < num_sms() ? n_pairs : num_sms();
-      MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, FWD_PAIR_THREADS, smem_p, stream, tmQ, tmK128, tmV128, p, n_pairs);
+      int* sched = sched_counters();
+      if (sched == nullptr) return set_error(MMFB_ERR_CUDA, "attn_fwd: scheduler counters");
+      CUtensorMap tmO, tmOlo;
+      if ((rc = make_tmap_3d(&tmO, a.ctx, W, a.Sq, a.B, a.ldo, a.ldo * a.Sq, 64, 128))) return rc;
+      tmOlo = tmO;
+      if (a.ctx_lo != nullptr && (rc = make_tmap_3d(&tmOlo, a.ctx_lo, W, a.Sq, a.B, W, static_cast<int64_t>(W) * a.Sq, 64, 128))) return rc;
+      MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, FWD_PAIR_THREADS, smem_p, stream, tmQ, tmK128, tmV128, tmO, tmOlo, p, n_pairs, sched);
       cudaError_t e2 = cudaGetLastError();
       if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd_pair launch: %s", cudaGetErrorString(e2));
       count_launch();
@@ -2123,7 +2274,7 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     const int threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
     MMFB_LAUNCH(attn_delta_kernel, static_cast<unsigned>(blocks), threads, 0, stream, 
-        reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, a.ctx32, a.delta,
+        reinterpret_cast<const bf16*>(a.dctx), a.ld_dctx, reinterpret_cast<const bf16*>(a.ctx), a.ldo, reinterpret_cast<const bf16*>(a.ctx_lo), a.delta,
         a.B, a.heads, a.Sq, D);
     count_launch();
   }
@@ -2168,8 +2319,10 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       }
       const int n_items = a.heads * a.B;
       const int grid_p = n_items < num_sms() ? n_items : num_sms();
-      if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_pers_kernel<true>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items);
-      else MMFB_LAUNCH(attn_bwd_pers_kernel<false>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items);
+      int* sched = sched_counters();
+      if (sched == nullptr) return set_error(MMFB_ERR_CUDA, "attn_bwd: scheduler counters");
+      if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_pers_kernel<true>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items, sched + 4);
+      else MMFB_LAUNCH(attn_bwd_pers_kernel<false>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items, sched + 4);
     } else if (w_env[0] != '8') {
       static bool w16_attr = false;
       if (!w16_attr) {
@@ -2234,3 +2387,16 @@ int attn_bwd(const mmfb_attn_args& a, cudaStream_t stream) {
 }
 
 }  // namespace mmfb
+
+#ifdef MMFB_TRACE
+// development builds only: copies the trace stamps of CTA 0 to the host (see MMFB_TR above, tools/trace_attn.py)
+extern "C" int mmfb_trace_read(long long* host, int n) {
+  if (n > 4 * 64 * 16) n = 4 * 64 * 16;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host, mmfb::mmfb_trace_buf, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+extern "C" int mmfb_trace_clear(void) {
+  static long long zeros[4 * 64 * 16];
+  return cudaMemcpyToSymbol(mmfb::mmfb_trace_buf, zeros, sizeof(zeros)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -102,26 +102,27 @@ def _attn_args(q, k, v, B, heads, Sq, Skv, mask, drop_mask, drop_scale):
     return a
 
 
-def attention_fwd(q, k, v, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0, out=None, save_fp32=False):
-    """ctx, lse2 (, ctx32) = fused softmax(QK^T/sqrt(d) + mask) V.  q [B*Sq, h*d], k/v [B*Skv, h*d] (views allowed).
-    save_fp32: also return an fp32 copy of ctx for the backward's delta = rowsum(dO * O)."""
+def attention_fwd(q, k, v, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0, out=None, save_lo=False):
+    """ctx, lse2 (, ctx_lo) = fused softmax(QK^T/sqrt(d) + mask) V.  q [B*Sq, h*d], k/v [B*Skv, h*d] (views allowed).
+    save_lo: also return ctx_lo = bf16(O - float(ctx)), the part of the fp32 output the bf16 ctx drops; the backward's
+    delta = rowsum(dO * (ctx + ctx_lo)) then carries no common rounding bias per row."""
     a = _attn_args(q, k, v, B, heads, Sq, Skv, mask, drop_mask, drop_scale)
     W = q.shape[-1]
     ctx = out if out is not None else torch.empty(B * Sq, W, dtype=torch.bfloat16, device=q.device)
     lse2 = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
     a.ctx, a.ldo, a.lse2 = ctx.data_ptr(), ctx.stride(0), lse2.data_ptr()
-    ctx32 = None
-    if save_fp32:
-        ctx32 = torch.empty(B * Sq, W, dtype=torch.float32, device=q.device)
-        a.ctx32 = ctx32.data_ptr()
+    ctx_lo = None
+    if save_lo:
+        ctx_lo = torch.empty(B * Sq, W, dtype=torch.bfloat16, device=q.device)
+        a.ctx_lo = ctx_lo.data_ptr()
     check(LIB.mmfb_attention_fwd(ctypes.byref(a), _stream_ptr()))
-    if save_fp32:
-        return ctx, lse2, ctx32
+    if save_lo:
+        return ctx, lse2, ctx_lo
     return ctx, lse2
 
 
 def attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0,
-                  dq=None, dk=None, dv=None, ctx32=None):
+                  dq=None, dk=None, dv=None, ctx_lo=None):
     """dq, dk, dv from the saved q, k, v, ctx and row statistics (probabilities are recomputed)."""
     a = _attn_args(q, k, v, B, heads, Sq, Skv, mask, drop_mask, drop_scale)
     _req(dctx, torch.bfloat16, "dctx")
@@ -133,9 +134,11 @@ def attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask=None, drop_m
     delta = torch.empty(B, heads, Sq, dtype=torch.float32, device=q.device)
     a.ctx, a.ldo, a.lse2 = ctx.data_ptr(), ctx.stride(0), lse2.data_ptr()
     a.dctx, a.ld_dctx, a.delta = dctx.data_ptr(), dctx.stride(0), delta.data_ptr()
-    if ctx32 is not None:
-        _req(ctx32, torch.float32, "ctx32")
-        a.ctx32 = ctx32.data_ptr()
+    if ctx_lo is not None:
+        _req(ctx_lo, torch.bfloat16, "ctx_lo")
+        if not ctx_lo.is_contiguous():
+            raise ValueError("ctx_lo must be contiguous [B*Sq, heads*head_dim]")
+        a.ctx_lo = ctx_lo.data_ptr()
     a.dq, a.ld_dq = dq.data_ptr(), dq.stride(0)
     a.dk, a.ld_dk = dk.data_ptr(), dk.stride(0)
     a.dv, a.ld_dv = dv.data_ptr(), dv.stride(0)

@@ -47,7 +47,7 @@ class AttnArgs(ctypes.Structure):
         ("ctx", ctypes.c_void_p), ("ldo", ctypes.c_int64),
         ("lse2", ctypes.c_void_p),
         ("drop_mask", ctypes.c_void_p), ("drop_scale", ctypes.c_float),
-        ("ctx32", ctypes.c_void_p),
+        ("ctx_lo", ctypes.c_void_p),
         ("dctx", ctypes.c_void_p), ("ld_dctx", ctypes.c_int64),
         ("delta", ctypes.c_void_p),
         ("dq", ctypes.c_void_p), ("ld_dq", ctypes.c_int64),

@@ -87,7 +87,7 @@ def _probs(q, k, B, heads, Sq, Skv, mask):
     return s
 
 
-def attention_fwd(q, k, v, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0, out=None, save_fp32=False):
+def attention_fwd(q, k, v, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0, out=None, save_lo=False):
     s = _probs(q, k, B, heads, Sq, Skv, mask)
     lse2 = torch.logsumexp(s, dim=-1) * LOG2E
     p = torch.softmax(s, dim=-1)
@@ -98,16 +98,16 @@ def attention_fwd(q, k, v, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_sc
     if out is not None:
         out.copy_(ctx)
         ctx = out
-    return (ctx, lse2, ctx32) if save_fp32 else (ctx, lse2)
+    return (ctx, lse2, (ctx32 - ctx.float()).to(BF)) if save_lo else (ctx, lse2)
 
 
 def attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask=None, drop_mask=None, drop_scale=1.0, dq=None,
-                  dk=None, dv=None, ctx32=None):
+                  dk=None, dv=None, ctx_lo=None):
     d = q.shape[-1] // heads
     s = _probs(q, k, B, heads, Sq, Skv, mask)
     p = torch.exp2(s * LOG2E - lse2.unsqueeze(-1))              # from the saved row statistics, as the kernel does
     dO = _heads(dctx, B, Sq, heads)
-    O = _heads(ctx32 if ctx32 is not None else ctx, B, Sq, heads)
+    O = _heads(ctx.float() + ctx_lo.float() if ctx_lo is not None else ctx, B, Sq, heads)
     delta = (dO * O).sum(-1, keepdim=True)
     dP = dO @ _heads(v, B, Skv, heads).transpose(-1, -2)
     pd = p

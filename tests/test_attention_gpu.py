@@ -37,11 +37,11 @@ def _case(B, heads, Sq, Skv, d, p_drop=0.0, masked=True, seed=0, full_mask_row=F
         dm = F.pack_keep_bits(keep)
     scale = 1.0 / (1.0 - p_drop)
     ctx, lse2, ctx32 = F.attention_fwd(q, k, v, B, heads, Sq, Skv, mask=add, drop_mask=dm, drop_scale=scale,
-                                       save_fp32=True)
-    assert rel(ctx32, ctx) < 5e-3     # the fp32 copy and the bf16 output are the same values
+                                       save_lo=True)
+    assert ctx32.dtype == torch.bfloat16 and ctx32.abs().max() <= ctx.abs().max() * 2.0 ** -7   # the low part is a rounding residual
     dctx = (torch.randn(B * Sq, W, generator=g, device="cuda")).to(torch.bfloat16)
     dq, dk, dv = F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, Sq, Skv, mask=add, drop_mask=dm,
-                                 drop_scale=scale, ctx32=ctx32 if seed % 2 == 0 else None)
+                                 drop_scale=scale, ctx_lo=ctx32 if seed % 2 == 0 else None)
     torch.cuda.synchronize()
     # oracle (fp32, same bf16-rounded inputs)
     qf = q.float().view(B, Sq, W).clone().requires_grad_(True)

@@ -28,7 +28,7 @@ lens = torch.randint(S // 2, S + 1, (B,), device=dev)          # ragged key padd
 mask = ((torch.arange(S, device=dev)[None] >= lens[:, None]).float() * -10000.0).contiguous()
 bits_a = F.dropout_bits((B, heads, S), S, 0.1, 7, 0, dev)
 dctx = torch.randn(M, H, device=dev).to(bf)
-ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_fp32=True)
+ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_lo=True)
 g = torch.ones(H, device=dev, dtype=bf)
 _, mean, rstd = F.layernorm_fwd(x, g, torch.zeros_like(g))
 dg, db_, dbias = (torch.zeros(H, device=dev) for _ in range(3))
@@ -39,7 +39,7 @@ def attn_bwd(env):
     for k_, v_ in env.items():
         os.environ[k_] = v_
     F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, S, S, mask, bits_a, 1 / 0.9, dq=dq[:, :H], dk=dq[:, H:2 * H],
-                    dv=dq[:, 2 * H:], ctx32=c32)
+                    dv=dq[:, 2 * H:], ctx_lo=c32)
     for k_ in env:
         os.environ.pop(k_, None)
 
@@ -54,7 +54,7 @@ def ln_bwd(variant):
 def attn_fwd(env):
     for k_, v_ in env.items():
         os.environ[k_] = v_
-    F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_fp32=True)
+    F.attention_fwd(q, k, v, B, heads, S, S, mask, bits_a, 1 / 0.9, save_lo=True)
     for k_ in env:
         os.environ.pop(k_, None)
 
