@@ -677,6 +677,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float* gSum = sSum + t * 256;
       const int bar_id = 1 + t;
       const uint32_t pcol = half == 0 ? COL_PLO : COL_PHI;
+      // Turn-taking around the exponential pass: the SM issues 16 MUFU.EX2 per clock, so the second passes of the two tiles
+      // (2 x 32768 exponentials per item) are a shared 4096-cycle resource; round-2 traces showed the groups in lockstep -
+      // both in the exponentials, then both idle behind their MMAs.  With the pass serialised (named barriers 3 / 4:
+      // a group enters when the other one has left) they settle half a period apart and one group's MMA waits, row-maximum
+      // pass and epilogue run under the other's exponentials.  Group 0 goes first.
+      const bool pingpong = nt == 2;
+      if (pingpong && t == 1) asm volatile("bar.arrive 3, 512;" ::: "memory");
       for (int n = 0;; ++n) {
         const bool tr = (threadIdx.x & 255) == 0;
         if (tr) MMFB_TR(t, n, 0);
@@ -722,6 +729,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (tr) MMFB_TR(t, n, 4);
         mx = fmaxf(gMax[row], gMax[128 + row]);
         // ---- pass 2, last chunk first (chunks 3 and 2 are still in rb / ra): probabilities -> tensor memory ----
+        if (pingpong) {
+          if (t == 0) asm volatile("bar.sync 3, 512;" ::: "memory");
+          else asm volatile("bar.sync 4, 512;" ::: "memory");
+        }
         float sum = 0.0f;
         uint32_t pk[16];
         if (on3) {
@@ -743,6 +754,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (on0) {
           fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk);
           tmem_st16(treg + pcol + 0, pk);
+        }
+        if (pingpong) {
+          if (t == 0) asm volatile("bar.arrive 4, 512;" ::: "memory");
+          else asm volatile("bar.arrive 3, 512;" ::: "memory");
         }
         gSum[half * 128 + row] = sum;
         if (tr) MMFB_TR(t, n, 5);
@@ -1731,12 +1746,13 @@ attn_bwd_fused16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 //     read, so the tensor core and the TMA engine work through the epilogue stores of the previous item.
 // 576 threads: warps 0..15 compute (thread = query row x 32-column chunk), warp 16 = MMA issue, warp 17 = loader.
 // ----------------------------------------------------------------------------------------------
-constexpr int BWD_PERS_THREADS = 576;
+constexpr int BWD_PERS_THREADS = 608;       // 16 compute warps + MMA-issue warp + loader warp + store warp
 template <bool DROP>
 __global__ void __launch_bounds__(BWD_PERS_THREADS, 1)
 attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                     AttnBwdFusedDev p, int n_items, int* sched) {
+                     const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
+                     const __grid_constant__ CUtensorMap tmdV, AttnBwdFusedDev p, int n_items, int* sched) {
   griddep_launch();
   griddep_wait();
   constexpr int D = 64;
@@ -1760,7 +1776,11 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* acc_done = bars + 12;
   uint64_t* kv_read = bars + 13;      // 512 arrivals, phase = key-block counter parity
   uint64_t* dq_read = bars + 14;      // 512 arrivals, phase = item parity
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* sdp_read = bars + 15;     // 512 arrivals: S / dP of the pair are in registers, the score columns are free
+  uint64_t* kv_staged = bars + 16;    // 512 arrivals: dK_j / dV_j are in the K_j / V_j slots (phase = key-block counter)
+  uint64_t* dq_staged = bars + 17;    // 512 arrivals: dQ_i are in the P' buffer (phase = item parity)
+  uint64_t* stg_free = bars + 18;     // the dQ store has finished reading the P' buffer (phase = item parity)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   uint32_t* sAct = tmem_slot + 1;     // [2 buffers] bit c: 32-key chunk c has an attendable key
   int* sItem = reinterpret_cast<int*>(sAct + 2);    // [2 buffers] (batch, head) item, -1 = no more work; published by stat_full
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
@@ -1773,7 +1793,9 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (lane == 0) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       for (int x = 0; x < 2; ++x) { mbar_init(&q_full[x], 1); mbar_init(&kv_full[x], 1); mbar_init(&stat_full[x], 32); }
-      for (int x = 0; x < 4; ++x) mbar_init(&tile_free[x], 1);
+      // K_j / V_j slots double as staging for dK_j / dV_j: released by the MMA thread's commit AND the store warp
+      mbar_init(&tile_free[0], 2); mbar_init(&tile_free[1], 1); mbar_init(&tile_free[2], 1); mbar_init(&tile_free[3], 2);
+      mbar_init(sdp_read, 512); mbar_init(kv_staged, 512); mbar_init(dq_staged, 512); mbar_init(stg_free, 1);
       mbar_init(s_ready, 1);
       mbar_init(p_ready, 512);
       mbar_init(acc_done, 1);
@@ -1905,13 +1927,18 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int pidx = j * ni + i;
             const uint32_t aQ = smem_u32(sQ + i * TILE), adO = smem_u32(sdO + i * TILE);
             const uint32_t aK = smem_u32(sK + j * TILE);
-            mbar_wait(p_ready, g & 1);               // S/dP of this pair have been read, P'/dS' are in shared memory
-            MMFB_TR(1, n, 2 * pidx);
             const bool last_pair = pidx == np - 1;
+            // the next pair's scores go out as soon as every thread holds S / dP of this one in registers: the tensor core
+            // computes them while the threads are still in the exp / dS arithmetic (the round-2 trace showed ~1000 idle
+            // cycles per pair between "P'/dS' stored" and "next scores ready")
+            mbar_wait(sdp_read, g & 1);
             if (!last_pair) {
               const int i2 = (i + 1 < ni) ? i + 1 : 0, j2 = (i + 1 < ni) ? j : j + 1;
+              tc_fence_after();
               issue_scores(n, i2, j2);               // next pair of this item: its tiles are resident
             }
+            mbar_wait(p_ready, g & 1);               // P'/dS' of this pair are in shared memory
+            MMFB_TR(1, n, 2 * pidx);
             // accumulators that are overwritten (not accumulated) must have been read out by the compute threads
             if (i == 0 && kb > 0) mbar_wait(kv_read, (kb - 1) & 1);
             if (pidx == 0 && n > 0) mbar_wait(dq_read, (n - 1) & 1);
@@ -1944,17 +1971,80 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     }
+  } else if (warp == 18) {
+    // ------------------------------------ store warp: bulk tensor stores of dK_j, dV_j, dQ_i ------------------------------------
+    // (16-byte register stores of a warp to 32 different rows cost 32 LSU passes each; rows beyond Sq / Skv are clipped by
+    // the tensor maps)
+    uint32_t kbs = 0;
+    for (int n = 0;; ++n) {
+      mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
+      const int it = sItem[n & 1];
+      if (it < 0) break;
+      const int h = it % p.H, b = it / p.H;
+      for (int j = 0; j < nj; ++j, ++kbs) {
+        mbar_wait(kv_staged, kbs & 1);
+        if (lane == 0) {
+          tma_store_3d(&tmdK, sK + j * TILE, h * D, j * 128, b);
+          tma_store_3d(&tmdV, sV + j * TILE, h * D, j * 128, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&tile_free[j == 0 ? 0 : 3]);
+        }
+        __syncwarp();
+      }
+      mbar_wait(dq_staged, n & 1);
+      if (lane == 0) {
+        for (int i = 0; i < ni; ++i) tma_store_3d(&tmdQ, sP + i * TILE, h * D, i * 128, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(stg_free);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes complete before the CTA exits
   } else {
     // ------------------------------------ compute ------------------------------------
     const int quarter = warp & 3, c = warp >> 2;          // c: this thread's 32-column chunk of the key block
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t g = 0, kb = 0;
+    int h = 0, b = 0;
+    // dK_j, dV_j (rows = keys of block j, 16 of the 64 columns of each per thread) -> K_j / V_j slots (their last readers, the
+    // accumulations of the block's last pair, have completed) -> one bulk tensor store per tile by the store warp
+    auto readout_kv = [&](int jb) {
+      uint32_t rk[16], rv[16];
+      tc_fence_after();
+      tmem_ld16(trow + COL_DK + c * 16, rk);
+      tmem_ld16(trow + COL_DV + c * 16, rv);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(kv_read);
+      uint8_t* krow = sK + jb * TILE + row * 128;
+      uint8_t* vrow = sV + jb * TILE + row * 128;
+#pragma unroll
+      for (int qd = 0; qd < 2; ++qd) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(rk[qd * 8 + 0]) * p.scale, __uint_as_float(rk[qd * 8 + 1]) * p.scale);
+        o.y = pack_bf16x2(__uint_as_float(rk[qd * 8 + 2]) * p.scale, __uint_as_float(rk[qd * 8 + 3]) * p.scale);
+        o.z = pack_bf16x2(__uint_as_float(rk[qd * 8 + 4]) * p.scale, __uint_as_float(rk[qd * 8 + 5]) * p.scale);
+        o.w = pack_bf16x2(__uint_as_float(rk[qd * 8 + 6]) * p.scale, __uint_as_float(rk[qd * 8 + 7]) * p.scale);
+        const int chunk = ((c * 2 + qd) ^ (row & 7)) * 16;
+        *reinterpret_cast<uint4*>(krow + chunk) = o;
+        o.x = pack_bf16x2(__uint_as_float(rv[qd * 8 + 0]), __uint_as_float(rv[qd * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(rv[qd * 8 + 2]), __uint_as_float(rv[qd * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(rv[qd * 8 + 4]), __uint_as_float(rv[qd * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(rv[qd * 8 + 6]), __uint_as_float(rv[qd * 8 + 7]));
+        *reinterpret_cast<uint4*>(vrow + chunk) = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(kv_staged);
+    };
     for (int n = 0;; ++n) {
       mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
       const int it = sItem[n & 1];
       if (it < 0) break;
-      const int h = it % p.H, b = it / p.H;
+      h = it % p.H;
+      b = it / p.H;
       const int64_t bh = static_cast<int64_t>(b) * p.H + h;
       const float* sLse = sStat + (n & 1) * 768;
       const float* sDel = sLse + 256;
@@ -1980,6 +2070,8 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (!chunk_on) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) { wds[e] = 0u; wp[e] = 0u; }
+            tc_fence_before();
+            mbar_arrive(sdp_read);
           }
 #pragma unroll
           for (int hh = 0; hh < 2 && chunk_on; ++hh) {
@@ -1987,6 +2079,10 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tmem_ld16(trow + COL_S + c * 32 + hh * 16, rs);
             tmem_ld16(trow + COL_DP + c * 32 + hh * 16, rd);
             tmem_ld_wait();
+            if (hh == 1) {                                    // both halves are in registers: the score columns are free
+              tc_fence_before();
+              mbar_arrive(sdp_read);
+            }
             const uint64_t sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-l2, -l2), ndl2 = pk2(-dl, -dl);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
@@ -2016,6 +2112,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           // the accumulations of the previous pair still read P'/dS' while the arithmetic above ran
           if (tr) MMFB_TR(0, n, 3 * (j * ni + i) + 1);
           if (g > 0) mbar_wait(acc_done, (g - 1) & 1);
+          if (j == 0 && i == 0 && n > 0) mbar_wait(stg_free, (n - 1) & 1);   // the previous item's dQ store has read the P' buffer
           uint8_t* dsrow = sDS + (c >> 1) * TILE + row * 128;
           uint8_t* prow = sP + (c >> 1) * TILE + row * 128;
 #pragma unroll
@@ -2028,62 +2125,41 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tc_fence_before();
           mbar_arrive(p_ready);
           if (tr) MMFB_TR(0, n, 3 * (j * ni + i) + 2);
+          // the previous key block's dK / dV leave AFTER this pair's arithmetic: their accumulations (waited for above)
+          // completed while it ran, instead of 512 threads idling through them at the block boundary
+          if (i == 0 && j > 0) readout_kv(j - 1);
         }
-        // ---- dK_j, dV_j are complete: rows = keys of block j; this thread stores 16 of the 64 columns of each ----
-        mbar_wait(acc_done, (g - 1) & 1);
+      }
+      // ---- item end: the last key block's dK / dV, then dQ (every accumulation of the item is complete) ----
+      mbar_wait(acc_done, (g - 1) & 1);
+      readout_kv(nj - 1);
+      {
+        uint32_t rq[2][16];
         tc_fence_after();
-        {
-          const int kvr = j * 128 + row;
-          uint32_t rk[16], rv[16];
-          tmem_ld16(trow + COL_DK + c * 16, rk);
-          tmem_ld16(trow + COL_DV + c * 16, rv);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(kv_read);
-          if (kvr < p.Skv) {
-            uint4* dk4 = reinterpret_cast<uint4*>(p.dk + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dk + h * D + c * 16);
-            uint4* dv4 = reinterpret_cast<uint4*>(p.dv + (static_cast<int64_t>(b) * p.Skv + kvr) * p.ld_dv + h * D + c * 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (i < ni) tmem_ld16(trow + COL_DQ + i * D + c * 16, rq[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_read);
+        if (tr) MMFB_TR(0, n, 12);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (i < ni) {
+            uint8_t* qrow = sP + i * TILE + row * 128;           // P' buffer: free since the last accumulation completed
 #pragma unroll
             for (int qd = 0; qd < 2; ++qd) {
               uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(rk[qd * 8 + 0]) * p.scale, __uint_as_float(rk[qd * 8 + 1]) * p.scale);
-              o.y = pack_bf16x2(__uint_as_float(rk[qd * 8 + 2]) * p.scale, __uint_as_float(rk[qd * 8 + 3]) * p.scale);
-              o.z = pack_bf16x2(__uint_as_float(rk[qd * 8 + 4]) * p.scale, __uint_as_float(rk[qd * 8 + 5]) * p.scale);
-              o.w = pack_bf16x2(__uint_as_float(rk[qd * 8 + 6]) * p.scale, __uint_as_float(rk[qd * 8 + 7]) * p.scale);
-              dk4[qd] = o;
-              o.x = pack_bf16x2(__uint_as_float(rv[qd * 8 + 0]), __uint_as_float(rv[qd * 8 + 1]));
-              o.y = pack_bf16x2(__uint_as_float(rv[qd * 8 + 2]), __uint_as_float(rv[qd * 8 + 3]));
-              o.z = pack_bf16x2(__uint_as_float(rv[qd * 8 + 4]), __uint_as_float(rv[qd * 8 + 5]));
-              o.w = pack_bf16x2(__uint_as_float(rv[qd * 8 + 6]), __uint_as_float(rv[qd * 8 + 7]));
-              dv4[qd] = o;
+              o.x = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 0]) * p.scale, __uint_as_float(rq[i][qd * 8 + 1]) * p.scale);
+              o.y = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 2]) * p.scale, __uint_as_float(rq[i][qd * 8 + 3]) * p.scale);
+              o.z = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 4]) * p.scale, __uint_as_float(rq[i][qd * 8 + 5]) * p.scale);
+              o.w = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 6]) * p.scale, __uint_as_float(rq[i][qd * 8 + 7]) * p.scale);
+              *reinterpret_cast<uint4*>(qrow + (((c * 2 + qd) ^ (row & 7)) * 16)) = o;
             }
           }
         }
-      }
-      // ---- dQ_i: rows = queries (every accumulation of the item is complete: acc_done of its last pair was waited for) ----
-      uint32_t rq[2][16];
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (i < ni) tmem_ld16(trow + COL_DQ + i * D + c * 16, rq[i]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_read);
-      if (tr) MMFB_TR(0, n, 12);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int q = i * 128 + row;
-        if (i < ni && q < p.Sq) {
-          uint4* dq4 = reinterpret_cast<uint4*>(p.dq + (static_cast<int64_t>(b) * p.Sq + q) * p.ld_dq + h * D + c * 16);
-#pragma unroll
-          for (int qd = 0; qd < 2; ++qd) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 0]) * p.scale, __uint_as_float(rq[i][qd * 8 + 1]) * p.scale);
-            o.y = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 2]) * p.scale, __uint_as_float(rq[i][qd * 8 + 3]) * p.scale);
-            o.z = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 4]) * p.scale, __uint_as_float(rq[i][qd * 8 + 5]) * p.scale);
-            o.w = pack_bf16x2(__uint_as_float(rq[i][qd * 8 + 6]) * p.scale, __uint_as_float(rq[i][qd * 8 + 7]) * p.scale);
-            dq4[qd] = o;
-          }
-        }
+        fence_proxy_async();
+        mbar_arrive(dq_staged);
       }
     }
   }
@@ -2321,8 +2397,12 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       const int grid_p = n_items < num_sms() ? n_items : num_sms();
       int* sched = sched_counters();
       if (sched == nullptr) return set_error(MMFB_ERR_CUDA, "attn_bwd: scheduler counters");
-      if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_pers_kernel<true>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items, sched + 4);
-      else MMFB_LAUNCH(attn_bwd_pers_kernel<false>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, f, n_items, sched + 4);
+      CUtensorMap tmdQ, tmdK, tmdV;
+      if ((rc = make_tmap_3d(&tmdQ, a.dq, W, a.Sq, a.B, a.ld_dq, a.ld_dq * a.Sq, 64, 128))) return rc;
+      if ((rc = make_tmap_3d(&tmdK, a.dk, W, a.Skv, a.B, a.ld_dk, a.ld_dk * a.Skv, 64, 128))) return rc;
+      if ((rc = make_tmap_3d(&tmdV, a.dv, W, a.Skv, a.B, a.ld_dv, a.ld_dv * a.Skv, 64, 128))) return rc;
+      if (f.dmask != nullptr) MMFB_LAUNCH(attn_bwd_pers_kernel<true>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, tmdQ, tmdK, tmdV, f, n_items, sched + 4);
+      else MMFB_LAUNCH(attn_bwd_pers_kernel<false>, grid_p, BWD_PERS_THREADS, smem_p, stream, tmQ, tmdO, tmK, tmV, tmdQ, tmdK, tmdV, f, n_items, sched + 4);
     } else if (w_env[0] != '8') {
       static bool w16_attr = false;
       if (!w16_attr) {
