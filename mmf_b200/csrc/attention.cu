@@ -677,13 +677,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float* gSum = sSum + t * 256;
       const int bar_id = 1 + t;
       const uint32_t pcol = half == 0 ? COL_PLO : COL_PHI;
-      // Turn-taking around the exponential pass: the SM issues 16 MUFU.EX2 per clock, so the second passes of the two tiles
-      // (2 x 32768 exponentials per item) are a shared 4096-cycle resource; round-2 traces showed the groups in lockstep -
-      // both in the exponentials, then both idle behind their MMAs.  With the pass serialised (named barriers 3 / 4:
-      // a group enters when the other one has left) they settle half a period apart and one group's MMA waits, row-maximum
-      // pass and epilogue run under the other's exponentials.  Group 0 goes first.
-      const bool pingpong = nt == 2;
-      if (pingpong && t == 1) asm volatile("bar.arrive 3, 512;" ::: "memory");
+      // (Measured and dropped: serialising the two groups' exponential passes with named barriers so that they settle half
+      // a period apart - 185 k cycles per 14 items with and without it: the pass is bound by the issue slots of the group's
+      // own 8 warps, not by the SM's 16 MUFU lanes, so running both groups' passes together costs nothing extra.)
       for (int n = 0;; ++n) {
         const bool tr = (threadIdx.x & 255) == 0;
         if (tr) MMFB_TR(t, n, 0);
@@ -729,10 +725,6 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (tr) MMFB_TR(t, n, 4);
         mx = fmaxf(gMax[row], gMax[128 + row]);
         // ---- pass 2, last chunk first (chunks 3 and 2 are still in rb / ra): probabilities -> tensor memory ----
-        if (pingpong) {
-          if (t == 0) asm volatile("bar.sync 3, 512;" ::: "memory");
-          else asm volatile("bar.sync 4, 512;" ::: "memory");
-        }
         float sum = 0.0f;
         uint32_t pk[16];
         if (on3) {
@@ -754,10 +746,6 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (on0) {
           fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk);
           tmem_st16(treg + pcol + 0, pk);
-        }
-        if (pingpong) {
-          if (t == 0) asm volatile("bar.arrive 4, 512;" ::: "memory");
-          else asm volatile("bar.arrive 3, 512;" ::: "memory");
         }
         gSum[half * 128 + row] = sum;
         if (tr) MMFB_TR(t, n, 5);

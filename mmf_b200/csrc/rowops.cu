@@ -852,24 +852,33 @@ colsum_kernel(const bf16* __restrict__ X, int64_t ldx, float* __restrict__ out, 
 // ----------------------------------------------------------------------------------------------
 // dropout keep-bits: word w, bit j keeps element 32*w + j with probability 1-p (16-bit resolution)
 // ----------------------------------------------------------------------------------------------
+// Bit-sliced comparison: the 16 Philox words of a thread are read as 16 bit-PLANES of 32 sixteen-bit uniforms r_e (bit e of
+// plane b = bit b of r_e), and r_e >= thresh16 is evaluated for the 32 elements at once, most significant plane first
+// (<= 2 logic operations per plane; the branch on the threshold bit is uniform).  Same distribution and resolution as
+// comparing 16-bit fields one by one (the round-1 form: ~3 extract / compare / insert operations per ELEMENT).
 __global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t nwords, uint64_t seed, uint64_t offset,
                                     uint32_t thresh16) {
   griddep_launch();
   griddep_wait();
   const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (w >= nwords) return;
-  uint32_t bits = 0;
+  uint32_t gt = 0u, eq = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint4 r = philox4x32(seed, offset + static_cast<uint64_t>(w) * 4 + i);
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      bits |= ((rr[k] & 0xFFFFu) >= thresh16 ? 1u : 0u) << (i * 8 + k * 2);
-      bits |= ((rr[k] >> 16) >= thresh16 ? 1u : 0u) << (i * 8 + k * 2 + 1);
+      const int b = 15 - (i * 4 + k);              // plane of bit b, most significant first
+      if ((thresh16 >> b) & 1u) {
+        eq &= rr[k];                               // threshold bit 1: equal so far only where the uniform's bit is 1 too
+      } else {
+        gt |= eq & rr[k];                          // threshold bit 0, uniform bit 1: greater from here on
+        eq &= ~rr[k];
+      }
     }
   }
-  out[w] = bits;
+  out[w] = gt | eq;                                // keep where r >= thresh16
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1117,11 +1126,12 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
   if (!a.dx || !a.y || !a.mean || !a.rstd || !a.gamma) return set_error(MMFB_ERR_ARG, "layernorm_bwd: null pointer");
   if (a.drop_mask && !a.dz) return set_error(MMFB_ERR_ARG, "layernorm_bwd: dropout mask given without dz");
   const int nv_ = (a.H + 255) / 256;
-  // read per call (not cached) so that one test process can run both variants back to back
-  // default: the single-pass "lean" kernel (74 us against 103 us for the rows + cols pair and 79 us for the tile variant
-  // at [37848, 768], profiles/r2_kbench_before.json); MMFB_LN_BWD=pair / tile select the others for A/B runs
+  // read per call (not cached) so that one test process can run the variants back to back.
+  // default: the streaming single-pass kernel (58 us at [37848, 768] against 66 us for "lean", 80 us for "tile" and 100 us
+  // for the rows + cols "pair", profiles/r2_kbench_persistent_attn_stream_ln.json); MMFB_LN_BWD=lean / tile / pair select
+  // the others for A/B runs
   const char* lean_env = getenv("MMFB_LN_BWD");
-  const bool lean = lean_env == nullptr || lean_env[0] == 'l';
+  const bool lean = lean_env != nullptr && lean_env[0] == 'l';
   const bool tile = lean_env != nullptr && lean_env[0] == 't';
   if (tile && nv_ <= 4) {
     const int64_t n_steps = (static_cast<int64_t>(a.M) + 3) / 4;
@@ -1145,7 +1155,7 @@ int ln_bwd(const mmfb_ln_args& a, cudaStream_t s) {
 #undef LN_TILE
     return launch_ok("layernorm_bwd(tile)");
   }
-  const bool stream = lean_env != nullptr && lean_env[0] == 's';
+  const bool stream = lean_env == nullptr || lean_env[0] == 's';
   // bulk copies need 16-byte aligned rows (H % 8 == 0 is already required; leading dimensions in elements % 8 too)
   if (stream && nv_ <= 4 && a.lddx % 8 == 0 && a.ldy % 8 == 0 && (a.dx2 == nullptr || a.lddx2 % 8 == 0)) {
     int grid = (a.M + ROW_WARPS - 1) / ROW_WARPS;
@@ -1248,7 +1258,8 @@ int colsum(const void* X, int64_t ldx, float* out, int M, int N, cudaStream_t s)
 int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, cudaStream_t s) {
   if (nwords <= 0) return set_error(MMFB_ERR_ARG, "dropout_bits: empty");
   if (!(p >= 0.0f && p < 1.0f)) return set_error(MMFB_ERR_ARG, "dropout_bits: p must be in [0,1), got %f", p);
-  const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  if (thresh > 65535u) thresh = 65535u;          // 16 planes: p within 2^-16 of 1 keeps one element in 65536
   MMFB_LAUNCH(dropout_bits_kernel, static_cast<unsigned>((nwords + 255) / 256), 256, 0, s, out, nwords, seed, offset, thresh);
   return launch_ok("dropout_bits");
 }

@@ -37,6 +37,21 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    # host synchronisations inside the step (each one drains the launch queue): torch reports them with a stack
+    import warnings
+    torch.cuda.set_sync_debug_mode("warn")
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        step()
+    torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    print("synchronising calls in one step: %d" % len(caught))
+    seen = set()
+    for w in caught:
+        key = (w.filename, w.lineno)
+        if key not in seen:
+            seen.add(key)
+            print("  %s:%d  %s" % (w.filename.replace(ROOT + "/", ""), w.lineno, str(w.message)[:100]))
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(args.steps):
             step()
