@@ -716,6 +716,9 @@ def main():
     ap.add_argument("--optimizer", action="store_true",
                     help="also time the step WITH the fused AdamW update (mmf_b200.optim.B200AdamW, BERT parameter groups); "
                          "reported as `with_optimizer`, the headline value stays forward + backward (BASELINE.json metric)")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step (forward + backward) as ONE CUDA graph (mmf_b200.graphs.GraphedStep): for the "
+                         "small configurations whose kernels are shorter than a host launch; single GPU only")
     ap.add_argument("--profile", action="store_true", help="device-resident steps only (for ncu launch lists)")
     args = ap.parse_args()
 
@@ -785,6 +788,19 @@ def main():
         loss.backward()
         return loss
 
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph is a single-GPU mode")
+        from mmf_b200.graphs import GraphedStep
+        lc0 = lib.launch_count()
+        graphed = GraphedStep(model, lambda b: wl.loss(net, b, aux), dev_batch, warmup=3)
+        graph_launches = (lib.launch_count() - lc0) // 4        # 3 warm-up steps + the captured one: kernels per replay
+        config["kernels_per_graph"] = graph_launches
+        config["step_launch"] = "one CUDA graph per step (stream capture of the eager step; dropout masks advance through a device counter)"
+
+        def step(batch):        # noqa: F811  (same contract: forward + backward of `batch`, returns the loss)
+            return graphed(batch)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -827,6 +843,8 @@ def main():
     if args.profile:
         torch.cuda.profiler.stop()
     launches = lib.launch_count() - launches0
+    if args.graph:
+        launches = graph_launches * args.steps      # replays do not pass through the C ABI: kernels recorded at capture x steps
     clocks = sampler.stop() if rank == 0 else None
     if args.profile:
         if rank == 0:

@@ -126,6 +126,10 @@ int mmfb_colsum(const void* X, int64_t ldx, float* out, int M, int N, mmfb_strea
 
 /* Philox keep-bits for nn.Dropout(p): word w bit j <-> element 32*w+j, P(bit=1) = 1-p (16-bit resolution) */
 int mmfb_dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, mmfb_stream stream);
+/* the same with a step counter in DEVICE memory mixed into the Philox counter (counter += *epoch << 40): a CUDA-graph replay of a
+ * captured training step draws fresh masks as long as the graph increments *epoch (mmf_b200/graphs.py) */
+int mmfb_dropout_bits_epoch(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, const uint64_t* epoch, float p,
+                            mmfb_stream stream);
 
 /* Embedding row composer (K1): y[r] = src0[src_row0[r]] + src1[src_row1[r]] + tab0[idx0[r]] + tab1[idx1[r]] +
  * tab2[idx2[r]]; a NULL pointer or a negative index drops the term.  src*: bf16 [*, ldsrc] dense rows (e.g. the

@@ -37,6 +37,7 @@ _LAZY = {
     "MMFTransformer": ("mmft", "MMFTransformer"),
     "build_model": ("models", "build_model"),
     "load_model_config": ("models", "load_model_config"),
+    "GraphedStep": ("graphs", "GraphedStep"),
 }
 
 

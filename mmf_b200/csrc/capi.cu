@@ -165,7 +165,13 @@ int mmfb_colsum(const void* X, int64_t ldx, float* out, int M, int N, mmfb_strea
 int mmfb_dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, mmfb_stream stream) {
   if (!out) return set_error(MMFB_ERR_ARG, "mmfb_dropout_bits: null pointer");
   MMFB_REQUIRE_DEVICE();
-  return dropout_bits(out, nwords, seed, offset, p, reinterpret_cast<cudaStream_t>(stream));
+  return dropout_bits(out, nwords, seed, offset, p, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+int mmfb_dropout_bits_epoch(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, const uint64_t* epoch, float p,
+                            mmfb_stream stream) {
+  if (!out || !epoch) return set_error(MMFB_ERR_ARG, "mmfb_dropout_bits_epoch: null pointer");
+  MMFB_REQUIRE_DEVICE();
+  return dropout_bits(out, nwords, seed, offset, p, epoch, reinterpret_cast<cudaStream_t>(stream));
 }
 int mmfb_embed_compose(const mmfb_compose_args* args, mmfb_stream stream) {
   if (!args) return set_error(MMFB_ERR_ARG, "mmfb_embed_compose: null args");

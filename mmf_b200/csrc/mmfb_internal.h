@@ -69,7 +69,7 @@ int attn_bwd(const mmfb_attn_args& a, cudaStream_t stream);
 int ln_fwd(const mmfb_ln_args& a, cudaStream_t s);
 int ln_bwd(const mmfb_ln_args& a, cudaStream_t s);
 int colsum(const void* X, int64_t ldx, float* out, int M, int N, cudaStream_t s);
-int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, cudaStream_t s);
+int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, const uint64_t* epoch, cudaStream_t s);
 int compose(const mmfb_compose_args& a, cudaStream_t s);
 int scatter(const mmfb_scatter_args& a, cudaStream_t s);
 int cast_params(const float* in, void* out, int64_t n, cudaStream_t s);

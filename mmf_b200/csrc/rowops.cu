@@ -856,12 +856,15 @@ colsum_kernel(const bf16* __restrict__ X, int64_t ldx, float* __restrict__ out, 
 // plane b = bit b of r_e), and r_e >= thresh16 is evaluated for the 32 elements at once, most significant plane first
 // (<= 2 logic operations per plane; the branch on the threshold bit is uniform).  Same distribution and resolution as
 // comparing 16-bit fields one by one (the round-1 form: ~3 extract / compare / insert operations per ELEMENT).
+// `epoch` (optional, device memory): a step counter added to the Philox counter as epoch << 40, so that a CUDA-graph replay of a
+// captured step (host arguments frozen at capture) still draws fresh masks once the graph itself increments the counter.
 __global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t nwords, uint64_t seed, uint64_t offset,
-                                    uint32_t thresh16) {
+                                    uint32_t thresh16, const unsigned long long* __restrict__ epoch) {
   griddep_launch();
   griddep_wait();
   const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (w >= nwords) return;
+  if (epoch != nullptr) offset += static_cast<uint64_t>(*epoch) << 40;
   uint32_t gt = 0u, eq = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -1255,12 +1258,13 @@ int colsum(const void* X, int64_t ldx, float* out, int M, int N, cudaStream_t s)
   return launch_ok("colsum");
 }
 
-int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, cudaStream_t s) {
+int dropout_bits(uint32_t* out, int64_t nwords, uint64_t seed, uint64_t offset, float p, const uint64_t* epoch, cudaStream_t s) {
   if (nwords <= 0) return set_error(MMFB_ERR_ARG, "dropout_bits: empty");
   if (!(p >= 0.0f && p < 1.0f)) return set_error(MMFB_ERR_ARG, "dropout_bits: p must be in [0,1), got %f", p);
   uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
   if (thresh > 65535u) thresh = 65535u;          // 16 planes: p within 2^-16 of 1 keeps one element in 65536
-  MMFB_LAUNCH(dropout_bits_kernel, static_cast<unsigned>((nwords + 255) / 256), 256, 0, s, out, nwords, seed, offset, thresh);
+  MMFB_LAUNCH(dropout_bits_kernel, static_cast<unsigned>((nwords + 255) / 256), 256, 0, s, out, nwords, seed, offset, thresh,
+              reinterpret_cast<const unsigned long long*>(epoch));
   return launch_ok("dropout_bits");
 }
 

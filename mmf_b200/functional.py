@@ -217,12 +217,32 @@ def colsum(x, out):
     return out
 
 
+_DROPOUT_EPOCH = {}      # device index -> int64 [1] step counter in device memory (set by mmf_b200.graphs)
+
+
+def dropout_epoch(device, create=False):
+    """The device-resident step counter mixed into every keep-bit draw on `device` once it exists (None otherwise).
+    A CUDA-graph capture freezes the host-side (seed, offset) of each draw; the captured graph increments this counter,
+    so every replay still draws fresh masks (mmf_b200/graphs.py)."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _DROPOUT_EPOCH and create:
+        _DROPOUT_EPOCH[idx] = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+    return _DROPOUT_EPOCH.get(idx)
+
+
 def dropout_bits(shape_rows, ncols, p, seed, offset, device):
     """int32 keep-bit words [*shape_rows, ceil(ncols/32)] for nn.Dropout(p)."""
     words = (ncols + 31) // 32
     out = torch.empty(*shape_rows, words, dtype=torch.int32, device=device)
-    check(LIB.mmfb_dropout_bits(out.data_ptr(), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), float(p),
-                                _stream_ptr()))
+    epoch = dropout_epoch(out.device)
+    if epoch is None:
+        check(LIB.mmfb_dropout_bits(out.data_ptr(), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), float(p),
+                                    _stream_ptr()))
+    else:
+        check(LIB.mmfb_dropout_bits_epoch(out.data_ptr(), out.numel(), int(seed) & (2 ** 64 - 1), int(offset),
+                                          epoch.data_ptr(), float(p), _stream_ptr()))
     return out
 
 

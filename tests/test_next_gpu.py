@@ -266,3 +266,52 @@ def test_fused_masked_lm_loss_matches_the_materialised_head():
     errs = [abs(out["fused"][0] - out["all"][0]) / abs(out["all"][0])] + [rel(a, b) for a, b in zip(out["fused"][1:], out["all"][1:])]
     print("fused vs materialised MLM head: loss %.2e dseq %.2e dW_vocab %.2e dW_transform %.2e dbias %.2e" % tuple(errs))
     assert max(errs) < 1e-2
+
+
+def test_graphed_step_replays_the_eager_step_and_redraws_dropout():
+    """mmf_b200.graphs.GraphedStep: forward + backward captured as one CUDA graph.  Without dropout a replay reproduces the
+    eager loss and gradients bit for bit (same kernels, same order); with dropout every replay draws new masks through the
+    device-resident step counter (the host-side seeds are frozen at capture)."""
+    import types
+    from mmf_b200 import functional as F
+    from mmf_b200.graphs import GraphedStep
+    from mmf_b200.modules import B200BertEncoder
+    torch.manual_seed(0)
+
+    def build(p):
+        cfg = types.SimpleNamespace(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2,
+                                    hidden_dropout_prob=p, attention_probs_dropout_prob=p, layer_norm_eps=1e-12, hidden_act="gelu")
+        return B200BertEncoder(cfg).cuda().train()
+    B, S = 3, 40
+    x = torch.randn(B, S, 128, device="cuda")
+    mask = torch.zeros(B, 1, 1, S, device="cuda")
+    mask[1, ..., 30:] = -10000.0
+    w = torch.randn(B, S, 128, device="cuda")
+    loss_fn_of = lambda enc: (lambda b: (enc(b["x"], b["mask"])[0].float() * w).sum())
+    # --- no dropout: graph == eager ---
+    enc = build(0.0)
+    enc.zero_grad(set_to_none=True)
+    ref = loss_fn_of(enc)({"x": x, "mask": mask})
+    ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in enc.named_parameters()}
+    step = GraphedStep(enc, loss_fn_of(enc), {"x": x, "mask": mask})
+    for _ in range(2):
+        loss = step({"x": x, "mask": mask})
+    torch.cuda.synchronize()
+    assert torch.equal(loss, ref.detach())
+    for n, p in enc.named_parameters():
+        assert torch.equal(p.grad, ref_grads[n]), n
+    x2 = torch.randn_like(x)
+    enc.zero_grad(set_to_none=True)
+    ref2 = loss_fn_of(enc)({"x": x2, "mask": mask}).detach()
+    assert torch.equal(step({"x": x2, "mask": mask}), ref2)         # new inputs are copied into the static buffers
+    # --- dropout: replays differ, and the counter advances ---
+    enc = build(0.3)
+    step = GraphedStep(enc, loss_fn_of(enc), {"x": x, "mask": mask})
+    e0 = int(F.dropout_epoch("cuda").item())
+    l1 = step().clone()
+    l2 = step().clone()
+    torch.cuda.synchronize()
+    assert int(F.dropout_epoch("cuda").item()) == e0 + 2
+    assert l1.item() != l2.item() and torch.isfinite(l1) and torch.isfinite(l2)
+    F._DROPOUT_EPOCH.clear()          # later tests draw their masks from the host-side counters alone
