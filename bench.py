@@ -713,6 +713,8 @@ def main():
     ap.add_argument("--ddp-mode", default=os.environ.get("MMFB_DDP_MODE", "end"), choices=["end", "bucket"],
                     help="gradient exchange: one all-reduce per flat buffer after the backward, or bucket slices "
                          "overlapped with it (mmf_b200/ddp.py)")
+    ap.add_argument("--ddp-payload", default=os.environ.get("MMFB_DDP_PAYLOAD", "fp32"), choices=["fp32", "bf16"],
+                    help="dtype of the gradients on the wire (bf16: half the bytes, 2^-9 rounding of the averaged gradients)")
     ap.add_argument("--optimizer", action="store_true",
                     help="also time the step WITH the fused AdamW update (mmf_b200.optim.B200AdamW, BERT parameter groups); "
                          "reported as `with_optimizer`, the headline value stays forward + backward (BASELINE.json metric)")
@@ -773,8 +775,9 @@ def main():
     ddp = None
     if world > 1:
         from mmf_b200.ddp import B200DataParallel
-        ddp = B200DataParallel(model, mode=args.ddp_mode)
+        ddp = B200DataParallel(model, mode=args.ddp_mode, payload=args.ddp_payload)
         config["ddp_mode"] = args.ddp_mode
+        config["ddp_payload"] = args.ddp_payload
     net = ddp if ddp is not None else model
     host = _pin(wl.host_batch(B, 1234 + rank))
     dev_batch = to_device(host, dev)

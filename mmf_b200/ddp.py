@@ -34,10 +34,16 @@ def _runners(module):
 
 
 class B200DataParallel(nn.Module):
-    def __init__(self, module, process_group=None, bucket_bytes=64 << 20, overlap=True, mode=None):
+    def __init__(self, module, process_group=None, bucket_bytes=64 << 20, overlap=True, mode=None, payload=None):
+        """payload: "fp32" (default: the flat fp32 gradient buffer is reduced as it is, the reference's DDP semantics) or
+        "bf16" (the buffer is cast to bf16, reduced, and cast back: half the bytes on the wire for a 2^-9 relative rounding
+        of each averaged gradient - the trade torch's bf16_compress_hook makes; opt-in)."""
         super().__init__()
         import os
         self.mode = mode or os.environ.get("MMFB_DDP_MODE", "bucket")
+        self.payload = payload or os.environ.get("MMFB_DDP_PAYLOAD", "fp32")
+        if self.payload not in ("fp32", "bf16"):
+            raise ValueError("B200DataParallel payload must be 'fp32' or 'bf16', got %r" % (self.payload,))
         if self.mode not in ("bucket", "end"):
             raise ValueError("B200DataParallel mode must be 'bucket' or 'end', got %r" % (self.mode,))
         if not dist.is_initialized():
@@ -140,6 +146,14 @@ class B200DataParallel(nn.Module):
 
     def _avg(self, flat):
         """mean over ranks: NCCL reduces with AVG in one pass; gloo (CPU tests) has no AVG"""
+        if self.payload == "bf16" and flat.dtype == torch.float32 and flat.numel() >= (1 << 16):
+            wire = flat.to(torch.bfloat16)
+            self._avg_raw(wire)
+            flat.copy_(wire)
+            return
+        self._avg_raw(flat)
+
+    def _avg_raw(self, flat):
         if dist.get_backend(self.group) == "nccl":
             dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:

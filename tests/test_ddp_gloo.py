@@ -225,8 +225,9 @@ def test_data_parallel_tied_and_bf16_pack_world2():
     assert result.get(0) and result.get(1)
 
 
-def _end_mode_worker(rank, world, port, result):
-    """mode="end": hooks send nothing, the end-of-backward callback all-reduces each flat buffer once"""
+def _end_mode_worker(rank, world, port, result, payload="fp32"):
+    """mode="end": hooks send nothing, the end-of-backward callback all-reduces each flat buffer once
+    (payload "bf16": through a bf16 copy of the buffer - both ranks end with the same values, 2^-9 from the fp32 mean)"""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -243,7 +244,7 @@ def _end_mode_worker(rank, world, port, result):
                                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, layer_norm_eps=1e-12)
         torch.manual_seed(300 + rank)
         enc = M.B200BertEncoder(cfg).eval()
-        ddp = B200DataParallel(enc, mode="end", overlap=False)
+        ddp = B200DataParallel(enc, mode="end", overlap=False, payload=payload)
         calls = []
         orig = ddp._avg
         ddp._avg = lambda flat: (calls.append(flat.numel()), orig(flat))[1]
@@ -260,9 +261,15 @@ def _end_mode_worker(rank, world, port, result):
             (ref_enc(xs[r], None)[0] * ws[r]).sum().backward()
             cur = {k: p.grad.detach().clone() for k, p in ref_enc.named_parameters()}
             acc = cur if acc is None else {k: acc[k] + cur[k] for k in acc}
+        tol = 1e-3 if payload == "fp32" else 1e-2
         for k, p in enc.named_parameters():
             ref = acc[k] / world
-            assert (p.grad - ref).norm() / ref.norm().clamp_min(1e-3 * ref.numel() ** 0.5) < 1e-3, k
+            assert (p.grad - ref).norm() / ref.norm().clamp_min(1e-3 * ref.numel() ** 0.5) < tol, k
+        if payload == "bf16":      # every rank holds the SAME reduced values (replicas stay in lock-step)
+            flat = enc._runner.pack.grad.clone()
+            other = flat.clone()
+            dist.broadcast(other, src=0)
+            assert torch.equal(flat, other)
         result[rank] = True
     finally:
         dist.destroy_process_group()
@@ -273,4 +280,12 @@ def test_data_parallel_end_mode_world2():
     mgr = mp.Manager()
     result = mgr.dict()
     mp.spawn(_end_mode_worker, args=(2, port, result), nprocs=2, join=True)
+    assert result.get(0) and result.get(1)
+
+
+def test_data_parallel_bf16_payload_world2():
+    port = 37500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_end_mode_worker, args=(2, port, result, "bf16"), nprocs=2, join=True)
     assert result.get(0) and result.get(1)
