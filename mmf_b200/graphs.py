@@ -56,7 +56,10 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         model.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # captured on the warm-up stream: autograd binds every parameter's gradient accumulator to the stream that was current
+        # when the accumulator was created, i.e. this one, as long as no autograd graph from an earlier eager step on another
+        # stream is still alive (it would keep the old accumulators - and their stream - in use)
+        with torch.cuda.graph(self.graph, stream=side):
             self.epoch.add_(1)
             self.loss = loss_fn(self.static)
             self.loss.backward()

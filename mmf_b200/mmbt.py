@@ -137,8 +137,7 @@ def extract_modal_end_token(sample_list):
     ids, mask = sample_list["input_ids"], sample_list["input_mask"]
     last = mask.sum(dim=1) - 1                                   # index of the last attended token
     end_token = ids[torch.arange(ids.size(0), device=ids.device), last].clone()
-    sample_list["input_ids"] = torch.roll(ids, shifts=-1, dims=1).index_copy(
-        1, torch.tensor([ids.size(1) - 1], device=ids.device), ids[:, -1:])
+    sample_list["input_ids"] = torch.cat([ids[:, 1:], ids[:, -1:]], dim=1)     # shift left, the last id repeated
     shifted_mask = torch.roll(mask, shifts=-1, dims=1)
     shifted_mask[:, -1] = 0
     sample_list["input_mask"] = shifted_mask

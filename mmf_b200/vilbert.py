@@ -104,7 +104,7 @@ class B200ViLBERTBase(nn.Module):
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_txt)
         if image_attention_mask is None:
-            image_attention_mask = torch.ones(image_feature.size(0), image_feature.size(1)).type_as(input_txt)
+            image_attention_mask = torch.ones(image_feature.size(0), image_feature.size(1), dtype=input_txt.dtype, device=input_txt.device)
         dt = self.embeddings.LayerNorm.weight.dtype
         ext_t = (1.0 - attention_mask.unsqueeze(1).unsqueeze(2).to(dt)) * -10000.0          # vilbert.py:982-1003
         ext_v = (1.0 - image_attention_mask.unsqueeze(1).unsqueeze(2).to(dt)) * -10000.0

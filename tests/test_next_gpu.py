@@ -290,20 +290,22 @@ def test_graphed_step_replays_the_eager_step_and_redraws_dropout():
     loss_fn_of = lambda enc: (lambda b: (enc(b["x"], b["mask"])[0].float() * w).sum())
     # --- no dropout: graph == eager ---
     enc = build(0.0)
-    enc.zero_grad(set_to_none=True)
-    ref = loss_fn_of(enc)({"x": x, "mask": mask})
+    import copy
+    twin = copy.deepcopy(enc)            # the eager reference runs on a copy: no autograd graph of `enc` from another stream
+    ref = loss_fn_of(twin)({"x": x, "mask": mask})
     ref.backward()
-    ref_grads = {n: p.grad.clone() for n, p in enc.named_parameters()}
+    ref_grads = {n: p.grad.clone() for n, p in twin.named_parameters()}
+    ref = ref.detach()
     step = GraphedStep(enc, loss_fn_of(enc), {"x": x, "mask": mask})
     for _ in range(2):
         loss = step({"x": x, "mask": mask})
     torch.cuda.synchronize()
-    assert torch.equal(loss, ref.detach())
+    assert torch.equal(loss, ref)
     for n, p in enc.named_parameters():
         assert torch.equal(p.grad, ref_grads[n]), n
     x2 = torch.randn_like(x)
-    enc.zero_grad(set_to_none=True)
-    ref2 = loss_fn_of(enc)({"x": x2, "mask": mask}).detach()
+    with torch.no_grad():
+        ref2 = loss_fn_of(twin)({"x": x2, "mask": mask})
     assert torch.equal(step({"x": x2, "mask": mask}), ref2)         # new inputs are copied into the static buffers
     # --- dropout: replays differ, and the counter advances ---
     enc = build(0.3)

@@ -87,10 +87,12 @@ def test_one_cta_per_item_attention_backward_matches_the_default(Sq, Skv, drop, 
         assert (r != t).float().mean() < 0.01, (name, (r != t).float().mean().item())
 
 
+@pytest.mark.parametrize("variant", ["1", "2"])
 @pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (128, 256, False), (100, 36, True), (256, 17, False), (36, 130, True)])
-def test_one_cta_per_tile_attention_forward_matches_the_default(Sq, Skv, drop):
-    """MMFB_ATTN_FWD=1 (one CTA per 128-query tile, P through shared memory) against the default paired-tile persistent kernel
-    (K/V loaded once per (batch, head), P in tensor memory, ping-pong softmax groups): same arithmetic per element"""
+def test_other_attention_forwards_match_the_default(Sq, Skv, drop, variant):
+    """MMFB_ATTN_FWD=1 (one CTA per 128-query tile, P through shared memory) and =2 (paired tiles, scores of all 256 keys in one
+    region, two passes) against the default (paired tiles, two key blocks with their own statistics combined in the epilogue):
+    the same softmax, evaluated with a different split of the key range"""
     from mmf_b200 import functional as F
     torch.manual_seed(Sq + Skv)
     B, heads, d = 7, 3, 64
@@ -106,7 +108,7 @@ def test_one_cta_per_tile_attention_forward_matches_the_default(Sq, Skv, drop):
 
     def run(flag):
         if flag:
-            os.environ["MMFB_ATTN_FWD"] = "1"
+            os.environ["MMFB_ATTN_FWD"] = variant
         else:
             os.environ.pop("MMFB_ATTN_FWD", None)
         out = F.attention_fwd(q, k, v, B, heads, Sq, Skv, mask, bits, scale, save_lo=True)
