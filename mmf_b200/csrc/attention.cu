@@ -457,9 +457,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* p_ready = bars + 10;     // [2 tiles]
   uint64_t* o_ready = bars + 12;     // [2 tiles]
   uint64_t* o_read = bars + 14;      // [2 tiles]
-  uint64_t* o_staged = bars + 16;    // [2 tiles] 256 arrivals: the output tile is in shared memory
-  uint64_t* k_free = bars + 18;      // [2 stages] both tiles' score MMAs of the stage have completed: the K slots are free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  // [2 tiles][2 stages] 256 arrivals: the output tile is in shared memory.  Per STAGE: a group may run a whole item ahead of
+  // the other one, and the store warp serves the tiles in order - with one barrier per tile its phase could complete twice
+  // before the store warp looked at it once (seen as a rare hang under ragged padding); two items ahead is impossible, the
+  // ring stage is not refilled before the store warp has released it.
+  uint64_t* o_staged = bars + 16;
+  uint64_t* k_free = bars + 20;      // [2 stages] both tiles' score MMAs of the stage have completed: the K slots are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   uint32_t* sAct = tmem_slot + 1;    // [2 stages] bit c: 32-key chunk c has at least one key that is not masked out
   int* sItem = reinterpret_cast<int*>(sAct + 2);   // [2 stages] (batch, head) item of the stage, -1 = no more work
 
@@ -479,6 +483,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_init(&mask_full[s], 32);
         mbar_init(&stage_free[s], 2 * nt);
         mbar_init(&o_staged[s], 256);
+        mbar_init(&o_staged[2 + s], 256);
         mbar_init(&k_free[s], nt);
         mbar_init(&s_ready[s], 1);
         mbar_init(&p_ready[s], 256);
@@ -651,7 +656,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int h = it % p.H, b = it / p.H;
       uint8_t* stage_base = smem + (n & 1) * STAGE;
       for (int t = 0; t < nt; ++t) {
-        mbar_wait(&o_staged[t], n & 1);
+        mbar_wait(&o_staged[t * 2 + (n & 1)], (n >> 1) & 1);
         if (lane == 0) {
           tma_store_3d(&tmO, stage_base + t * TILE, h * D, t * 128, b);
           if (p.ctx_lo != nullptr) tma_store_3d(&tmOlo, stage_base + (2 + t) * TILE, h * D, t * 128, b);
@@ -790,7 +795,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (want_lo) *reinterpret_cast<uint4*>(lrow + chunk) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
           }
           fence_proxy_async();
-          mbar_arrive(&o_staged[t]);
+          mbar_arrive(&o_staged[t * 2 + (n & 1)]);
         }
         if (tr) MMFB_TR(t, n, 10);
       }
@@ -809,8 +814,40 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// One key block of one softmax thread: scores -> registers (once), block maximum (exchanged with the partner thread of the
+// row through shared memory), exponentials -> P_j in tensor memory.  Kept out of line: inlined next to the epilogue, ptxas
+// allocated the two phases together and spilled ~800 bytes per thread.
+__device__ __noinline__ void fwd_block_softmax(uint32_t tblk, int half, bool on0, bool on1, const float4* m4, float scale2,
+                                               float* gmax_mine, const float* gmax_a, const float* gmax_b, int bar_id,
+                                               uint32_t b0, uint32_t b1, float& m_out, float& l_out) {
+  uint32_t ra[32], rb[32];
+  if (on0) tmem_ld32(tblk + half * 64, ra);
+  if (on1) tmem_ld32(tblk + half * 64 + 32, rb);
+  tmem_ld_wait();
+  float mx = -INFINITY;
+  if (on0) fwd_chunk_max(ra, m4, scale2, mx);
+  if (on1) fwd_chunk_max(rb, m4 + 8, scale2, mx);
+  *gmax_mine = mx;
+  asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");     // every thread of the group holds its S columns
+  mx = fmaxf(*gmax_a, *gmax_b);
+  m_out = mx;
+  float sum = 0.0f;
+  uint32_t pk[16];
+  if (on0) {
+    fwd_chunk_exp(ra, m4, scale2, mx, b0, sum, pk);
+    tmem_st16(tblk + 64 + half * 32, pk);
+  }
+  if (on1) {
+    fwd_chunk_exp(rb, m4 + 8, scale2, mx, b1, sum, pk);
+    tmem_st16(tblk + 64 + half * 32 + 16, pk);
+  }
+  l_out = sum;
+  tmem_st_wait();
+  tc_fence_before();
+}
+
 // ----------------------------------------------------------------------------------------------
-// forward, paired tiles, key BLOCKS (the default for d = 64, Sq, Skv <= 256)
+// forward, paired tiles, key BLOCKS (MMFB_ATTN_FWD=b; an experiment that did NOT pay off, kept for A/B runs)
 //
 // Same CTA organisation as attn_fwd_pair_kernel (persistent, item counter, loader / MMA / store warps, two softmax groups),
 // but the 256 keys are two independent blocks of 128 with their own statistics, combined in the epilogue:
@@ -849,9 +886,9 @@ attn_fwd_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_ready = bars + 10;     // [2 tiles][2 blocks] 256 arrivals
   uint64_t* o_ready = bars + 14;     // [2 tiles][2 blocks]
   uint64_t* o_read = bars + 18;      // [2 tiles]
-  uint64_t* o_staged = bars + 20;    // [2 tiles] 256 arrivals: the output tile is in shared memory
-  uint64_t* k_free = bars + 22;      // [2 stages] both tiles' score MMAs of the stage have completed: the K slots are free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* o_staged = bars + 20;    // [2 tiles][2 stages] 256 arrivals: the output tile is in shared memory (per stage: see attn_fwd_pair_kernel)
+  uint64_t* k_free = bars + 24;      // [2 stages] both tiles' score MMAs of the stage have completed: the K slots are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   uint32_t* sAct = tmem_slot + 1;    // [2 stages] bit c: 32-key chunk c has at least one key that is not masked out
   int* sItem = reinterpret_cast<int*>(sAct + 2);   // [2 stages] (batch, head) item of the stage, -1 = no more work
 
@@ -870,6 +907,7 @@ attn_fwd_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_init(&mask_full[s], 32);
         mbar_init(&stage_free[s], 2 * nt);
         mbar_init(&o_staged[s], 256);
+        mbar_init(&o_staged[2 + s], 256);
         mbar_init(&k_free[s], nt);
         mbar_init(&s_ready[s], 1);
         mbar_init(&o_read[s], 256);
@@ -1049,7 +1087,7 @@ attn_fwd_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int h = it % p.H, b = it / p.H;
       uint8_t* stage_base = smem + (n & 1) * STAGE;
       for (int t = 0; t < nt; ++t) {
-        mbar_wait(&o_staged[t], n & 1);
+        mbar_wait(&o_staged[t * 2 + (n & 1)], (n >> 1) & 1);
         if (lane == 0) {
           tma_store_3d(&tmO, stage_base + t * TILE, h * D, t * 128, b);
           if (p.ctx_lo != nullptr) tma_store_3d(&tmOlo, stage_base + (2 + t) * TILE, h * D, t * 128, b);
@@ -1098,30 +1136,8 @@ attn_fwd_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               if (c + 1 < nch) b1 = __ldg(dm + c + 1);
             }
             const float4* m4 = reinterpret_cast<const float4*>(sMask + (n & 1) * 256 + j * 128 + half * 64);
-            uint32_t ra[32], rb[32];
-            if (on0) tmem_ld32(treg + j * BLK + half * 64, ra);
-            if (on1) tmem_ld32(treg + j * BLK + half * 64 + 32, rb);
-            tmem_ld_wait();
-            float mx = -INFINITY;
-            if (on0) fwd_chunk_max(ra, m4, p.scale2, mx);
-            if (on1) fwd_chunk_max(rb, m4 + 8, p.scale2, mx);
-            gMax[(j * 2 + half) * 128 + row] = mx;
-            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");     // every thread of the group holds its S columns
-            mx = fmaxf(gMax[(j * 2) * 128 + row], gMax[(j * 2 + 1) * 128 + row]);
-            m_out = mx;
-            float sum = 0.0f;
-            uint32_t pk[16];
-            if (on0) {
-              fwd_chunk_exp(ra, m4, p.scale2, mx, b0, sum, pk);
-              tmem_st16(treg + j * BLK + COL_P + half * 32, pk);
-            }
-            if (on1) {
-              fwd_chunk_exp(rb, m4 + 8, p.scale2, mx, b1, sum, pk);
-              tmem_st16(treg + j * BLK + COL_P + half * 32 + 16, pk);
-            }
-            l_out = sum;
-            tmem_st_wait();
-            tc_fence_before();
+            fwd_block_softmax(treg + j * BLK, half, on0, on1, m4, p.scale2, gMax + (j * 2 + half) * 128 + row,
+                              gMax + (j * 2) * 128 + row, gMax + (j * 2 + 1) * 128 + row, bar_id, b0, b1, m_out, l_out);
           }
           mbar_arrive(&p_ready[t * 2 + j]);
         };
@@ -1192,7 +1208,7 @@ attn_fwd_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (want_lo) *reinterpret_cast<uint4*>(lrow + chunk) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
           }
           fence_proxy_async();
-          mbar_arrive(&o_staged[t]);
+          mbar_arrive(&o_staged[t * 2 + (n & 1)]);
         }
         if (tr) MMFB_TR(t, n, 10);
       }
@@ -2167,10 +2183,11 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* kv_read = bars + 13;      // 512 arrivals, phase = key-block counter parity
   uint64_t* dq_read = bars + 14;      // 512 arrivals, phase = item parity
   uint64_t* sdp_read = bars + 15;     // 512 arrivals: S / dP of the pair are in registers, the score columns are free
-  uint64_t* kv_staged = bars + 16;    // 512 arrivals: dK_j / dV_j are in the K_j / V_j slots (phase = key-block counter)
-  uint64_t* dq_staged = bars + 17;    // 512 arrivals: dQ_i are in the P' buffer (phase = item parity)
-  uint64_t* stg_free = bars + 18;     // the dQ store has finished reading the P' buffer (phase = item parity)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* kv_staged = bars + 16;    // [2] 512 arrivals: dK_j / dV_j are in the K_j / V_j slots; alternating by key-block counter so
+                                      // that two read-outs may be outstanding before the store warp has looked at the first
+  uint64_t* dq_staged = bars + 18;    // 512 arrivals: dQ_i are in the P' buffer (phase = item parity)
+  uint64_t* stg_free = bars + 19;     // the dQ store has finished reading the P' buffer (phase = item parity)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   uint32_t* sAct = tmem_slot + 1;     // [2 buffers] bit c: 32-key chunk c has an attendable key
   int* sItem = reinterpret_cast<int*>(sAct + 2);    // [2 buffers] (batch, head) item, -1 = no more work; published by stat_full
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
@@ -2185,7 +2202,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int x = 0; x < 2; ++x) { mbar_init(&q_full[x], 1); mbar_init(&kv_full[x], 1); mbar_init(&stat_full[x], 32); }
       // K_j / V_j slots double as staging for dK_j / dV_j: released by the MMA thread's commit AND the store warp
       mbar_init(&tile_free[0], 2); mbar_init(&tile_free[1], 1); mbar_init(&tile_free[2], 1); mbar_init(&tile_free[3], 2);
-      mbar_init(sdp_read, 512); mbar_init(kv_staged, 512); mbar_init(dq_staged, 512); mbar_init(stg_free, 1);
+      mbar_init(sdp_read, 512); mbar_init(&kv_staged[0], 512); mbar_init(&kv_staged[1], 512); mbar_init(dq_staged, 512); mbar_init(stg_free, 1);
       mbar_init(s_ready, 1);
       mbar_init(p_ready, 512);
       mbar_init(acc_done, 1);
@@ -2372,7 +2389,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (it < 0) break;
       const int h = it % p.H, b = it / p.H;
       for (int j = 0; j < nj; ++j, ++kbs) {
-        mbar_wait(kv_staged, kbs & 1);
+        mbar_wait(&kv_staged[kbs & 1], (kbs >> 1) & 1);
         if (lane == 0) {
           tma_store_3d(&tmdK, sK + j * TILE, h * D, j * 128, b);
           tma_store_3d(&tmdV, sV + j * TILE, h * D, j * 128, b);
@@ -2397,7 +2414,7 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int quarter = warp & 3, c = warp >> 2;          // c: this thread's 32-column chunk of the key block
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint32_t g = 0, kb = 0;
+    uint32_t g = 0, kb = 0, ro = 0;       // pair, key-block and read-out counters over all items
     int h = 0, b = 0;
     // dK_j, dV_j (rows = keys of block j, 16 of the 64 columns of each per thread) -> K_j / V_j slots (their last readers, the
     // accumulations of the block's last pair, have completed) -> one bulk tensor store per tile by the store warp
@@ -2427,7 +2444,8 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         *reinterpret_cast<uint4*>(vrow + chunk) = o;
       }
       fence_proxy_async();
-      mbar_arrive(kv_staged);
+      mbar_arrive(&kv_staged[ro & 1]);
+      ++ro;
     };
     for (int n = 0;; ++n) {
       mbar_wait(&stat_full[n & 1], (n >> 1) & 1);
@@ -2687,7 +2705,9 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       if ((rc = make_tmap_3d(&tmO, a.ctx, W, a.Sq, a.B, a.ldo, a.ldo * a.Sq, 64, 128))) return rc;
       tmOlo = tmO;
       if (a.ctx_lo != nullptr && (rc = make_tmap_3d(&tmOlo, a.ctx_lo, W, a.Sq, a.B, W, static_cast<int64_t>(W) * a.Sq, 64, 128))) return rc;
-      if (f_env != nullptr && f_env[0] == '2') {           // the two-pass form (scores of all 256 keys in one region), for A/B runs
+      if (f_env == nullptr || f_env[0] != 'b') {
+        // default: scores of all 256 keys in one region, two passes (120 us per layer at the bench shape); MMFB_ATTN_FWD=b selects
+        // the key-block form below (one read of S, per-block statistics) - slower as measured: 218 us, ~900 bytes of spills
         MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, FWD_PAIR_THREADS, smem_p, stream, tmQ, tmK128, tmV128, tmO, tmOlo, p, n_pairs, sched);
       } else {
         const int smem_b = smem_p + 1024 * 4 + 256;
