@@ -814,418 +814,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
-// One key block of one softmax thread: scores -> registers (once), block maximum (exchanged with the partner thread of the
-// row through shared memory), exponentials -> P_j in tensor memory.  Kept out of line: inlined next to the epilogue, ptxas
-// allocated the two phases together and spilled ~800 bytes per thread.
-__device__ __noinline__ void fwd_block_softmax(uint32_t tblk, int half, bool on0, bool on1, const float4* m4, float scale2,
-                                               float* gmax_mine, const float* gmax_a, const float* gmax_b, int bar_id,
-                                               uint32_t b0, uint32_t b1, float& m_out, float& l_out) {
-  uint32_t ra[32], rb[32];
-  if (on0) tmem_ld32(tblk + half * 64, ra);
-  if (on1) tmem_ld32(tblk + half * 64 + 32, rb);
-  tmem_ld_wait();
-  float mx = -INFINITY;
-  if (on0) fwd_chunk_max(ra, m4, scale2, mx);
-  if (on1) fwd_chunk_max(rb, m4 + 8, scale2, mx);
-  *gmax_mine = mx;
-  asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");     // every thread of the group holds its S columns
-  mx = fmaxf(*gmax_a, *gmax_b);
-  m_out = mx;
-  float sum = 0.0f;
-  uint32_t pk[16];
-  if (on0) {
-    fwd_chunk_exp(ra, m4, scale2, mx, b0, sum, pk);
-    tmem_st16(tblk + 64 + half * 32, pk);
-  }
-  if (on1) {
-    fwd_chunk_exp(rb, m4 + 8, scale2, mx, b1, sum, pk);
-    tmem_st16(tblk + 64 + half * 32 + 16, pk);
-  }
-  l_out = sum;
-  tmem_st_wait();
-  tc_fence_before();
-}
-
-// ----------------------------------------------------------------------------------------------
-// forward, paired tiles, key BLOCKS (MMFB_ATTN_FWD=b; an experiment that did NOT pay off, kept for A/B runs)
-//
-// Same CTA organisation as attn_fwd_pair_kernel (persistent, item counter, loader / MMA / store warps, two softmax groups),
-// but the 256 keys are two independent blocks of 128 with their own statistics, combined in the epilogue:
-//     O = (O_0 2^(m_0 - m) + O_1 2^(m_1 - m)) / (l_0 2^(m_0 - m) + l_1 2^(m_1 - m)),   m = max(m_0, m_1)
-// Why (round-2 timeline of the two-pass form, profiles/r2_trace_fwd_tma_store.txt: ~13 k cycles per item, of which 2 k
-// waiting for S, 1.7 k in the row-maximum pass, 4.5 k in the exponential pass, 2.3 k waiting for all 14 PV steps):
-//   * a thread's 64 score columns of a block fit in registers: they are read from tensor memory ONCE (scale + mask applied
-//     once), the maximum and the exponentials are taken from registers - no second pass over S;
-//   * S_1 = Q K_1^T is computed while block 0 is in its softmax, O_0 = P_0 V_0 while block 1 is: the group waits for one
-//     8-step PV product at the end instead of a 14-step one;
-//   * a block whose keys are all masked out costs nothing but its (unused) score MMA.
-// Region map per tile and block (128 columns): S_j [0,128) -> O_j [0,64) | P_j [64,128)  (P / O are written only after the
-// group barrier that exchanges the row maxima, i.e. after every thread holds its S columns in registers).
-// ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FWD_PAIR_THREADS, 1)
-attn_fwd_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                    const __grid_constant__ CUtensorMap tmOlo, AttnFwdDev p, int n_pairs, int* sched) {
-  griddep_launch();
-  griddep_wait();
-  constexpr int D = 64;
-  constexpr int TILE = 16384;                        // [128 x 128 B]
-  constexpr int STAGE = 6 * TILE;                    // Q0 | Q1 | K0 K1 | V0 V1
-  constexpr uint32_t REG = 256, BLK = 128, COL_O = 0, COL_P = 64;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_align1024(smem_raw);
-  float* sMask = reinterpret_cast<float*>(smem + 2 * STAGE);      // [2 stages][256]
-  float* sMax = sMask + 512;                                      // [2 tiles][2 blocks][2 halves][128 rows]
-  float* sSum = sMax + 1024;                                      // [2 tiles][2 blocks][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 1024);
-  uint64_t* qk_full = bars;          // [2]
-  uint64_t* v_full = bars + 2;       // [2]
-  uint64_t* mask_full = bars + 4;    // [2]
-  uint64_t* stage_free = bars + 6;   // [2]  per tile: one commit of the MMA thread + one arrival of the store warp
-  uint64_t* s_ready = bars + 8;      // [2 tiles]  both blocks' scores
-  uint64_t* p_ready = bars + 10;     // [2 tiles][2 blocks] 256 arrivals
-  uint64_t* o_ready = bars + 14;     // [2 tiles][2 blocks]
-  uint64_t* o_read = bars + 18;      // [2 tiles]
-  uint64_t* o_staged = bars + 20;    // [2 tiles][2 stages] 256 arrivals: the output tile is in shared memory (per stage: see attn_fwd_pair_kernel)
-  uint64_t* k_free = bars + 24;      // [2 stages] both tiles' score MMAs of the stage have completed: the K slots are free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-  uint32_t* sAct = tmem_slot + 1;    // [2 stages] bit c: 32-key chunk c has at least one key that is not masked out
-  int* sItem = reinterpret_cast<int*>(sAct + 2);   // [2 stages] (batch, head) item of the stage, -1 = no more work
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = (p.Sq + 127) / 128;                 // query tiles per pair (1 or 2)
-  const int nkt = (p.Skv + 127) / 128;               // key tiles = key blocks (1 or 2)
-
-  if (warp == 17) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&qk_full[s], 1);
-        mbar_init(&v_full[s], 1);
-        mbar_init(&mask_full[s], 32);
-        mbar_init(&stage_free[s], 2 * nt);
-        mbar_init(&o_staged[s], 256);
-        mbar_init(&o_staged[2 + s], 256);
-        mbar_init(&k_free[s], nt);
-        mbar_init(&s_ready[s], 1);
-        mbar_init(&o_read[s], 256);
-        for (int j = 0; j < 2; ++j) {
-          mbar_init(&p_ready[s * 2 + j], 256);
-          mbar_init(&o_ready[s * 2 + j], 1);
-        }
-      }
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 17) {
-    // ------------------------------------ loader: TMA tiles + mask rows, two pairs ahead ------------------------------------
-    // Items are handed out by an atomic counter (sched[0]), not by a fixed stride: their cost varies with the padding of the
-    // sample (masked chunks are skipped), and with 13.5 items per CTA a static split leaves the slowest CTA ~10 % behind.
-    // The item of ring stage s travels with its mask row: sItem[s], sAct[s], sMask[s] are published by mask_full[s].
-    auto load_pair = [&](int n, int it) {  // lane 0: Q tiles + K into qk_full, V into v_full of ring stage n & 1
-      const int h = it % p.H, b = it / p.H;
-      const int s = n & 1;
-      uint8_t* st = smem + s * STAGE;
-      mbar_expect_tx(&qk_full[s], (nt + nkt) * TILE);
-      for (int t = 0; t < nt; ++t) tma_load_3d(st + t * TILE, &tmQ, &qk_full[s], h * D, t * 128, b);
-      for (int j = 0; j < nkt; ++j) tma_load_3d(st + (2 + j) * TILE, &tmK, &qk_full[s], h * D, j * 128, b);
-      mbar_expect_tx(&v_full[s], nkt * TILE);
-      for (int j = 0; j < nkt; ++j) tma_load_3d(st + (4 + j) * TILE, &tmV, &v_full[s], h * D, j * 128, b);
-    };
-    auto load_mask = [&](int n, int it) {  // whole warp: log2-domain additive mask, -inf on the padded key columns
-      float* dst = sMask + (n & 1) * 256;
-      // Chunks whose 32 keys are ALL masked out (additive -10000, or beyond Skv) contribute exp2(-14427 + ...) = 0 exactly:
-      // they are skipped in both softmax passes and in the P V contraction (identical results; a quarter of the chunks at
-      // the padding rates of the reference's text / region batches).  A sample without any attendable key keeps them all:
-      // its softmax is uniform over the masked keys (hf_layers.py:191-196 semantics).
-      uint32_t act = 0;
-      if (it >= 0) {
-        const int b = it / p.H;
-        float mv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = lane + 32 * j;
-          mv[j] = (i < p.Skv) ? (p.mask != nullptr ? p.mask[static_cast<int64_t>(b) * p.Skv + i] * LOG2E : 0.0f) : -INFINITY;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          dst[lane + 32 * j] = mv[j];
-          if (__any_sync(0xffffffffu, mv[j] > -5000.0f)) act |= 1u << j;
-        }
-        if (act == 0) act = (1u << ((p.Skv + 31) / 32)) - 1u;
-      }
-      if (lane == 0) { sAct[n & 1] = act; sItem[n & 1] = it; }
-      __syncwarp();
-      mbar_arrive(&mask_full[n & 1]);
-    };
-    for (int n = 0;; ++n) {
-      // ring stage n & 1 (tiles, mask row, item) is refilled once every MMA of the item that used it has completed
-      if (n >= 2) mbar_wait(&stage_free[n & 1], ((n - 2) >> 1) & 1);
-      int it = 0;
-      if (lane == 0) it = atomicAdd(sched, 1);
-      it = __shfl_sync(0xffffffffu, it, 0);
-      if (it >= n_pairs) it = -1;
-      if (lane == 0) MMFB_TR(3, n, 0);
-      if (lane == 0 && it >= 0) load_pair(n, it);
-      load_mask(n, it);
-      if (lane == 0) MMFB_TR(3, n, 1);
-      if (it < 0) break;
-    }
-  } else if (warp == 16) {
-    // ------------------------------------ MMA issue: one thread, both tiles, never blocked on one of them ------------------------------------
-    if (lane == 0) {
-      auto issue_s = [&](int n, int t) {   // S_j = Q_t K_j^T for every key block j
-        const uint32_t st = smem_u32(smem + (n & 1) * STAGE);
-        const uint32_t aQ = st + t * TILE;
-        const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
-        for (int j = 0; j < nkt; ++j) {
-          const uint32_t aK = st + (2 + j) * TILE;
-#pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk)
-            umma_bf16(tmem_base + t * REG + j * BLK, umma_desc_sw128(aQ + kk * 32, 16, 1024), umma_desc_sw128(aK + kk * 32, 16, 1024),
-                      idesc, kk > 0 ? 1u : 0u);
-        }
-        umma_commit(&s_ready[t]);
-        umma_commit(&k_free[n & 1]);
-      };
-      auto issue_o = [&](int n, int t, int j) {   // O_j = P_j V_j, A = P_j from tensor memory (8 columns per 16 keys)
-        const uint32_t aV = smem_u32(smem + (n & 1) * STAGE + (4 + j) * TILE);
-        const uint32_t idesc = umma_idesc_bf16(128, D, false, true);
-        const uint32_t act = sAct[n & 1];
-        const int ksteps = min(8, (p.Skv - j * 128 + 15) / 16);
-        bool first = true;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          if (!((act >> (j * 4 + (kk >> 1))) & 1u)) continue;        // P is exactly zero over this chunk
-          umma_bf16_ts(tmem_base + t * REG + j * BLK + COL_O, tmem_base + t * REG + j * BLK + COL_P + kk * 8,
-                       umma_desc_sw128(aV + kk * 2048, TILE, 1024), idesc, first ? 0u : 1u);
-          first = false;
-        }
-        umma_commit(&o_ready[t * 2 + j]);
-      };
-      // Per tile: S(n) -> [P_0 ready] O_0 -> [P_1 ready] O_1 -> [O copied out, item n+1 published] S(n+1) -> ...  The chains of
-      // the two tiles are independent; their barriers are PROBED (mbarrier.test_wait) in turn so that whichever softmax group
-      // gets there first is served first.  An idle probe round sleeps ~50 ns: a spinning warp would take issue slots from
-      // the softmax warps of its scheduler partition.
-      int pn[2] = {0, 0};                  // item index (per CTA) the tile is in
-      int ph[2] = {0, 0};                  // 0 / 1: O_0 / O_1 of item pn is next, 2: S of item pn + 1 is next, 3: done
-      int live = nt;
-      if (nt < 2) ph[1] = 3;
-      mbar_wait(&mask_full[0], 0);
-      if (sItem[0] < 0) live = 0;
-      else {
-        mbar_wait(&qk_full[0], 0);
-        tc_fence_after();
-        for (int t = 0; t < nt; ++t) issue_s(0, t);
-      }
-      uint32_t spins = 0;
-      long long t0 = 0;
-      while (live > 0) {
-        bool progressed = false;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int n = pn[t];
-          if (ph[t] == 0 || ph[t] == 1) {
-            const int j = ph[t];
-            if (mbar_test(&p_ready[t * 2 + j], n & 1) && mbar_test(&v_full[n & 1], (n >> 1) & 1)) {
-              tc_fence_after();
-              MMFB_TR(2, n, 4 * t + j);
-              issue_o(n, t, j);
-              if (j == nkt - 1) {
-                umma_commit(&stage_free[n & 1]);               // every MMA of this tile that reads the ring stage has been issued
-                ph[t] = 2;
-              } else {
-                ph[t] = 1;
-              }
-              progressed = true;
-            }
-          } else if (ph[t] == 2) {
-            if (mbar_test(&o_read[t], n & 1) && mbar_test(&mask_full[(n + 1) & 1], ((n + 1) >> 1) & 1)) {
-              if (sItem[(n + 1) & 1] < 0) {                    // no further item
-                ph[t] = 3;
-                --live;
-                progressed = true;
-              } else if (mbar_test(&qk_full[(n + 1) & 1], ((n + 1) >> 1) & 1)) {
-                tc_fence_after();
-                MMFB_TR(2, n, 4 * t + 2);
-                issue_s(n + 1, t);
-                pn[t] = n + 1;
-                ph[t] = 0;
-                progressed = true;
-              }
-            }
-          }
-        }
-        if (progressed) { spins = 0; t0 = 0; }
-        else {
-          __nanosleep(40);
-          if (((++spins) & 0xFFFFu) == 0) {                    // watchdog: a protocol bug traps instead of hanging the GPU
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000LL) { printf("mmfb: attention forward issue loop timeout (block %d)\n", (int)blockIdx.x); __trap(); }
-          }
-        }
-      }
-    }
-  } else if (warp == 18) {
-    // ------------------------------------ store warp: one bulk tensor store per output tile ------------------------------------
-    // rows beyond Sq are clipped by the tensor map ([B][Sq][heads * d]); the ring stage is released to the loader only after
-    // the stores have finished READING shared memory
-    for (int n = 0;; ++n) {
-      mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
-      const int it = sItem[n & 1];
-      if (it < 0) break;
-      const int h = it % p.H, b = it / p.H;
-      uint8_t* stage_base = smem + (n & 1) * STAGE;
-      for (int t = 0; t < nt; ++t) {
-        mbar_wait(&o_staged[t * 2 + (n & 1)], (n >> 1) & 1);
-        if (lane == 0) {
-          tma_store_3d(&tmO, stage_base + t * TILE, h * D, t * 128, b);
-          if (p.ctx_lo != nullptr) tma_store_3d(&tmOlo, stage_base + (2 + t) * TILE, h * D, t * 128, b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(&stage_free[n & 1]);
-        }
-        __syncwarp();
-      }
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes complete before the CTA exits
-  } else {
-    // ------------------------------------ softmax groups ------------------------------------
-    const int t = warp >> 3;                                  // tile / group
-    if (t < nt) {
-      const int quarter = warp & 3, half = (warp >> 2) & 1;
-      const int row = quarter * 32 + lane;
-      const uint32_t treg = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * REG;
-      const int nch = (p.Skv + 31) / 32;
-      float* gMax = sMax + t * 512;                           // [2 blocks][2 halves][128 rows]
-      float* gSum = sSum + t * 512;
-      const int bar_id = 1 + t;
-      for (int n = 0;; ++n) {
-        const bool tr = (threadIdx.x & 255) == 0;
-        if (tr) MMFB_TR(t, n, 0);
-        mbar_wait(&mask_full[n & 1], (n >> 1) & 1);
-        const int it = sItem[n & 1];
-        if (it < 0) break;
-        const int h = it % p.H, b = it / p.H;
-        const int q = t * 128 + row;
-        const bool valid = q < p.Sq;
-        const uint32_t act_all = sAct[n & 1];
-        mbar_wait(&s_ready[t], n & 1);
-        tc_fence_after();
-        if (tr) MMFB_TR(t, n, 1);
-        const uint32_t* dm = (p.dmask != nullptr && valid) ? p.dmask + (static_cast<int64_t>(b * p.H + h) * p.Sq + q) * p.W : nullptr;
-        // one key block: scores -> registers (once), block maximum, exponentials -> P_j in tensor memory; returns (m_j, l_j part)
-        auto block = [&](const int j, float& m_out, float& l_out) {
-          const uint32_t actb = (act_all >> (j * 4)) & 0xFu;              // this block's four chunks
-          const bool on0 = (actb >> (half * 2)) & 1u, on1 = (actb >> (half * 2 + 1)) & 1u;
-          if (actb != 0u) {                                               // (uniform over the group)
-            const int c = j * 4 + half * 2;
-            uint32_t b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;                  // keep-bit words of the two chunks
-            if (dm != nullptr) {
-              if (c < nch) b0 = __ldg(dm + c);
-              if (c + 1 < nch) b1 = __ldg(dm + c + 1);
-            }
-            const float4* m4 = reinterpret_cast<const float4*>(sMask + (n & 1) * 256 + j * 128 + half * 64);
-            fwd_block_softmax(treg + j * BLK, half, on0, on1, m4, p.scale2, gMax + (j * 2 + half) * 128 + row,
-                              gMax + (j * 2) * 128 + row, gMax + (j * 2 + 1) * 128 + row, bar_id, b0, b1, m_out, l_out);
-          }
-          mbar_arrive(&p_ready[t * 2 + j]);
-        };
-        float m0 = -INFINITY, m1 = -INFINITY, ls0 = 0.0f, ls1 = 0.0f;
-#pragma unroll 1
-        for (int j = 0; j < nkt; ++j) {      // one copy of the block code: two inlined copies cost ~2 KB of register spills
-          float mo = -INFINITY, lo = 0.0f;
-          block(j, mo, lo);
-          if (j == 0) { m0 = mo; ls0 = lo; } else { m1 = mo; ls1 = lo; }
-          if (tr) MMFB_TR(t, n, 2 + j);
-        }
-        // ---- combine the blocks: row sums across the two halves, common maximum ----
-        gSum[(0 * 2 + half) * 128 + row] = ls0;
-        gSum[(1 * 2 + half) * 128 + row] = ls1;
-        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-        const float l0 = gSum[0 * 128 + row] + gSum[1 * 128 + row], l1 = gSum[2 * 128 + row] + gSum[3 * 128 + row];
-        const float m = fmaxf(m0, m1);
-        const float a0s = (m0 == -INFINITY) ? 0.0f : ex2_approx(m0 - m), a1s = (m1 == -INFINITY) ? 0.0f : ex2_approx(m1 - m);
-        const float l = l0 * a0s + l1 * a1s;
-        const float inv = p.dscale / l;
-        const float w0 = a0s * inv, w1 = a1s * inv;
-        const bool blk0 = (act_all & 0xFu) != 0u, blk1 = nkt > 1 && ((act_all >> 4) & 0xFu) != 0u;
-        // ---- O = O_0 w_0 + O_1 w_1: 32 of the 64 columns per thread ----
-        float acc[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
-        if (blk0) {
-          uint32_t r[32];
-          mbar_wait(&o_ready[t * 2 + 0], n & 1);
-          tc_fence_after();
-          tmem_ld32(treg + 0 * BLK + COL_O + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(r[e]) * w0;
-        }
-        if (tr) MMFB_TR(t, n, 8);
-        if (blk1) {
-          uint32_t r[32];
-          mbar_wait(&o_ready[t * 2 + 1], n & 1);
-          tc_fence_after();
-          tmem_ld32(treg + 1 * BLK + COL_O + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = fmaf(__uint_as_float(r[e]), w1, acc[e]);
-        }
-        tc_fence_before();
-        mbar_arrive(&o_read[t]);
-        if (tr) MMFB_TR(t, n, 9);
-        {
-          if (valid && half == 0) p.lse2[static_cast<int64_t>(b * p.H + h) * p.Sq + q] = m + log2f(l);
-          uint8_t* stage_base = smem + (n & 1) * STAGE;
-          uint8_t* orow = stage_base + t * TILE + row * 128;            // the Q_t slot: free since S_t completed
-          uint8_t* lrow = stage_base + (2 + t) * TILE + row * 128;      // the K_t slot: free once BOTH tiles' S completed
-          const bool want_lo = p.ctx_lo != nullptr;
-          if (want_lo) mbar_wait(&k_free[n & 1], (n >> 1) & 1);
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t wh[4], wl[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float o0 = acc[qd * 8 + 2 * e], o1 = acc[qd * 8 + 2 * e + 1];
-              wh[e] = pack_bf16x2(o0, o1);
-              const float2 hi = unpack_bf16x2(wh[e]);
-              wl[e] = pack_bf16x2(o0 - hi.x, o1 - hi.y);
-            }
-            const int chunk = ((half * 4 + qd) ^ (row & 7)) * 16;
-            *reinterpret_cast<uint4*>(orow + chunk) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-            if (want_lo) *reinterpret_cast<uint4*>(lrow + chunk) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-          }
-          fence_proxy_async();
-          mbar_arrive(&o_staged[t * 2 + (n & 1)]);
-        }
-        if (tr) MMFB_TR(t, n, 10);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-  // the last CTA to finish re-arms the item counter for the next launch (launches of one stream are serialised)
-  if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-    atomicExch(sched, 0);
-    atomicExch(sched + 1, 0);
-  }
-}
+// (Measured and removed in round 2: a key-BLOCK form of the paired kernel - two blocks of 128 keys with their own statistics,
+// each thread's 64 score columns read from tensor memory once and kept in registers, combined in the epilogue.  At 96
+// registers per thread ptxas spilled 0.5-0.9 KB per thread whichever way the block code was arranged (inlined, looped,
+// out of line), and the kernel ran at 255 us against 112 us for the two-pass form above; profiles/r2_trace_fwd_key_blocks.txt.)
 
 // ----------------------------------------------------------------------------------------------
 // backward
@@ -2705,22 +2297,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
       if ((rc = make_tmap_3d(&tmO, a.ctx, W, a.Sq, a.B, a.ldo, a.ldo * a.Sq, 64, 128))) return rc;
       tmOlo = tmO;
       if (a.ctx_lo != nullptr && (rc = make_tmap_3d(&tmOlo, a.ctx_lo, W, a.Sq, a.B, W, static_cast<int64_t>(W) * a.Sq, 64, 128))) return rc;
-      if (f_env == nullptr || f_env[0] != 'b') {
-        // default: scores of all 256 keys in one region, two passes (120 us per layer at the bench shape); MMFB_ATTN_FWD=b selects
-        // the key-block form below (one read of S, per-block statistics) - slower as measured: 218 us, ~900 bytes of spills
-        MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, FWD_PAIR_THREADS, smem_p, stream, tmQ, tmK128, tmV128, tmO, tmOlo, p, n_pairs, sched);
-      } else {
-        const int smem_b = smem_p + 1024 * 4 + 256;
-        static bool attr_b = false;
-        if (!attr_b) {
-          cudaError_t e3 = cudaFuncSetAttribute(attn_fwd_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
-          if (e3 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd_blk smem attr (%d B): %s", smem_b, cudaGetErrorString(e3));
-          attr_b = true;
-        }
-        MMFB_LAUNCH(attn_fwd_blk_kernel, grid_p, FWD_PAIR_THREADS, smem_b, stream, tmQ, tmK128, tmV128, tmO, tmOlo, p, n_pairs, sched);
-      }
-      cudaError_t e2 = cudaGetLastError();
-      if (e2 != cudaSuccess) return set_error(MMFB_ERR_CUDA, "attn_fwd_pair launch: %s", cudaGetErrorString(e2));
+      MMFB_LAUNCH(attn_fwd_pair_kernel, grid_p, FWD_PAIR_THREADS, smem_p, stream, tmQ, tmK128, tmV128, tmO, tmOlo, p, n_pairs, sched);
       count_launch();
       return MMFB_OK;
     }

@@ -98,6 +98,35 @@ def test_attention_many_items_per_cta(B, heads, Sq, Skv, p_drop):
     assert max(errs.values()) < 1e-2
 
 
+def test_attention_repeated_launches_are_identical_under_ragged_padding():
+    """Race / hang regression for the persistent kernels (work counter, ring stages, staged-output barriers): 25 forward +
+    backward launches over 1152 items with ragged key padding, the kind of input under which one softmax group gets a whole
+    item ahead of the other.  Every repetition must reproduce the first one bit for bit, and none may trap."""
+    from mmf_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, heads, S, d = 96, 12, 228, 64
+    W = heads * d
+    qkv = (torch.randn(B * S, 3 * W, generator=g, device="cuda") * 0.8).to(torch.bfloat16)
+    q, k, v = qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:]
+    lens = torch.randint(20, S + 1, (B,), generator=g, device="cuda")
+    add = ((torch.arange(S, device="cuda")[None, :] >= lens[:, None]).float() * -10000.0).contiguous()
+    bits = F.dropout_bits((B, heads, S), S, 0.1, 3, 0, "cuda")
+    dctx = torch.randn(B * S, W, generator=g, device="cuda").to(torch.bfloat16)
+    first = None
+    for rep in range(25):
+        ctx, lse2, lo = F.attention_fwd(q, k, v, B, heads, S, S, mask=add, drop_mask=bits, drop_scale=1 / 0.9, save_lo=True)
+        dq, dk, dv = F.attention_bwd(dctx, q, k, v, ctx, lse2, B, heads, S, S, mask=add, drop_mask=bits, drop_scale=1 / 0.9,
+                                     ctx_lo=lo)
+        torch.cuda.synchronize()
+        cur = [ctx, lse2, lo, dq, dk, dv]
+        if first is None:
+            first = [t.clone() for t in cur]
+            assert all(torch.isfinite(t.float()).all() for t in cur)
+        else:
+            for name, a, b in zip(("ctx", "lse2", "ctx_lo", "dq", "dk", "dv"), first, cur):
+                assert torch.equal(a, b), (name, rep)
+
+
 def test_attention_limits_raise():
     from mmf_b200 import functional as F
     q = torch.zeros(500, 64, device="cuda", dtype=torch.bfloat16)

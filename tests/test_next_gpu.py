@@ -270,7 +270,7 @@ def test_fused_masked_lm_loss_matches_the_materialised_head():
 
 def test_graphed_step_replays_the_eager_step_and_redraws_dropout():
     """mmf_b200.graphs.GraphedStep: forward + backward captured as one CUDA graph.  Without dropout a replay reproduces the
-    eager loss and gradients bit for bit (same kernels, same order); with dropout every replay draws new masks through the
+    eager loss bit for bit and the gradients to fp32 summation order (same kernels, same order); with dropout every replay draws new masks through the
     device-resident step counter (the host-side seeds are frozen at capture)."""
     import types
     from mmf_b200 import functional as F
@@ -301,8 +301,8 @@ def test_graphed_step_replays_the_eager_step_and_redraws_dropout():
         loss = step({"x": x, "mask": mask})
     torch.cuda.synchronize()
     assert torch.equal(loss, ref)
-    for n, p in enc.named_parameters():
-        assert torch.equal(p.grad, ref_grads[n]), n
+    for n, p in enc.named_parameters():      # column sums (bias / LayerNorm gradients) are fp32 atomics: same values, free order
+        assert (p.grad - ref_grads[n]).abs().max() <= 1e-5 * ref_grads[n].abs().max().clamp_min(1.0), n
     x2 = torch.randn_like(x)
     with torch.no_grad():
         ref2 = loss_fn_of(twin)({"x": x2, "mask": mask})

@@ -87,12 +87,11 @@ def test_one_cta_per_item_attention_backward_matches_the_default(Sq, Skv, drop, 
         assert (r != t).float().mean() < 0.01, (name, (r != t).float().mean().item())
 
 
-@pytest.mark.parametrize("variant", ["1", "b"])
+@pytest.mark.parametrize("variant", ["1"])
 @pytest.mark.parametrize("Sq,Skv,drop", [(228, 228, True), (128, 256, False), (100, 36, True), (256, 17, False), (36, 130, True)])
 def test_other_attention_forwards_match_the_default(Sq, Skv, drop, variant):
-    """MMFB_ATTN_FWD=1 (one CTA per 128-query tile, P through shared memory) and =b (paired tiles, two key blocks with their
-    own statistics combined in the epilogue) against the default (paired tiles, scores of all 256 keys in one region, two
-    passes): the same softmax, evaluated with a different split of the key range"""
+    """MMFB_ATTN_FWD=1 (one CTA per 128-query tile, P through shared memory) against the default (paired tiles, persistent,
+    P in tensor memory, outputs through bulk tensor stores): the same arithmetic per element"""
     from mmf_b200 import functional as F
     torch.manual_seed(Sq + Skv)
     B, heads, d = 7, 3, 64

@@ -105,7 +105,7 @@ def main():
         f_fwd, f_bwd = 4.0 * B * heads * S * S * d, 10.0 * B * heads * S * S * d
         b_fwd = M * 3 * H * 2 + M * H * 2 + M * H * 4 + bits.numel() * 4
         b_bwd = M * 3 * H * 2 * 2 + M * H * 2 + bits.numel() * 4
-        for tag, env in (("default paired tiles", {}), ("MMFB_ATTN_FWD=b", {"MMFB_ATTN_FWD": "b"}), ("MMFB_ATTN_FWD=1", {"MMFB_ATTN_FWD": "1"})):
+        for tag, env in (("default paired tiles", {}), ("MMFB_ATTN_FWD=1", {"MMFB_ATTN_FWD": "1"})):
             timeit("attention_fwd [%s]" % tag, lambda: F.attention_fwd(q, k, v, B, heads, S, S, mask, bits, 1 / 0.9, save_lo=True),
                    f_fwd, b_fwd, env)
         ctx, lse2, c32 = F.attention_fwd(q, k, v, B, heads, S, S, mask, bits, 1 / 0.9, save_lo=True)
