@@ -323,11 +323,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(&auxfull[set * 2 + (gslice & 1)], (gslice >> 1) & 1);
             auxrow = auxs + (set * 2 + (gslice & 1)) * STG_BYTES + row * 128;
           }
+          // both 32-column halves of the slice are requested up front: the second load is in flight while the first half
+          // goes through the fused math (the epilogue warps - two per scheduler partition - were stalled on this wait)
+#ifndef MMFB_EPI_PREFETCH
+#define MMFB_EPI_PREFETCH 1
+#endif
+          uint32_t rr[2][32];
+          tmem_ld32(t_row + sl * 64, rr[0]);
+          tmem_ld_wait();
+          if (MMFB_EPI_PREFETCH) tmem_ld32(t_row + sl * 64 + 32, rr[1]);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t r[32];
-            tmem_ld32(t_row + sl * 64 + h * 32, r);
-            tmem_ld_wait();
+            uint32_t (&r)[32] = rr[h];
+            if (h == 1) {
+              if (!MMFB_EPI_PREFETCH) tmem_ld32(t_row + sl * 64 + 32, rr[1]);
+              tmem_ld_wait();
+            }
             if (sl + 2 >= NSL && h == 1) {
               // this thread has drained its share of the accumulator: hand the TMEM stage back to the MMA warp
               tc_fence_before();
