@@ -387,9 +387,11 @@ __device__ __forceinline__ void fwd_chunk_max(const uint32_t (&r)[32], const flo
   }
 #endif
 }
-// exp2(s*scale2 + mask - mx) of one 32-column chunk -> 16 packed bf16 pairs (dropout applied), row sum accumulated
+// exp2(s*scale2 + mask - mx) of one 32-column chunk -> 16 packed bf16 pairs (dropout applied), row sum accumulated.
+// Dropout: the packed pair is ANDed with a mask looked up per 8 keep-bits in `keep_lut` ([256][4] words, 0xFFFF per kept
+// half) - half an instruction per element instead of a shift / test / select each.
 __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const float4* m4, float scale2, float mx,
-                                              uint32_t bits, float& sum, uint32_t (&pk)[16]) {
+                                              uint32_t bits, float& sum, uint32_t (&pk)[16], const uint32_t* keep_lut) {
 #if MMFB_F32X2
   const uint64_t sc2 = pk2(scale2, scale2), nmx2 = pk2(-mx, -mx);
   uint64_t sum2 = pk2(sum, 0.0f);
@@ -412,8 +414,13 @@ __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const flo
       sum += e0;
       sum += e1;
 #endif
-      pk[j >> 1] = pack_bf16x2(((bits >> j) & 1u) ? e0 : 0.0f, ((bits >> (j + 1)) & 1u) ? e1 : 0.0f);
+      pk[j >> 1] = pack_bf16x2(e0, e1);
     }
+  }
+#pragma unroll
+  for (int by = 0; by < 4; ++by) {
+    const uint4 kk = *reinterpret_cast<const uint4*>(keep_lut + ((bits >> (8 * by)) & 0xFFu) * 4);
+    pk[by * 4 + 0] &= kk.x; pk[by * 4 + 1] &= kk.y; pk[by * 4 + 2] &= kk.z; pk[by * 4 + 3] &= kk.w;
   }
 #if MMFB_F32X2
   float s0, s1;
@@ -448,7 +455,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* sMask = reinterpret_cast<float*>(smem + 2 * STAGE);      // [2 stages][256]
   float* sMax = sMask + 512;                                      // [2 tiles][2 halves][128 rows]
   float* sSum = sMax + 512;                                       // [2 tiles][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 512);
+  uint32_t* sKeep = reinterpret_cast<uint32_t*>(sSum + 512);      // [256][4] pair masks of 8 keep-bits (fwd_chunk_exp)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKeep + 1024);
   uint64_t* qk_full = bars;          // [2]
   uint64_t* v_full = bars + 2;       // [2]
   uint64_t* mask_full = bars + 4;    // [2]
@@ -472,6 +480,10 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int nkt = (p.Skv + 127) / 128;               // key tiles (1 or 2)
   const int SKP = nkt * 128;                         // padded key count: N of the score MMA
 
+  for (int e = threadIdx.x; e < 1024; e += FWD_PAIR_THREADS) {
+    const uint32_t bb = e >> 2, kk = e & 3;
+    sKeep[e] = (((bb >> (2 * kk)) & 1u) ? 0x0000ffffu : 0u) | (((bb >> (2 * kk + 1)) & 1u) ? 0xffff0000u : 0u);
+  }
   if (warp == 17) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
@@ -733,23 +745,23 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float sum = 0.0f;
         uint32_t pk[16];
         if (on3) {
-          fwd_chunk_exp(rb, m4 + 24, p.scale2, mx, bits[3], sum, pk);
+          fwd_chunk_exp(rb, m4 + 24, p.scale2, mx, bits[3], sum, pk, sKeep);
           tmem_st16(treg + pcol + 48, pk);
         }
         if (on1) tmem_ld32(treg + (c0 + 1) * 32, rb);
         if (on2) {
-          fwd_chunk_exp(ra, m4 + 16, p.scale2, mx, bits[2], sum, pk);
+          fwd_chunk_exp(ra, m4 + 16, p.scale2, mx, bits[2], sum, pk, sKeep);
           tmem_st16(treg + pcol + 32, pk);
         }
         tmem_ld_wait();
         if (on0) tmem_ld32(treg + (c0 + 0) * 32, ra);
         if (on1) {
-          fwd_chunk_exp(rb, m4 + 8, p.scale2, mx, bits[1], sum, pk);
+          fwd_chunk_exp(rb, m4 + 8, p.scale2, mx, bits[1], sum, pk, sKeep);
           tmem_st16(treg + pcol + 16, pk);
         }
         tmem_ld_wait();
         if (on0) {
-          fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk);
+          fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk, sKeep);
           tmem_st16(treg + pcol + 0, pk);
         }
         gSum[half * 128 + row] = sum;
@@ -1764,7 +1776,10 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sP = sV + 2 * TILE;        // [128 q x 128 kv] bf16 = 2 chunks of [128 x 128B]
   uint8_t* sDS = sP + 2 * TILE;
   float* sStat = reinterpret_cast<float*>(sDS + 2 * TILE);   // [2 buffers][lse 256 | delta 256 | mask 256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 768);
+  // keep-factor masks: entry b (8 keep-bits) -> eight words, all ones where the bit is set: kf = dscale & mask replaces a
+  // shift / test / select per element of the exp / dS arithmetic
+  uint32_t* sKf = reinterpret_cast<uint32_t*>(sStat + 2 * 768);         // [256][8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKf + 256 * 8);
   uint64_t* q_full = bars;            // [2]  Q_i + dO_i          (phase = item parity)
   uint64_t* kv_full = bars + 2;       // [2]  K_j + V_j           (phase = item parity)
   uint64_t* tile_free = bars + 4;     // [4]  K0V0 | Q0dO0 | Q1dO1 | K1V1: last reader of this item has completed
@@ -1788,6 +1803,8 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int ni = (p.Sq + 127) / 128, nj = (p.Skv + 127) / 128;
   const int np = ni * nj;
 
+  if (DROP)
+    for (int e = threadIdx.x; e < 256 * 8; e += BWD_PERS_THREADS) sKf[e] = (((e >> 3) >> (e & 7)) & 1) ? 0xFFFFFFFFu : 0u;
   if (warp == 17) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -2084,6 +2101,17 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               mbar_arrive(sdp_read);
             }
             const uint64_t sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-l2, -l2), ndl2 = pk2(-dl, -dl);
+            uint32_t km[16];
+            if (DROP) {
+              const uint32_t dsb = __float_as_uint(p.dscale);
+              const uint4* L0 = reinterpret_cast<const uint4*>(sKf + ((bits >> (16 * hh)) & 0xFFu) * 8);
+              const uint4* L1 = reinterpret_cast<const uint4*>(sKf + ((bits >> (16 * hh + 8)) & 0xFFu) * 8);
+              const uint4 k0 = L0[0], k1 = L0[1], k2 = L1[0], k3 = L1[1];
+              km[0] = k0.x & dsb; km[1] = k0.y & dsb; km[2] = k0.z & dsb; km[3] = k0.w & dsb;
+              km[4] = k1.x & dsb; km[5] = k1.y & dsb; km[6] = k1.z & dsb; km[7] = k1.w & dsb;
+              km[8] = k2.x & dsb; km[9] = k2.y & dsb; km[10] = k2.z & dsb; km[11] = k2.w & dsb;
+              km[12] = k3.x & dsb; km[13] = k3.y & dsb; km[14] = k3.z & dsb; km[15] = k3.w & dsb;
+            }
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const float4 m = m4[hh * 4 + q4];
@@ -2091,13 +2119,12 @@ attn_bwd_pers_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
               for (int k = 0; k < 4; k += 2) {
                 const int jx = q4 * 4 + k;                    // column inside the 16-column half
-                const int bx = hh * 16 + jx;                  // bit index inside the 32-column chunk
                 float ds0, ds1, pv0, pv1, a0, a1;
                 upk2(add2(fma2(pk2(__uint_as_float(rs[jx]), __uint_as_float(rs[jx + 1])), sc2, pk2(mm[k], mm[k + 1])), nl2), a0, a1);
                 const uint64_t pr = pk2(ex2_approx(a0), ex2_approx(a1));
                 const uint64_t dp = pk2(__uint_as_float(rd[jx]), __uint_as_float(rd[jx + 1]));
                 if (DROP) {
-                  const uint64_t kf = pk2(((bits >> bx) & 1u) ? p.dscale : 0.0f, ((bits >> (bx + 1)) & 1u) ? p.dscale : 0.0f);
+                  const uint64_t kf = pk2(__uint_as_float(km[jx]), __uint_as_float(km[jx + 1]));
                   upk2(mul2(pr, fma2(dp, kf, ndl2)), ds0, ds1);
                   upk2(mul2(pr, kf), pv0, pv1);
                 } else {
@@ -2282,7 +2309,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     // one-CTA-per-tile kernel below for A/B runs
     const char* f_env = getenv("MMFB_ATTN_FWD");
     if (f_env == nullptr || f_env[0] != '1') {
-      const int smem_p = 2 * 6 * 16384 + (512 + 512 + 512) * 4 + 256 + 1024;
+      const int smem_p = 2 * 6 * 16384 + (512 + 512 + 512) * 4 + 4096 + 256 + 1024;
       static bool attr_p = false;
       if (!attr_p) {
         cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
@@ -2383,7 +2410,7 @@ static int attn_bwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     if (w_env == nullptr || w_env[0] == 'p') {
       // default: the persistent kernel (one CTA per SM over its share of the (batch, head) items); MMFB_ATTN_BWD=16 / 8
       // (read per call) select the one-CTA-per-item kernels for A/B runs
-      const int smem_p = 12 * 16384 + 2 * 768 * 4 + 256 + 1024;
+      const int smem_p = 12 * 16384 + 2 * 768 * 4 + 256 * 8 * 4 + 256 + 1024;
       static bool pers_attr = false;
       if (!pers_attr) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
