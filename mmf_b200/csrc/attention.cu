@@ -387,11 +387,11 @@ __device__ __forceinline__ void fwd_chunk_max(const uint32_t (&r)[32], const flo
   }
 #endif
 }
-// exp2(s*scale2 + mask - mx) of one 32-column chunk -> 16 packed bf16 pairs (dropout applied), row sum accumulated.
-// Dropout: the packed pair is ANDed with a mask looked up per 8 keep-bits in `keep_lut` ([256][4] words, 0xFFFF per kept
-// half) - half an instruction per element instead of a shift / test / select each.
+// exp2(s*scale2 + mask - mx) of one 32-column chunk -> 16 packed bf16 pairs (dropout applied), row sum accumulated
+// (measured and dropped: dropout as an AND of the packed pair with a mask looked up per 8 keep-bits, as the LayerNorm
+//  backward does - 115 us against 111.5 us for the bit tests below: the look-ups queue behind the mask-row loads)
 __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const float4* m4, float scale2, float mx,
-                                              uint32_t bits, float& sum, uint32_t (&pk)[16], const uint32_t* keep_lut) {
+                                              uint32_t bits, float& sum, uint32_t (&pk)[16]) {
 #if MMFB_F32X2
   const uint64_t sc2 = pk2(scale2, scale2), nmx2 = pk2(-mx, -mx);
   uint64_t sum2 = pk2(sum, 0.0f);
@@ -414,13 +414,8 @@ __device__ __forceinline__ void fwd_chunk_exp(const uint32_t (&r)[32], const flo
       sum += e0;
       sum += e1;
 #endif
-      pk[j >> 1] = pack_bf16x2(e0, e1);
+      pk[j >> 1] = pack_bf16x2(((bits >> j) & 1u) ? e0 : 0.0f, ((bits >> (j + 1)) & 1u) ? e1 : 0.0f);
     }
-  }
-#pragma unroll
-  for (int by = 0; by < 4; ++by) {
-    const uint4 kk = *reinterpret_cast<const uint4*>(keep_lut + ((bits >> (8 * by)) & 0xFFu) * 4);
-    pk[by * 4 + 0] &= kk.x; pk[by * 4 + 1] &= kk.y; pk[by * 4 + 2] &= kk.z; pk[by * 4 + 3] &= kk.w;
   }
 #if MMFB_F32X2
   float s0, s1;
@@ -455,8 +450,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* sMask = reinterpret_cast<float*>(smem + 2 * STAGE);      // [2 stages][256]
   float* sMax = sMask + 512;                                      // [2 tiles][2 halves][128 rows]
   float* sSum = sMax + 512;                                       // [2 tiles][2 halves][128 rows]
-  uint32_t* sKeep = reinterpret_cast<uint32_t*>(sSum + 512);      // [256][4] pair masks of 8 keep-bits (fwd_chunk_exp)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKeep + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 512);
   uint64_t* qk_full = bars;          // [2]
   uint64_t* v_full = bars + 2;       // [2]
   uint64_t* mask_full = bars + 4;    // [2]
@@ -480,10 +474,6 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int nkt = (p.Skv + 127) / 128;               // key tiles (1 or 2)
   const int SKP = nkt * 128;                         // padded key count: N of the score MMA
 
-  for (int e = threadIdx.x; e < 1024; e += FWD_PAIR_THREADS) {
-    const uint32_t bb = e >> 2, kk = e & 3;
-    sKeep[e] = (((bb >> (2 * kk)) & 1u) ? 0x0000ffffu : 0u) | (((bb >> (2 * kk + 1)) & 1u) ? 0xffff0000u : 0u);
-  }
   if (warp == 17) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
@@ -745,23 +735,23 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float sum = 0.0f;
         uint32_t pk[16];
         if (on3) {
-          fwd_chunk_exp(rb, m4 + 24, p.scale2, mx, bits[3], sum, pk, sKeep);
+          fwd_chunk_exp(rb, m4 + 24, p.scale2, mx, bits[3], sum, pk);
           tmem_st16(treg + pcol + 48, pk);
         }
         if (on1) tmem_ld32(treg + (c0 + 1) * 32, rb);
         if (on2) {
-          fwd_chunk_exp(ra, m4 + 16, p.scale2, mx, bits[2], sum, pk, sKeep);
+          fwd_chunk_exp(ra, m4 + 16, p.scale2, mx, bits[2], sum, pk);
           tmem_st16(treg + pcol + 32, pk);
         }
         tmem_ld_wait();
         if (on0) tmem_ld32(treg + (c0 + 0) * 32, ra);
         if (on1) {
-          fwd_chunk_exp(rb, m4 + 8, p.scale2, mx, bits[1], sum, pk, sKeep);
+          fwd_chunk_exp(rb, m4 + 8, p.scale2, mx, bits[1], sum, pk);
           tmem_st16(treg + pcol + 16, pk);
         }
         tmem_ld_wait();
         if (on0) {
-          fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk, sKeep);
+          fwd_chunk_exp(ra, m4 + 0, p.scale2, mx, bits[0], sum, pk);
           tmem_st16(treg + pcol + 0, pk);
         }
         gSum[half * 128 + row] = sum;
@@ -2309,7 +2299,7 @@ static int attn_fwd_launch(const mmfb_attn_args& a, cudaStream_t stream) {
     // one-CTA-per-tile kernel below for A/B runs
     const char* f_env = getenv("MMFB_ATTN_FWD");
     if (f_env == nullptr || f_env[0] != '1') {
-      const int smem_p = 2 * 6 * 16384 + (512 + 512 + 512) * 4 + 4096 + 256 + 1024;
+      const int smem_p = 2 * 6 * 16384 + (512 + 512 + 512) * 4 + 256 + 1024;
       static bool attr_p = false;
       if (!attr_p) {
         cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
