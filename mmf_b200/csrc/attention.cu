@@ -2258,15 +2258,19 @@ static int check_attn_common(const mmfb_attn_args& a, const char* who) {
 }
 
 // Work counters of the persistent attention kernels ([0..1] forward: next item / finished CTAs, [4..5] backward): device
-// memory owned by the library, zero between launches (the last CTA of a launch re-arms them).  One set per process: the
-// kernels of ONE stream are serialised; concurrent attention launches on different streams are not supported.
+// memory owned by the library, zero between launches (the last CTA of a launch re-arms them).  One set per device: the
+// kernels of ONE stream are serialised; concurrent attention launches on different streams of a device are not supported.
 static int* sched_counters() {
-  static int* buf = nullptr;
-  if (buf == nullptr) {
-    if (cudaMalloc(&buf, 8 * sizeof(int)) != cudaSuccess) { buf = nullptr; return nullptr; }
-    if (cudaMemset(buf, 0, 8 * sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+  static int* buf[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (buf[dev] == nullptr) {
+    int* b = nullptr;
+    if (cudaMalloc(&b, 8 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(b, 0, 8 * sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+    buf[dev] = b;
   }
-  return buf;
+  return buf[dev];
 }
 
 template <int D>
