@@ -60,22 +60,23 @@ def attn_fwd(env):
 
 
 work = [
-    lambda: F.gemm(x, w_qkv, epi=lib.EPI_BIAS, bias=b3),
-    lambda: F.gemm(x, w_o, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9),
-    lambda: F.gemm(x, w_1, epi=lib.EPI_BIAS_GELU, bias=b1),
-    lambda: F.gemm(x, w_2, b_mn=True, epi=lib.EPI_GELU_BWD, aux=xi),
-    lambda: F.gemm(xi, w_2, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9),
-    lambda: attn_fwd({}),
-    lambda: attn_fwd({"MMFB_ATTN_FWD": "1"}),
-    lambda: attn_bwd({"MMFB_ATTN_BWD": "8"}),
-    lambda: attn_bwd({"MMFB_ATTN_BWD": "16"}),
-    lambda: ln_bwd("pair"),
-    lambda: ln_bwd("lean"),
-    lambda: F.dropout_bits((B, heads, S), S, 0.1, 7, 0, dev),
+    ("gemm", lambda: F.gemm(x, w_qkv, epi=lib.EPI_BIAS, bias=b3)),
+    ("gemm", lambda: F.gemm(x, w_o, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9)),
+    ("gemm", lambda: F.gemm(x, w_1, epi=lib.EPI_BIAS_GELU, bias=b1)),
+    ("gemm", lambda: F.gemm(x, w_2, b_mn=True, epi=lib.EPI_GELU_BWD, aux=xi)),
+    ("gemm", lambda: F.gemm(xi, w_2, epi=lib.EPI_BIAS_DROP_RESID, bias=bh, aux=x, drop_mask=bits_h, drop_scale=1 / 0.9)),
+    ("attn", lambda: attn_fwd({})),                          # default: paired tiles, persistent
+    ("attn", lambda: attn_fwd({"MMFB_ATTN_FWD": "1"})),      # one CTA per tile
+    ("attn", lambda: attn_bwd({})),                          # default: persistent (+ the delta kernel)
+    ("attn", lambda: attn_bwd({"MMFB_ATTN_BWD": "16"})),     # one CTA per (batch, head)
+    ("ln", lambda: ln_bwd(None)),                            # default: streaming single pass
+    ("ln", lambda: ln_bwd("lean")),
+    ("rows", lambda: F.dropout_bits((B, heads, S), S, 0.1, 7, 0, dev)),
 ]
-if os.environ.get("PROF_ONLY"):          # e.g. PROF_ONLY=attn,ln : skip the GEMMs
+if os.environ.get("PROF_ONLY"):          # e.g. PROF_ONLY=attn,ln
     keep = os.environ["PROF_ONLY"].split(",")
-    work = [w for i, w in enumerate(work) if ("attn" in keep and 5 <= i <= 8) or ("ln" in keep and 9 <= i <= 10)]
+    work = [w for w in work if w[0] in keep]
+work = [w[1] for w in work]
 for fn in work:
     fn()
 torch.cuda.synchronize()
