@@ -2,7 +2,7 @@
 # new defaults (paired forward with bulk stores, persistent backward v2, streaming LayerNorm backward, bit-sliced keep-bits):
 # whole GPU suite, bench, isolated timings, host synchronisations / idle time of a step
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -rfE > gpurun_out/r2_gpu_tests_full12.log 2>&1; tail -6 gpurun_out/r2_gpu_tests_full12.log
 timeout 400 python bench.py --optimizer > gpurun_out/r2_bench_call12.json 2> gpurun_out/r2_bench_call12.err; python tools/show_bench.py gpurun_out/r2_bench_call12.json

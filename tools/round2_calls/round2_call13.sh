@@ -1,7 +1,7 @@
 #!/bin/bash
 # whole-step CUDA graph: parity test, then the small configurations eager vs graph
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_next_gpu.py tests/test_rowops_gpu.py -m gpu -q -x -rfE > gpurun_out/r2_graph_tests13.log 2>&1; tail -6 gpurun_out/r2_graph_tests13.log
 for wl in mmbt vilbert; do

@@ -1,7 +1,7 @@
 #!/bin/bash
 # blocked forward (two key blocks, single read of S), graph fixes
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_variants_gpu.py tests/test_attention_gpu.py -m gpu -q -x -rfE > gpurun_out/r2_attn_tests14.log 2>&1; tail -6 gpurun_out/r2_attn_tests14.log
 timeout 300 python -m pytest tests/test_encoder_gpu.py tests/test_depth_gpu.py tests/test_next_gpu.py -m gpu -q -x -rfE 2>&1 | tail -4

@@ -2,7 +2,7 @@
 # GPU call 2 of round 2: whole suite again after the fixes, isolated kernel timings for every staged variant, the launch list
 # of one step with the default kernels.
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -rfEP > gpurun_out/r2_gpu_tests_full2.log 2>&1; tail -15 gpurun_out/r2_gpu_tests_full2.log
 MMFB_STAGED_TESTS=1 timeout 200 python -m pytest tests/test_staged_gpu.py -m gpu -q -k "layernorm" 2>&1 | tail -4

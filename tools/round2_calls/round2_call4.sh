@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -rfEP > gpurun_out/r2_gpu_tests_full4.log 2>&1; tail -12 gpurun_out/r2_gpu_tests_full4.log
 MMFB_PDL=0 timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x 2>&1 | tail -3

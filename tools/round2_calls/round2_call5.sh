@@ -1,7 +1,7 @@
 #!/bin/bash
 # paired-tile attention forward + masked-chunk skipping in the backward: parity, isolated timings, step
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_variants_gpu.py tests/test_attention_gpu.py -m gpu -q -x -rfEP > gpurun_out/r2_attn_tests5.log 2>&1; tail -15 gpurun_out/r2_attn_tests5.log
 timeout 600 python -m pytest tests -m gpu -q -rfE > gpurun_out/r2_gpu_tests_full5.log 2>&1; tail -6 gpurun_out/r2_gpu_tests_full5.log

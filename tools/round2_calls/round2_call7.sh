@@ -1,7 +1,7 @@
 #!/bin/bash
 # attention forward v2 (loader warp, probing MMA issuer, pipelined TMEM loads): parity, isolated timing, ncu, step
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_variants_gpu.py tests/test_attention_gpu.py tests/test_encoder_gpu.py -m gpu -q -x -rfE > gpurun_out/r2_attn_tests7.log 2>&1; tail -5 gpurun_out/r2_attn_tests7.log
 timeout 300 python tools/kbench.py --only attn --json gpurun_out/r2_kbench_call7.json 2>&1 | tail -7

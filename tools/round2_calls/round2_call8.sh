@@ -1,7 +1,7 @@
 #!/bin/bash
 # attention forward v2 + persistent backward + streaming LayerNorm backward: parity, isolated timings, step A/B
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_variants_gpu.py -m gpu -q -rfE > gpurun_out/r2_variant_tests8.log 2>&1; tail -8 gpurun_out/r2_variant_tests8.log
 timeout 300 python -m pytest tests/test_attention_gpu.py tests/test_encoder_gpu.py tests/test_rowops_gpu.py -m gpu -q -x -rfE > gpurun_out/r2_attn_tests8.log 2>&1; tail -5 gpurun_out/r2_attn_tests8.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # end-of-round evidence on one GPU: full GPU suite, bench lines of every workload, launch list + ncu --set full of the top kernels
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -rfE > gpurun_out/r2_gpu_tests_final.log 2>&1; tail -5 gpurun_out/r2_gpu_tests_final.log
 timeout 400 python bench.py --optimizer > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; python tools/show_bench.py gpurun_out/r2_bench_final.json

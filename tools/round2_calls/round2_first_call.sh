@@ -5,7 +5,7 @@
 #     python tools/ab.py build x2 -DMMFB_F32X2=1        (here, before the call)
 #     tools/gpurun_retry.sh 1500 'bash tools/round2_first_call.sh > gpurun_out/round2_first_call.log 2>&1'
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 timeout 900 python -m pytest tests -m gpu -q -rfEP > gpurun_out/r2_gpu_tests_full.log 2>&1; tail -40 gpurun_out/r2_gpu_tests_full.log

@@ -2,7 +2,7 @@
 # multi-GPU (one box): gradient equality, then the bench in both gradient-exchange modes.   usage: round2_scale.sh N
 set -x
 N=${1:-2}
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 MMFB_DDP_MODE=end timeout 300 $TR --master-port 29511 tools/check_ddp.py > gpurun_out/r2_check_ddp_n${N}_end.log 2>&1; tail -3 gpurun_out/r2_check_ddp_n${N}_end.log

@@ -2,7 +2,7 @@
 # 8 GPUs of one box (charged 8x): gradient equality once, then the bench in the default exchange mode (+ the bf16 payload)
 set -x
 N=${1:-8}
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 MMFB_DDP_MODE=end timeout 150 $TR --master-port 29511 tools/check_ddp.py > gpurun_out/r2_check_ddp_n${N}_end.log 2>&1; tail -2 gpurun_out/r2_check_ddp_n${N}_end.log
