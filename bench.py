@@ -803,13 +803,21 @@ def main():
             raise SystemExit("--graph is a single-GPU mode")
         from mmf_b200.graphs import GraphedStep
         lc0 = lib.launch_count()
-        graphed = GraphedStep(model, lambda b: wl.loss(net, b, aux), dev_batch, warmup=3)
-        graph_launches = (lib.launch_count() - lc0) // 4        # 3 warm-up steps + the captured one: kernels per replay
-        config["kernels_per_graph"] = graph_launches
-        config["step_launch"] = "one CUDA graph per step (stream capture of the eager step; dropout masks advance through a device counter)"
+        try:
+            graphed = GraphedStep(model, lambda b: wl.loss(net, b, aux), dev_batch, warmup=3)
+        except Exception as e:      # the eager step is always available: say what happened and go on
+            graphed = None
+            args.graph = False
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+            config["step_launch"] = "eager (CUDA graph capture failed: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
+        if graphed is not None:
+            graph_launches = (lib.launch_count() - lc0) // 4        # 3 warm-up steps + the captured one: kernels per replay
+            config["kernels_per_graph"] = graph_launches
+            config["step_launch"] = "one CUDA graph per step (stream capture of the eager step; dropout masks advance through a device counter)"
 
-        def step(batch):        # noqa: F811  (same contract: forward + backward of `batch`, returns the loss)
-            return graphed(batch)
+            def step(batch):        # noqa: F811  (same contract: forward + backward of `batch`, returns the loss)
+                return graphed(batch)
 
     def barrier():
         if world > 1:
